@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: assembled DoFs/s of the Poisson CG3 1-form
+``assemble(action(a, u))`` on an N^3 extruded hexahedral mesh (BASELINE.json
+configs[1], N = 256), fp64.
+
+A "step" is one assembly: zero the output Dat (firedrake/assemble.py:1042-1047),
+run the global kernel (gather + element kernel + scatter-add), i.e. exactly the
+work ``OneFormAssembler.assemble`` does in steady state.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python bench.py --impl reference            # CPU restatement on the host cores
+
+Prints ONE JSON line (see the key list in DESIGN.md section "Measurement").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "assembled DoFs/sec (Poisson CG3, 256^3 hex, 1-form/action)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=256, help="cells per axis")
+    ap.add_argument("--degree", type=int, default=3)
+    ap.add_argument("--warp", type=float, default=0.05)
+    ap.add_argument("--permute", type=int, default=-1, help="seed for a random base-cell order (-1: off)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        # "under load" = upper half of the samples
+        sm_sorted = sorted(sm)
+        med = float(np.median(sm_sorted[len(sm_sorted) // 2:])) if sm else None
+        return {"sm_mhz": med, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------- workload
+def make_problem(args, nx, pinned):
+    from firedrake_b200 import op2
+    from firedrake_b200.utility_meshes import ExtrudedHexMesh
+    n, p = args.n, args.degree
+    mesh = ExtrudedHexMesh(nx, n, n, Lx=nx / n, warp=args.warp,
+                           permute_seed=None if args.permute < 0 else args.permute)
+    V = mesh.function_space(p)
+    cells = op2.ExtrudedSet(op2.Set(mesh.num_base_cells), mesh.layers)
+    nodes = op2.Set(V.node_count)
+    vnodes = op2.Set(mesh.coord_space.node_count)
+    m0 = op2.Map(cells, nodes, V.arity, V.cell_node_map, offset=V.offset)
+    m1 = op2.Map(cells, vnodes, 8, mesh.coord_map, offset=mesh.coord_offset)
+    x = op2.Dat(nodes, pinned=pinned)
+    rng = np.random.default_rng(1234)
+    xa = x.data_with_halos
+    chunk = 1 << 24
+    for i in range(0, V.node_count, chunk):
+        xa[i:i + chunk] = rng.standard_normal(min(chunk, V.node_count - i))
+    y = op2.Dat(nodes, pinned=pinned)
+    X = op2.Dat(op2.DataSet(vnodes, 3), mesh.coordinates)
+    return mesh, V, cells, m0, m1, x, y, X
+
+
+def algorithmic_bytes(V, mesh):
+    """read x + write y, coordinates, map."""
+    return 16 * V.node_count + 24 * mesh.coord_space.node_count + 4 * V.arity * mesh.num_base_cells
+
+
+def cpu_baseline(args, seconds):
+    """The oracle (CPU restatement of the PyOP2 wrapper + TSFC kernel), one
+    sequential worker per host core on its own ghosted slab -- the reference's
+    MPI model.  Bounded sample: each worker gets an
+    sx x n base-cell slab of the n^3 mesh with all n layers."""
+    from firedrake_b200.fiat_lite import interval_element
+    from firedrake_b200.utility_meshes import ExtrudedHexMesh
+    from oracle import oracle
+    p, n = args.degree, args.n
+    el = interval_element(p)
+    P = os.cpu_count() or 1
+    native = True
+    oracle.lib(native)
+
+    def slab(sx):
+        mesh = ExtrudedHexMesh(sx, n, n, Lx=sx / n, warp=args.warp)
+        V = mesh.function_space(p)
+        x = np.random.default_rng(5).standard_normal(V.node_count)
+        return mesh, V, x
+
+    # calibrate on one worker, one base row
+    mesh, V, x = slab(1)
+    y = np.zeros(V.node_count)
+    prob = dict(start=0, end=mesh.num_base_cells, layers=[0, mesh.layers], y=y,
+                coords=mesh.coordinates, x=x, map0=V.cell_node_map, off0=V.offset,
+                map1=mesh.coord_map, off1=mesh.coord_offset)
+    oracle.action_workers(el, [prob], native=native)
+    t0 = time.perf_counter()
+    oracle.action_workers(el, [prob], native=native)
+    t_row = time.perf_counter() - t0
+    reps = 3
+    sx = max(1, min(n // max(P, 1) if P <= n else 1, int(seconds / (reps + 1) / max(t_row, 1e-9))))
+    mesh, V, x = slab(sx)
+    probs = []
+    for w in range(P):
+        probs.append(dict(start=0, end=mesh.num_base_cells, layers=[0, mesh.layers],
+                          y=np.zeros(V.node_count), coords=mesh.coordinates.copy(), x=x.copy(),
+                          map0=V.cell_node_map.copy(), off0=V.offset, map1=mesh.coord_map.copy(),
+                          off1=mesh.coord_offset))
+    oracle.action_workers(el, probs, native=native)          # warm-up
+    ts = []
+    for _ in range(reps):
+        for pr in probs:
+            pr["y"][:] = 0.0
+        t0 = time.perf_counter()
+        oracle.action_workers(el, probs, native=native)
+        ts.append(time.perf_counter() - t0)
+    t = float(np.median(ts))
+    # owned dofs of a slab in the global mesh: sx*p columns wide (one face shared)
+    owned = (sx * p) * (n * p + 1) * (n * p + 1)
+    value = P * owned / t
+    return {"value": value, "unit": "DoFs/s", "cores": P, "kind": "port",
+            "sample": f"{P} workers x ({sx}x{n} base cells x {n} layers, CG{p}) slabs of the "
+                      f"{n}^3 mesh, median of {reps}, {os.path.basename(oracle.lib(native)._path)}",
+            "seconds_per_pass": t}
+
+
+def run_reference(args):
+    base = cpu_baseline(args, max(args.cpu_seconds, 5.0) if args.steps <= 1 else args.cpu_seconds)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": "DoFs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": None, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"Poisson CG{args.degree} 1-form (action) on {args.n}^3 extruded hexes, "
+                               f"warp={args.warp}", "note": "CPU restatement of Firedrake/PyOP2/TSFC "
+                               "(oracle/), not Firedrake itself: omits Python glue and PETSc"},
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": "DoFs/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        if rank == 0:
+            run_reference(args)
+        return
+    if world != args.gpus:
+        if args.gpus != 1 or world != 1:
+            raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun")
+    if world > 1:
+        raise SystemExit("multi-GPU bench: see firedrake_b200.halo (not wired into this revision)")
+
+    import ctypes as C
+    from firedrake_b200 import _lib, op2
+    L = _lib.init(int(os.environ.get("LOCAL_RANK", "0")))
+    n, p = args.n, args.degree
+    t_setup = time.perf_counter()
+    mesh, V, cells, m0, m1, x, y, X = make_problem(args, n, pinned=not args.no_e2e)
+    ndof = V.node_count
+    kern = op2.Kernel("helmholtz", degree=p, alpha=1.0, beta=0.0)
+    gk = op2.GlobalKernel(kern, [m0, m1], extruded=True)
+    loop = op2.Parloop(gk, cells, [y(op2.INC, m0), X(op2.READ, m1), x(op2.READ, m0)], location="device")
+    t_setup = time.perf_counter() - t_setup
+
+    def step():
+        y.zero()
+        loop()
+
+    # make everything resident (inputs in HBM before the timed region)
+    x.device_ptr; y.device_ptr; X.device_ptr; m0.device_ptr; m1.device_ptr
+    for _ in range(max(args.warmup, 3)):
+        step()
+    _lib.check(L.fdb_synchronize())
+
+    tm = C.c_void_p(); tk = C.c_void_p()
+    _lib.check(L.fdb_timer_create(C.byref(tm)))
+    _lib.check(L.fdb_timer_create(C.byref(tk)))
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    sampler.start()
+    time.sleep(0.3)
+    launches0 = L.fdb_launch_count()
+    ms = C.c_float()
+    _lib.check(L.fdb_synchronize())
+    _lib.check(L.fdb_timer_start(tm))
+    for _ in range(args.steps):
+        step()
+    _lib.check(L.fdb_timer_stop(tm, C.byref(ms)))
+    total_ms = ms.value
+    launches = L.fdb_launch_count() - launches0
+    # kernel-only duration (CUDA events around the global kernel alone, same stream)
+    kms = []
+    for _ in range(args.steps):
+        y.zero()
+        _lib.check(L.fdb_timer_start(tk))
+        loop()
+        _lib.check(L.fdb_timer_stop(tk, C.byref(ms)))
+        kms.append(ms.value)
+    clocks = sampler.stop()
+    ms_per_step = total_ms / args.steps
+    value = ndof / (ms_per_step * 1e-3)
+    kernel_ms = float(np.mean(kms))
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_gbs = peaks.get("hbm_gbs", 6650.0)
+    abytes = algorithmic_bytes(V, mesh)
+    achieved = abytes / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                "frac": achieved / peak_gbs, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
+                "kernel": "helmholtz_action_kernel<4,false,true>", "kernel_ms": kernel_ms,
+                "algorithmic_bytes": abytes,
+                "note": "kernel is fp64-pipe-bound, not HBM-bound (DESIGN.md): fp64 fraction reported in fp64",
+                "fp64": {"flops_per_cell": kern.num_flops, "achieved_tflops":
+                         kern.num_flops * mesh.num_cells / (kernel_ms * 1e-3) / 1e12,
+                         "peak_tflops_nominal": 37.2}}
+    roofline["fp64"]["frac"] = roofline["fp64"]["achieved_tflops"] / 37.2
+
+    e2e = None
+    if not args.no_e2e:
+        hloop = op2.Parloop(gk, cells, [y(op2.INC, m0), X(op2.READ, m1), x(op2.READ, m0)], location="host")
+        nst = max(1, min(args.steps, 5))
+        def hstep():
+            x.data_with_halos[0] += 0.0      # host write: bumps dat_version -> H2D of x
+            y.zero()                         # host memset, as assemble() does
+            hloop()                          # H2D x, device memset y, kernel, D2H y
+            return float(y._data[0])
+        hstep()
+        t0 = time.perf_counter()
+        for _ in range(nst):
+            hstep()
+        t = (time.perf_counter() - t0) / nst
+        e2e = {"value": ndof / t, "unit": "DoFs/s", "h2d_bytes_per_step": x.nbytes,
+               "d2h_bytes_per_step": y.nbytes, "ms_per_step": t * 1e3, "steps": nst,
+               "path": "op2.Parloop(location='host') -> fdb_kernel_call(FDB_LOC_HOST): pinned host "
+                       "Dats, includes the host-side zero of y"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "DoFs/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"Poisson CG{p} 1-form assemble(action(a,u)) on {n}^3 extruded hexes "
+                               f"({mesh.num_cells} cells, {ndof} DoFs), Q1 geometry warp={args.warp}, "
+                               f"base-cell order={'lexicographic' if args.permute < 0 else 'random seed %d' % args.permute}",
+                   "quadrature": f"Gauss-Legendre {p + 1}^3 (dx(degree={2 * p}))",
+                   "l2": "inputs (x,y: %.1f GB) exceed the 126 MB L2; no flush needed" % (2 * 8 * ndof / 1e9),
+                   "setup_s": t_setup},
+        "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline,
+    }
+    if e2e:
+        line["e2e"] = e2e
+    if not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline(args, args.cpu_seconds)
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,73 @@
+// Shared internals of libfdb200 (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/fdb200.h"
+
+namespace fdb {
+
+struct Context {
+    bool ready = false;
+    int device = -1;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    uint64_t launches = 0;
+    void *flush_buf = nullptr;
+    size_t flush_bytes = 0;
+    double *reduce_scratch = nullptr;   // device scratch for reductions
+    double *reduce_host = nullptr;      // pinned
+};
+
+Context &ctx();
+void set_error(const char *fmt, ...);
+int require_init();
+
+#define FDB_CUDA(call)                                                              \
+    do {                                                                            \
+        cudaError_t e_ = (call);                                                    \
+        if (e_ != cudaSuccess) {                                                    \
+            fdb::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call,            \
+                           cudaGetErrorString(e_));                                 \
+            return 1;                                                               \
+        }                                                                           \
+    } while (0)
+
+#define FDB_LAUNCH_CHECK()                                                          \
+    do {                                                                            \
+        fdb::ctx().launches++;                                                      \
+        cudaError_t e_ = cudaGetLastError();                                        \
+        if (e_ != cudaSuccess) {                                                    \
+            fdb::set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__,        \
+                           cudaGetErrorString(e_));                                 \
+            return 1;                                                               \
+        }                                                                           \
+    } while (0)
+
+}  // namespace fdb
+
+// kernel object behind fdb_kernel_t
+struct fdb_kernel_s {
+    fdb_kernel_desc desc;
+    int n1d;                 // p + 1
+    int arity;               // dofs per cell of the argument map
+    fdb_int *d_off0 = nullptr;   // device copies of the layer offsets
+    fdb_int *d_off1 = nullptr;
+    fdb_int h_off0[512];
+    fdb_int h_off1[8];
+    double Dt[FDB_MAX_1D * FDB_MAX_1D];   // collocated derivative D * B^{-1}
+    // colouring plan for FDB_SCATTER_COLOURED, built lazily per map
+    const void *colour_map_key = nullptr;
+    fdb_int *d_colour_cols = nullptr;     // columns sorted by colour
+    int ncolours = 0;
+    fdb_int colour_start[65];
+};
+
+extern "C" int fdb_mirror_set_version(const void *host, uint64_t version);
+
+// launchers implemented in the kernel translation units
+int fdb_launch_helmholtz_action(fdb_kernel_s *k, fdb_int start, fdb_int end, int nlay,
+                                const fdb_int *subset, double *y, const double *coords,
+                                const double *x, const fdb_int *map0, const fdb_int *map1);

@@ -1,0 +1,276 @@
+// "Compile" and call of a global kernel: the replacement for
+// pyop2.global_kernel.compile_global_kernel + GlobalKernel.__call__
+// (reference pyop2/global_kernel.py:327-335, 426-456).  Nothing is JIT-compiled:
+// creation validates the descriptor against the set of hand-written sm_100a
+// kernels and precomputes the tables they need.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+using namespace fdb;
+
+namespace {
+
+// Dt = D * B^{-1}  (collocated derivative on the quadrature points).
+// Solves X B = D by Gaussian elimination with partial pivoting on B^T X^T = D^T.
+int collocated_derivative(int n, const double *B, const double *D, double *Dt)
+{
+    double A[FDB_MAX_1D][FDB_MAX_1D], R[FDB_MAX_1D][FDB_MAX_1D];
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++) {
+            A[i][j] = B[j * n + i];   // B^T
+            R[i][j] = D[j * n + i];   // D^T
+        }
+    for (int c = 0; c < n; c++) {
+        int piv = c;
+        for (int r = c + 1; r < n; r++)
+            if (fabs(A[r][c]) > fabs(A[piv][c])) piv = r;
+        if (fabs(A[piv][c]) < 1e-14) return 1;
+        if (piv != c)
+            for (int j = 0; j < n; j++) {
+                std::swap(A[piv][j], A[c][j]);
+                std::swap(R[piv][j], R[c][j]);
+            }
+        for (int r = 0; r < n; r++) {
+            if (r == c) continue;
+            double f = A[r][c] / A[c][c];
+            for (int j = 0; j < n; j++) {
+                A[r][j] -= f * A[c][j];
+                R[r][j] -= f * R[c][j];
+            }
+        }
+    }
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++) Dt[j * n + i] = R[i][j] / A[i][i];   // X = (X^T)^T
+    return 0;
+}
+
+// Greedy colouring of columns (base cells) so that no two columns of one
+// colour share a dof column: the deterministic fallback of the north_star
+// ("warp-aggregated atomic kernel with a colouring fallback").  Host side,
+// once per map.
+int build_colouring(fdb_kernel_s *k, const fdb_int *h_map, fdb_int ncols)
+{
+    const int arity = k->arity;
+    fdb_int maxnode = 0;
+    for (long long i = 0; i < (long long)ncols * arity; i++) maxnode = std::max(maxnode, h_map[i]);
+    // node -> bitmask of colours already used by a column touching it
+    std::vector<uint64_t> used((size_t)maxnode + 1, 0);
+    std::vector<int> colour(ncols);
+    int ncolours = 0;
+    for (fdb_int c = 0; c < ncols; c++) {
+        uint64_t m = 0;
+        for (int i = 0; i < arity; i++) m |= used[h_map[(size_t)c * arity + i]];
+        int col = 0;
+        while (col < 64 && (m >> col) & 1) col++;
+        if (col >= 64) {
+            set_error("colouring needs more than 64 colours");
+            return 1;
+        }
+        colour[c] = col;
+        ncolours = std::max(ncolours, col + 1);
+        for (int i = 0; i < arity; i++) used[h_map[(size_t)c * arity + i]] |= (uint64_t)1 << col;
+    }
+    std::vector<fdb_int> sorted(ncols);
+    int pos = 0;
+    for (int col = 0; col < ncolours; col++) {
+        k->colour_start[col] = pos;
+        for (fdb_int c = 0; c < ncols; c++)
+            if (colour[c] == col) sorted[pos++] = c;
+    }
+    k->colour_start[ncolours] = pos;
+    k->ncolours = ncolours;
+    if (k->d_colour_cols) cudaFree(k->d_colour_cols);
+    FDB_CUDA(cudaMalloc(&k->d_colour_cols, sizeof(fdb_int) * std::max(ncols, 1)));
+    FDB_CUDA(cudaMemcpyAsync(k->d_colour_cols, sorted.data(), sizeof(fdb_int) * ncols,
+                             cudaMemcpyHostToDevice, ctx().stream));
+    FDB_CUDA(cudaStreamSynchronize(ctx().stream));
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fdb_kernel_create(const fdb_kernel_desc *d, fdb_kernel_t *out)
+{
+    if (require_init()) return 1;
+    if (!d || !out) {
+        set_error("fdb_kernel_create: NULL argument");
+        return 1;
+    }
+    if (d->form != FDB_FORM_HELMHOLTZ) {
+        set_error("fdb_kernel_create: form %d is not in the supported set", d->form);
+        return 1;
+    }
+    if (d->cell != FDB_CELL_HEX_EXTRUDED && d->cell != FDB_CELL_HEX) {
+        set_error("fdb_kernel_create: cell type %d not supported for form %d", d->cell, d->form);
+        return 1;
+    }
+    if (d->integral != FDB_INTEGRAL_CELL) {
+        set_error("fdb_kernel_create: Helmholtz-family forms only have cell integrals");
+        return 1;
+    }
+    if (d->degree < 1 || d->degree > 5) {
+        set_error("fdb_kernel_create: degree %d outside 1..5", d->degree);
+        return 1;
+    }
+    if (d->nq != d->degree + 1) {
+        set_error("fdb_kernel_create: hex kernels need nq == degree+1 Gauss points per axis "
+                  "(got nq=%d for degree %d); pin the rule with dx(degree=2*p)",
+                  d->nq, d->degree);
+        return 1;
+    }
+    if (d->rank != 1 && d->rank != 2) {
+        set_error("fdb_kernel_create: rank must be 1 or 2");
+        return 1;
+    }
+    if (d->cdim < 1 || d->cdim > 3) {
+        set_error("fdb_kernel_create: cdim %d outside 1..3", d->cdim);
+        return 1;
+    }
+    if (d->cell == FDB_CELL_HEX_EXTRUDED && (!d->offset0 || !d->offset1)) {
+        set_error("fdb_kernel_create: extruded cells need offset0/offset1");
+        return 1;
+    }
+    fdb_kernel_s *k = new fdb_kernel_s;
+    k->desc = *d;
+    k->n1d = d->degree + 1;
+    k->arity = k->n1d * k->n1d * k->n1d;
+    memset(k->h_off0, 0, sizeof(k->h_off0));
+    memset(k->h_off1, 0, sizeof(k->h_off1));
+    if (d->offset0) memcpy(k->h_off0, d->offset0, sizeof(fdb_int) * k->arity);
+    if (d->offset1) memcpy(k->h_off1, d->offset1, sizeof(fdb_int) * 8);
+    k->desc.offset0 = k->h_off0;
+    k->desc.offset1 = k->h_off1;
+    if (collocated_derivative(k->n1d, d->B, d->D, k->Dt)) {
+        set_error("fdb_kernel_create: basis table B is singular");
+        delete k;
+        return 1;
+    }
+    FDB_CUDA(cudaMalloc(&k->d_off0, sizeof(fdb_int) * k->arity));
+    FDB_CUDA(cudaMalloc(&k->d_off1, sizeof(fdb_int) * 8));
+    FDB_CUDA(cudaMemcpyAsync(k->d_off0, k->h_off0, sizeof(fdb_int) * k->arity,
+                             cudaMemcpyHostToDevice, ctx().stream));
+    FDB_CUDA(cudaMemcpyAsync(k->d_off1, k->h_off1, sizeof(fdb_int) * 8, cudaMemcpyHostToDevice,
+                             ctx().stream));
+    FDB_CUDA(cudaStreamSynchronize(ctx().stream));
+    *out = k;
+    return 0;
+}
+
+int fdb_kernel_destroy(fdb_kernel_t k)
+{
+    if (!k) return 0;
+    if (ctx().ready) {
+        cudaStreamSynchronize(ctx().stream);
+        cudaFree(k->d_off0);
+        cudaFree(k->d_off1);
+        if (k->d_colour_cols) cudaFree(k->d_colour_cols);
+    }
+    delete k;
+    return 0;
+}
+
+int fdb_kernel_call(fdb_kernel_t k, const fdb_call_args *a)
+{
+    if (require_init()) return 1;
+    if (!k || !a) {
+        set_error("fdb_kernel_call: NULL argument");
+        return 1;
+    }
+    const bool extruded = k->desc.cell == FDB_CELL_HEX_EXTRUDED;
+    if (extruded && !a->layers) {
+        set_error("fdb_kernel_call: extruded kernel called without layers");
+        return 1;
+    }
+    if (a->end < a->start) {
+        set_error("fdb_kernel_call: end < start");
+        return 1;
+    }
+    const int nlay = extruded ? (a->layers[1] - a->layers[0] - 1) : 1;
+    if (extruded && a->layers[0] != 0) {
+        set_error("fdb_kernel_call: nonzero bottom layer not supported");
+        return 1;
+    }
+    if ((long long)(a->end - a->start) * nlay >= (1ll << 31) - 64) {
+        set_error("fdb_kernel_call: iteration set too large for IntType");
+        return 1;
+    }
+    if (k->desc.rank != 1) {
+        set_error("fdb_kernel_call: rank-2 kernels are called through fdb_mat_assemble");
+        return 1;
+    }
+    // 1-form: args = [y (INC), coords (READ), x (READ)], maps = [V map, coord map]
+    if (a->nargs != 3 || a->nmaps != 2) {
+        set_error("fdb_kernel_call: 1-form expects 3 args (y, coords, x) and 2 maps, got %d/%d",
+                  a->nargs, a->nmaps);
+        return 1;
+    }
+    void *dargs[3];
+    const fdb_int *dmaps[2];
+    const fdb_int *dsubset = a->subset;
+    if (a->location == FDB_LOC_HOST) {
+        if (!a->arg_bytes || !a->map_bytes) {
+            set_error("fdb_kernel_call: host mode needs arg_bytes and map_bytes");
+            return 1;
+        }
+        for (int i = 0; i < 3; i++) {
+            uint64_t ver = a->arg_versions ? a->arg_versions[i] : 0;
+            // without versions every call re-uploads (drop-in default: the
+            // reference hands over live NumPy buffers)
+            if (!a->arg_versions) fdb_mirror_drop(a->args[i]);
+            const bool zero_out = (i == 0 && a->output_is_zero);
+            if (fdb_mirror_acquire(a->args[i], a->arg_bytes[i], ver, zero_out ? 0 : 1, &dargs[i]))
+                return 1;
+            if (zero_out)
+                FDB_CUDA(cudaMemsetAsync(dargs[i], 0, a->arg_bytes[i], ctx().stream));
+        }
+        for (int i = 0; i < 2; i++) {
+            void *p;
+            if (fdb_mirror_acquire(a->maps[i], a->map_bytes[i], 0, 1, &p)) return 1;
+            dmaps[i] = (const fdb_int *)p;
+        }
+        if (a->subset) {
+            void *p;
+            if (fdb_mirror_acquire(a->subset, sizeof(fdb_int) * (size_t)a->end, 0, 1, &p)) return 1;
+            dsubset = (const fdb_int *)p;
+        }
+    } else {
+        for (int i = 0; i < 3; i++) dargs[i] = a->args[i];
+        for (int i = 0; i < 2; i++) dmaps[i] = a->maps[i];
+    }
+    if (k->desc.scatter == FDB_SCATTER_COLOURED && k->colour_map_key != (const void *)a->maps[0]) {
+        // colouring covers columns [0, end): copy the map to the host if needed
+        std::vector<fdb_int> hmap;
+        const fdb_int *src = a->maps[0];
+        if (a->location == FDB_LOC_DEVICE) {
+            hmap.resize((size_t)a->end * k->arity);
+            FDB_CUDA(cudaMemcpy(hmap.data(), a->maps[0], sizeof(fdb_int) * hmap.size(),
+                                cudaMemcpyDeviceToHost));
+            src = hmap.data();
+        }
+        if (build_colouring(k, src, a->end)) return 1;
+        k->colour_map_key = (const void *)a->maps[0];
+    }
+    if (k->desc.scatter == FDB_SCATTER_COLOURED && a->start != 0) {
+        set_error("fdb_kernel_call: coloured scatter needs start == 0");
+        return 1;
+    }
+    int rc = fdb_launch_helmholtz_action(k, a->start, a->end, nlay, dsubset, (double *)dargs[0],
+                                         (const double *)dargs[1], (const double *)dargs[2],
+                                         dmaps[0], dmaps[1]);
+    if (rc) return rc;
+    if (a->location == FDB_LOC_HOST && a->writeback) {
+        // the output mirror now differs from the host copy: write it back
+        if (fdb_mirror_writeback(a->args[0])) return 1;
+        if (a->arg_versions) fdb_mirror_set_version(a->args[0], a->arg_versions[0] + 1);
+    }
+    return 0;
+}
+
+}  // extern "C"

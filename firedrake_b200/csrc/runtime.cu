@@ -1,0 +1,332 @@
+// Runtime plumbing of libfdb200: context, device memory, the host-pointer
+// mirror cache, timers.  No numerics here.
+#include <stdarg.h>
+#include <string.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+
+namespace fdb {
+
+static Context g_ctx;
+static thread_local char g_err[1024] = "";
+
+Context &ctx() { return g_ctx; }
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int require_init()
+{
+    if (!g_ctx.ready) {
+        set_error("fdb_init() has not been called");
+        return 1;
+    }
+    return 0;
+}
+
+struct Mirror {
+    void *dev = nullptr;
+    size_t nbytes = 0;
+    uint64_t version = 0;
+    bool valid = false;
+};
+static std::unordered_map<const void *, Mirror> g_mirrors;
+
+}  // namespace fdb
+
+using namespace fdb;
+
+extern "C" {
+
+const char *fdb_last_error(void) { return g_err; }
+
+int fdb_init(int device)
+{
+    Context &c = ctx();
+    if (c.ready) {
+        if (c.device != device) {
+            set_error("fdb_init: already initialised on device %d", c.device);
+            return 1;
+        }
+        return 0;
+    }
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        set_error("fdb_init: no CUDA device available (%s)", cudaGetErrorString(e));
+        return 1;
+    }
+    if (device < 0 || device >= n) {
+        set_error("fdb_init: device %d out of range (have %d)", device, n);
+        return 1;
+    }
+    FDB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    FDB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        set_error("fdb_init: device %s is sm_%d%d; this library is built for sm_100a only",
+                  prop.name, prop.major, prop.minor);
+        return 1;
+    }
+    c.device = device;
+    c.sm_count = prop.multiProcessorCount;
+    FDB_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    FDB_CUDA(cudaMalloc(&c.reduce_scratch, 4096 * sizeof(double)));
+    FDB_CUDA(cudaHostAlloc((void **)&c.reduce_host, 64 * sizeof(double), cudaHostAllocDefault));
+    c.ready = true;
+    return 0;
+}
+
+int fdb_finalize(void)
+{
+    Context &c = ctx();
+    if (!c.ready) return 0;
+    cudaStreamSynchronize(c.stream);
+    for (auto &kv : g_mirrors) cudaFree(kv.second.dev);
+    g_mirrors.clear();
+    if (c.flush_buf) cudaFree(c.flush_buf);
+    cudaFree(c.reduce_scratch);
+    cudaFreeHost(c.reduce_host);
+    cudaStreamDestroy(c.stream);
+    c = Context();
+    return 0;
+}
+
+int fdb_synchronize(void)
+{
+    if (require_init()) return 1;
+    FDB_CUDA(cudaStreamSynchronize(ctx().stream));
+    return 0;
+}
+
+int fdb_device_info(char *name, int name_len, int *sm_count, size_t *total_mem)
+{
+    if (require_init()) return 1;
+    cudaDeviceProp prop;
+    FDB_CUDA(cudaGetDeviceProperties(&prop, ctx().device));
+    if (name && name_len > 0) {
+        strncpy(name, prop.name, name_len - 1);
+        name[name_len - 1] = 0;
+    }
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (total_mem) *total_mem = prop.totalGlobalMem;
+    return 0;
+}
+
+uint64_t fdb_launch_count(void) { return ctx().launches; }
+
+void *fdb_malloc(size_t nbytes)
+{
+    if (require_init()) return nullptr;
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, nbytes ? nbytes : 1);
+    if (e != cudaSuccess) {
+        set_error("fdb_malloc(%zu): %s", nbytes, cudaGetErrorString(e));
+        return nullptr;
+    }
+    return p;
+}
+
+int fdb_free(void *dptr)
+{
+    if (require_init()) return 1;
+    FDB_CUDA(cudaStreamSynchronize(ctx().stream));
+    FDB_CUDA(cudaFree(dptr));
+    return 0;
+}
+
+int fdb_memset(void *dptr, int value, size_t nbytes)
+{
+    if (require_init()) return 1;
+    FDB_CUDA(cudaMemsetAsync(dptr, value, nbytes, ctx().stream));
+    return 0;
+}
+
+int fdb_memcpy_h2d(void *dst, const void *src, size_t nbytes)
+{
+    if (require_init()) return 1;
+    FDB_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyHostToDevice, ctx().stream));
+    FDB_CUDA(cudaStreamSynchronize(ctx().stream));
+    return 0;
+}
+
+int fdb_memcpy_d2h(void *dst, const void *src, size_t nbytes)
+{
+    if (require_init()) return 1;
+    FDB_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToHost, ctx().stream));
+    FDB_CUDA(cudaStreamSynchronize(ctx().stream));
+    return 0;
+}
+
+int fdb_memcpy_d2d(void *dst, const void *src, size_t nbytes)
+{
+    if (require_init()) return 1;
+    FDB_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToDevice, ctx().stream));
+    return 0;
+}
+
+void *fdb_host_alloc(size_t nbytes)
+{
+    if (require_init()) return nullptr;
+    void *p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, nbytes ? nbytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        set_error("fdb_host_alloc(%zu): %s", nbytes, cudaGetErrorString(e));
+        return nullptr;
+    }
+    return p;
+}
+
+int fdb_host_free(void *hptr)
+{
+    if (require_init()) return 1;
+    FDB_CUDA(cudaFreeHost(hptr));
+    return 0;
+}
+
+int fdb_host_register(void *hptr, size_t nbytes)
+{
+    if (require_init()) return 1;
+    FDB_CUDA(cudaHostRegister(hptr, nbytes, cudaHostRegisterDefault));
+    return 0;
+}
+
+int fdb_host_unregister(void *hptr)
+{
+    if (require_init()) return 1;
+    FDB_CUDA(cudaHostUnregister(hptr));
+    return 0;
+}
+
+/* ---------------------------------------------------------------- mirror cache */
+
+int fdb_mirror_acquire(const void *host, size_t nbytes, uint64_t version, int upload,
+                       void **dev_out)
+{
+    if (require_init()) return 1;
+    if (!host) {
+        set_error("fdb_mirror_acquire: NULL host pointer");
+        return 1;
+    }
+    Mirror &m = g_mirrors[host];
+    if (m.dev && m.nbytes != nbytes) {
+        FDB_CUDA(cudaStreamSynchronize(ctx().stream));
+        FDB_CUDA(cudaFree(m.dev));
+        m = Mirror();
+    }
+    if (!m.dev) {
+        FDB_CUDA(cudaMalloc(&m.dev, nbytes ? nbytes : 1));
+        m.nbytes = nbytes;
+        m.valid = false;
+    }
+    if (upload && (!m.valid || m.version != version)) {
+        FDB_CUDA(cudaMemcpyAsync(m.dev, host, nbytes, cudaMemcpyHostToDevice, ctx().stream));
+        m.valid = true;
+        m.version = version;
+    }
+    *dev_out = m.dev;
+    return 0;
+}
+
+int fdb_mirror_writeback(void *host)
+{
+    if (require_init()) return 1;
+    auto it = g_mirrors.find(host);
+    if (it == g_mirrors.end()) {
+        set_error("fdb_mirror_writeback: %p has no mirror", host);
+        return 1;
+    }
+    FDB_CUDA(cudaMemcpyAsync(host, it->second.dev, it->second.nbytes, cudaMemcpyDeviceToHost,
+                             ctx().stream));
+    FDB_CUDA(cudaStreamSynchronize(ctx().stream));
+    return 0;
+}
+
+int fdb_mirror_set_version(const void *host, uint64_t version)
+{
+    auto it = g_mirrors.find(host);
+    if (it == g_mirrors.end()) return 1;
+    it->second.version = version;
+    it->second.valid = true;
+    return 0;
+}
+
+int fdb_mirror_drop(const void *host)
+{
+    if (require_init()) return 1;
+    auto it = g_mirrors.find(host);
+    if (it == g_mirrors.end()) return 0;
+    FDB_CUDA(cudaStreamSynchronize(ctx().stream));
+    FDB_CUDA(cudaFree(it->second.dev));
+    g_mirrors.erase(it);
+    return 0;
+}
+
+int fdb_mirror_drop_all(void)
+{
+    if (require_init()) return 1;
+    FDB_CUDA(cudaStreamSynchronize(ctx().stream));
+    for (auto &kv : g_mirrors) cudaFree(kv.second.dev);
+    g_mirrors.clear();
+    return 0;
+}
+
+/* ---------------------------------------------------------------------- timers */
+
+struct fdb_timer_s {
+    cudaEvent_t a, b;
+};
+
+int fdb_timer_create(fdb_timer_t *out)
+{
+    if (require_init()) return 1;
+    fdb_timer_s *t = new fdb_timer_s;
+    FDB_CUDA(cudaEventCreate(&t->a));
+    FDB_CUDA(cudaEventCreate(&t->b));
+    *out = t;
+    return 0;
+}
+
+int fdb_timer_start(fdb_timer_t t)
+{
+    FDB_CUDA(cudaEventRecord(t->a, ctx().stream));
+    return 0;
+}
+
+int fdb_timer_stop(fdb_timer_t t, float *ms_out)
+{
+    FDB_CUDA(cudaEventRecord(t->b, ctx().stream));
+    FDB_CUDA(cudaEventSynchronize(t->b));
+    FDB_CUDA(cudaEventElapsedTime(ms_out, t->a, t->b));
+    return 0;
+}
+
+int fdb_timer_destroy(fdb_timer_t t)
+{
+    cudaEventDestroy(t->a);
+    cudaEventDestroy(t->b);
+    delete t;
+    return 0;
+}
+
+int fdb_flush_l2(void)
+{
+    if (require_init()) return 1;
+    Context &c = ctx();
+    if (!c.flush_buf) {
+        c.flush_bytes = (size_t)256 << 20;   // 2x the 126 MB L2
+        FDB_CUDA(cudaMalloc(&c.flush_buf, c.flush_bytes));
+    }
+    FDB_CUDA(cudaMemsetAsync(c.flush_buf, 0, c.flush_bytes, c.stream));
+    return 0;
+}
+
+}  // extern "C"

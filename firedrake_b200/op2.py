@@ -1,0 +1,619 @@
+"""A minimal mirror of the PyOP2 object model, backed by ``libfdb200.so``.
+
+Same names, argument meaning and call protocol as the reference for the part
+of PyOP2 that sits on the assembly hot path:
+
+=================  ===========================================================
+here               reference
+=================  ===========================================================
+``Set``            pyop2/types/set.py:18-125  (core | owned | ghost sizes)
+``ExtrudedSet``    pyop2/types/set.py:306-394 (constant layers)
+``Subset``         pyop2/types/set.py:397-
+``DataSet``        pyop2/types/dataset.py
+``Map``            pyop2/types/map.py:17-165  (values + per-dof layer offset)
+``Dat``            pyop2/types/dat.py:27-712  (NumPy buffer + dat_version)
+``Global``         pyop2/types/glob.py
+``Kernel``         pyop2/local_kernel.py:33-43 -- here a *form descriptor*
+                   instead of C/loopy source: the element kernels are
+                   hand-written CUDA, selected by descriptor
+``GlobalKernel``   pyop2/global_kernel.py:255-335
+``Parloop``        pyop2/parloop.py:167-260
+``par_loop``       pyop2/parloop.py:705-762 (legacy ``dat(access, map)`` args)
+=================  ===========================================================
+
+Two data-placement modes, chosen per parloop:
+
+* ``"host"`` (drop-in): the arglist carries HOST pointers exactly as
+  pyop2/parloop.py:203-212 builds it; the engine mirrors them on the device
+  keyed on ``dat_version`` and writes the output back.
+* ``"device"``: Dats own a device buffer (``Dat.device_ptr``) that stays
+  resident across calls; the host copy is refreshed lazily by ``Dat.data_ro``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+import itertools
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+from ._lib import EngineError
+
+IntType = np.int32
+ScalarType = np.float64
+
+
+class Access(enum.IntEnum):
+    READ = 1
+    WRITE = 2
+    RW = 3
+    INC = 4
+    MIN = 5
+    MAX = 6
+
+
+READ, WRITE, RW, INC, MIN, MAX = (Access.READ, Access.WRITE, Access.RW, Access.INC,
+                                  Access.MIN, Access.MAX)
+
+ALL = "ALL"
+ON_BOTTOM = "ON_BOTTOM"
+ON_TOP = "ON_TOP"
+
+
+class MapValueError(ValueError):
+    pass
+
+
+class DataSetTypeError(TypeError):
+    pass
+
+
+# ---------------------------------------------------------------------- sets
+class Set:
+    """Iteration/data set with ``[core | owned | ghost]`` partitions."""
+    _extruded = False
+
+    def __init__(self, size, name=None):
+        if isinstance(size, (int, np.integer)):
+            size = (size, size, size)
+        if len(size) == 2:
+            size = (size[0], size[0], size[1])
+        self.core_size, self.size, self.total_size = (int(s) for s in size)
+        if not (0 <= self.core_size <= self.size <= self.total_size):
+            raise ValueError("need core <= owned <= total sizes")
+        self.name = name or "set"
+
+    @property
+    def sizes(self):
+        return (self.core_size, self.size, self.total_size)
+
+    # pyop2/types/set.py:119-125
+    @property
+    def core_part(self):
+        return (0, self.core_size)
+
+    @property
+    def owned_part(self):
+        return (self.core_size, self.size)
+
+    def __call__(self, *indices):
+        return Subset(self, np.asarray(indices, dtype=IntType).ravel())
+
+
+class ExtrudedSet(Set):
+    """A set of columns with a constant number of node layers
+    (pyop2/types/set.py:306-394): ``layers`` counts NODE layers, cells per
+    column = layers - 1; ``layers_array`` is the int[1][2] the wrapper gets."""
+    _extruded = True
+    constant_layers = True
+
+    def __init__(self, parent: Set, layers: int):
+        super().__init__(parent.sizes, name=parent.name + "_extruded")
+        if layers < 2:
+            raise ValueError("an extruded set needs at least 2 node layers")
+        self.parent = parent
+        self.layers = int(layers)
+        self.layers_array = np.array([[0, self.layers]], dtype=IntType)
+
+
+class Subset(Set):
+    _extruded = False
+
+    def __init__(self, superset: Set, indices):
+        idx = np.unique(np.asarray(indices, dtype=IntType))
+        if len(idx) and (idx[0] < 0 or idx[-1] >= superset.total_size):
+            raise ValueError("subset indices out of range")
+        self.superset = superset
+        self.indices = np.ascontiguousarray(idx)
+        core = int(np.searchsorted(idx, superset.core_size))
+        owned = int(np.searchsorted(idx, superset.size))
+        Set.__init__(self, (core, owned, len(idx)), name=superset.name + "_subset")
+        self._extruded = superset._extruded
+        if self._extruded:
+            self.layers = superset.layers
+            self.layers_array = superset.layers_array
+
+
+class DataSet:
+    def __init__(self, iter_set: Set, dim=1, name=None):
+        self.set = iter_set
+        self.dim = (dim,) if isinstance(dim, (int, np.integer)) else tuple(dim)
+        self.cdim = int(np.prod(self.dim))
+        self.name = name or "dset"
+
+
+def _as_dataset(s):
+    return s if isinstance(s, DataSet) else DataSet(s, 1)
+
+
+# ---------------------------------------------------------------------- maps
+class Map:
+    """``values`` has shape (iterset.total_size, arity); for extruded iteration
+    sets each row addresses the BOTTOM cell of a column and ``offset[i]`` is
+    added per layer (pyop2/types/map.py:36-56)."""
+    _ids = itertools.count()
+
+    def __init__(self, iterset, toset, arity, values, name=None, offset=None):
+        self.iterset, self.toset, self.arity = iterset, toset, int(arity)
+        v = np.ascontiguousarray(np.asarray(values, dtype=IntType).reshape(-1, self.arity))
+        if v.shape[0] != iterset.total_size:
+            raise MapValueError(f"map has {v.shape[0]} rows, iterset has {iterset.total_size}")
+        if v.size and (v.min() < 0 or v.max() >= toset.total_size):
+            raise MapValueError("map values out of range of the target set")
+        self.values_with_halo = v
+        self.offset = None if offset is None else np.ascontiguousarray(offset, dtype=IntType)
+        if self.offset is not None and self.offset.shape != (self.arity,):
+            raise MapValueError("offset must have one entry per arity index")
+        self.name = name or f"map_{next(Map._ids)}"
+        self._dev = None
+
+    @property
+    def values(self):
+        return self.values_with_halo[:self.iterset.size]
+
+    @property
+    def device_ptr(self):
+        if self._dev is None:
+            self._dev = DeviceArray.from_host(self.values_with_halo)
+        return self._dev.ptr
+
+
+# -------------------------------------------------------------- device memory
+class DeviceArray:
+    """RAII wrapper around fdb_malloc/fdb_free."""
+
+    def __init__(self, nbytes):
+        L = _lib.lib()
+        self.nbytes = int(nbytes)
+        self.ptr = L.fdb_malloc(self.nbytes)
+        if not self.ptr:
+            raise EngineError(L.fdb_last_error().decode())
+
+    @classmethod
+    def from_host(cls, arr):
+        arr = np.ascontiguousarray(arr)
+        d = cls(arr.nbytes)
+        _lib.check(_lib.lib().fdb_memcpy_h2d(d.ptr, arr.ctypes.data, arr.nbytes), "h2d")
+        return d
+
+    def to_host(self, out):
+        _lib.check(_lib.lib().fdb_memcpy_d2h(out.ctypes.data, self.ptr, out.nbytes), "d2h")
+        return out
+
+    def __del__(self):
+        try:
+            if self.ptr and _lib._initialised is not None:
+                _lib._lib.fdb_free(self.ptr)
+        except Exception:
+            pass
+        self.ptr = None
+
+
+class PinnedArray:
+    """NumPy view of page-locked host memory (fdb_host_alloc)."""
+
+    def __init__(self, shape, dtype):
+        L = _lib.lib()
+        self.dtype = np.dtype(dtype)
+        self.shape = tuple(shape)
+        n = int(np.prod(self.shape)) * self.dtype.itemsize
+        self.ptr = L.fdb_host_alloc(max(n, 1))
+        if not self.ptr:
+            raise EngineError(L.fdb_last_error().decode())
+        buf = (C.c_char * max(n, 1)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def __del__(self):
+        try:
+            if self.ptr and _lib._initialised is not None:
+                _lib._lib.fdb_host_free(self.ptr)
+        except Exception:
+            pass
+        self.ptr = None
+
+
+# ----------------------------------------------------------------------- Dats
+class Dat:
+    """Node data: C-contiguous ``(total_size, *dim)``, owned rows first, ghosts
+    at the tail, vector spaces AoS (pyop2/types/dat.py:72-96).
+
+    ``dat_version`` follows pyop2/types/data_carrier.py:79-97: it is bumped by
+    every write access to ``data`` and by every parloop that writes the Dat.
+    """
+    _ids = itertools.count()
+
+    def __init__(self, dataset, data=None, dtype=ScalarType, name=None, pinned=False):
+        self.dataset = _as_dataset(dataset)
+        shape = (self.dataset.set.total_size,) + (self.dataset.dim if self.dataset.cdim > 1 else ())
+        self._pinned = None
+        if pinned:
+            self._pinned = PinnedArray(shape, dtype)
+            self._data = self._pinned.array
+            self._data[...] = 0 if data is None else np.asarray(data, dtype=dtype).reshape(shape)
+        elif data is None:
+            self._data = np.zeros(shape, dtype=dtype)
+        else:
+            self._data = np.ascontiguousarray(np.asarray(data, dtype=dtype).reshape(shape))
+        self.dtype = np.dtype(dtype)
+        self.name = name or f"dat_{next(Dat._ids)}"
+        self.dat_version = 0
+        self._dev = None            # DeviceArray, device-resident mode
+        self._host_valid = True
+        self._dev_valid = False
+        self._is_zero = data is None
+        self.halo_valid = True
+
+    # -- shape helpers
+    @property
+    def cdim(self):
+        return self.dataset.cdim
+
+    @property
+    def nbytes(self):
+        return self._data.nbytes
+
+    # -- host access (pyop2/types/dat.py data / data_ro / data_with_halos)
+    def _sync_host(self):
+        if not self._host_valid:
+            self._dev.to_host(self._data)
+            self._host_valid = True
+
+    @property
+    def data_ro(self):
+        self._sync_host()
+        v = self._data[:self.dataset.set.size].view()
+        v.setflags(write=False)
+        return v
+
+    @property
+    def data_ro_with_halos(self):
+        self._sync_host()
+        v = self._data.view()
+        v.setflags(write=False)
+        return v
+
+    @property
+    def data(self):
+        self._sync_host()
+        self.increment_dat_version()
+        self._dev_valid = False
+        self._is_zero = False
+        return self._data[:self.dataset.set.size]
+
+    @property
+    def data_with_halos(self):
+        self._sync_host()
+        self.increment_dat_version()
+        self._dev_valid = False
+        self._is_zero = False
+        return self._data
+
+    def increment_dat_version(self):
+        self.dat_version += 1
+
+    # -- device residency
+    @property
+    def device_ptr(self):
+        """Device buffer holding the current values (uploads if stale)."""
+        if self._dev is None:
+            self._dev = DeviceArray(self._data.nbytes)
+        if not self._dev_valid:
+            if self._is_zero:
+                _lib.check(_lib.lib().fdb_memset(self._dev.ptr, 0, self._data.nbytes), "memset")
+            else:
+                _lib.check(_lib.lib().fdb_memcpy_h2d(self._dev.ptr, self._data.ctypes.data,
+                                                     self._data.nbytes), "h2d")
+            self._dev_valid = True
+        return self._dev.ptr
+
+    def _device_written(self):
+        self._host_valid = False
+        self._dev_valid = True
+        self._is_zero = False
+        self.increment_dat_version()
+
+    # -- whole-Dat operations (pyop2/types/dat.py:297-311, 354-540)
+    def zero(self, subset=None):
+        if subset is not None:
+            if self._dev_valid and not self._host_valid:
+                nodes = DeviceArray.from_host(subset.indices)
+                _lib.check(_lib.lib().fdb_dat_zero_nodes(self._dev.ptr, self.cdim, nodes.ptr,
+                                                         len(subset.indices)), "zero_nodes")
+                _lib.check(_lib.lib().fdb_synchronize())
+                self.increment_dat_version()
+            else:
+                self.data_with_halos[subset.indices] = 0
+            return
+        if self._dev is not None and self._dev_valid and not self._host_valid:
+            _lib.check(_lib.lib().fdb_memset(self._dev.ptr, 0, self._data.nbytes), "memset")
+            self.increment_dat_version()
+        else:
+            self._data[...] = 0
+            self._host_valid = True
+            self._dev_valid = False
+            self.increment_dat_version()
+        self._is_zero = True
+
+    def _vec_op(self, other, fn, *scalars):
+        L = _lib.lib()
+        n = self._data.size
+        _lib.check(fn(n, *scalars, other.device_ptr, self.device_ptr))
+        self._device_written()
+
+    def axpy(self, alpha, other):
+        """self += alpha * other"""
+        self._vec_op(other, _lib.lib().fdb_vec_axpy, float(alpha))
+
+    def inner(self, other):
+        out = C.c_double()
+        _lib.check(_lib.lib().fdb_vec_dot(self._data.size, self.device_ptr, other.device_ptr,
+                                          C.byref(out)), "dot")
+        return out.value
+
+    def norm(self):
+        return float(np.sqrt(self.inner(self)))
+
+    def __call__(self, access, path=None):
+        """Legacy parloop argument ``dat(op2.INC, map)`` (pyop2/parloop.py:709-743)."""
+        return LegacyArg(self, access, path)
+
+
+class Global:
+    def __init__(self, dim, data=None, dtype=ScalarType, name=None, comm=None):
+        self.dim = (dim,) if isinstance(dim, (int, np.integer)) else tuple(dim)
+        self._data = (np.zeros(self.dim, dtype=dtype) if data is None
+                      else np.asarray(data, dtype=dtype).reshape(self.dim).copy())
+        self.name = name or "global"
+        self.dat_version = 0
+
+    @property
+    def data(self):
+        self.dat_version += 1
+        return self._data
+
+    @property
+    def data_ro(self):
+        return self._data
+
+    def __call__(self, access, path=None):
+        return LegacyArg(self, access, None)
+
+
+@dataclass
+class LegacyArg:
+    data: object
+    access: Access
+    map: object = None
+
+
+# ------------------------------------------------------------------- kernels
+@dataclass(frozen=True)
+class Kernel:
+    """The local kernel.  In the reference this wraps TSFC-generated loopy or a
+    C string (pyop2/local_kernel.py:33-43, 186-207); here it names one of the
+    hand-written sm_100a element kernels through a form descriptor.
+
+    ``form``: "helmholtz" family = ``alpha*inner(grad u, grad v)*dx +
+    beta*inner(u, v)*dx``.  ``rank`` 1 means the 1-form ``action(a, w)``
+    (arguments: output Dat INC, coordinates READ, coefficient READ), the kernel
+    TSFC names ``form0_cell_integral``.
+    """
+    form: str = "helmholtz"
+    degree: int = 1
+    alpha: float = 1.0
+    beta: float = 0.0
+    rank: int = 1
+    cdim: int = 1
+    name: str = "form0_cell_integral"
+    accesses: tuple = (INC, READ, READ)
+    # tabulation: a fiat_lite.Interval1D, or None for the default GLL/Gauss pair
+    element: object = field(default=None, compare=False, hash=False)
+
+    @property
+    def num_flops(self):
+        n = self.degree + 1
+        return 2 * 6 * n ** 4 * 2 + 130 * n ** 3
+
+
+_FORMS = {"helmholtz": _lib.FORM_HELMHOLTZ}
+
+
+class GlobalKernel:
+    """pyop2/global_kernel.py:255-335: the compile-time description of a
+    parloop.  ``__call__`` is the Python -> native boundary."""
+    _cache = {}
+
+    def __init__(self, local_kernel: Kernel, arguments, *, extruded=False,
+                 constant_layers=True, subset=False, scatter="atomic"):
+        self.local_kernel = local_kernel
+        self.arguments = tuple(arguments)      # (Map, Map): argument map, coordinate map
+        self.extruded = extruded
+        self.constant_layers = constant_layers
+        self.subset = subset
+        self.scatter = scatter
+        self._handle = None
+        if extruded and not constant_layers:
+            raise NotImplementedError("variable layers are deprecated in the reference "
+                                      "(firedrake/mesh.py:3540-3546) and not supported")
+
+    @property
+    def name(self):
+        return "wrap_" + self.local_kernel.name          # global_kernel.py:344-346
+
+    def compile(self):
+        if self._handle is not None:
+            return self._handle
+        from .fiat_lite import interval_element
+        lk = self.local_kernel
+        el = lk.element or interval_element(lk.degree)
+        n = lk.degree + 1
+        if el.ndof != n:
+            raise ValueError("element degree does not match the kernel")
+        d = _lib.KernelDesc()
+        d.form = _FORMS[lk.form]
+        d.rank = lk.rank
+        d.cell = _lib.CELL_HEX_EXTRUDED if self.extruded else _lib.CELL_HEX
+        d.integral = _lib.INTEGRAL_CELL
+        d.degree = lk.degree
+        d.nq = el.nq
+        d.cdim = lk.cdim
+        d.scatter = {"atomic": _lib.SCATTER_ATOMIC, "coloured": _lib.SCATTER_COLOURED}[self.scatter]
+        d.alpha, d.beta = lk.alpha, lk.beta
+        for q in range(el.nq):
+            d.wq[q] = el.wq[q]
+            d.xq[q] = el.xq[q]
+            for a in range(n):
+                d.B[q * n + a] = el.B[q, a]
+                d.D[q * n + a] = el.D[q, a]
+        m0, m1 = self.arguments
+        keep = []
+        if self.extruded:
+            if m0.offset is None or m1.offset is None:
+                raise MapValueError("extruded parloop needs maps with offsets")
+            o0 = np.ascontiguousarray(m0.offset, dtype=IntType)
+            o1 = np.ascontiguousarray(m1.offset, dtype=IntType)
+            keep = [o0, o1]
+            d.offset0 = o0.ctypes.data_as(C.POINTER(C.c_int32))
+            d.offset1 = o1.ctypes.data_as(C.POINTER(C.c_int32))
+        h = C.c_void_p()
+        _lib.check(_lib.lib().fdb_kernel_create(C.byref(d), C.byref(h)), "fdb_kernel_create")
+        del keep
+        self._handle = h
+        return h
+
+    def __call__(self, start, end, layers, subset_indices, args, arg_bytes, arg_versions,
+                 maps, map_bytes, location, writeback, output_is_zero):
+        h = self.compile()
+        ca = _lib.CallArgs()
+        ca.start, ca.end = int(start), int(end)
+        if layers is not None:
+            ca.layers = layers.ctypes.data_as(C.POINTER(C.c_int32))
+        ca.subset = subset_indices
+        ca.nargs = len(args)
+        ca.args = (C.c_void_p * len(args))(*args)
+        if arg_bytes is not None:
+            ca.arg_bytes = (C.c_size_t * len(args))(*arg_bytes)
+            ca.arg_versions = (C.c_uint64 * len(args))(*arg_versions)
+        ca.nmaps = len(maps)
+        ca.maps = (C.c_void_p * len(maps))(*maps)
+        if map_bytes is not None:
+            ca.map_bytes = (C.c_size_t * len(maps))(*map_bytes)
+        ca.location = location
+        ca.writeback = int(writeback)
+        ca.output_is_zero = int(output_is_zero)
+        _lib.check(_lib.lib().fdb_kernel_call(h, C.byref(ca)), self.name)
+
+    def __del__(self):
+        try:
+            if self._handle is not None and _lib._initialised is not None:
+                _lib._lib.fdb_kernel_destroy(self._handle)
+        except Exception:
+            pass
+
+
+class Parloop:
+    """pyop2/parloop.py:167-260.  ``args`` are ``LegacyArg``s in TSFC argument
+    order (output, coordinates, coefficient).  ``__call__`` follows the
+    reference protocol: compute core, (halo exchanges are driven by
+    firedrake_b200.halo when a halo is attached), compute owned, bump the
+    version of written Dats."""
+
+    def __init__(self, global_knl: GlobalKernel, iterset: Set, args, location="device"):
+        self.global_kernel = global_knl
+        self.iterset = iterset
+        self.args = list(args)
+        self.location = location
+        self._check()
+
+    def _check(self):
+        lk = self.global_kernel.local_kernel
+        if len(self.args) != len(lk.accesses):
+            raise ValueError(f"kernel takes {len(lk.accesses)} arguments, got {len(self.args)}")
+        for a, acc in zip(self.args, lk.accesses):
+            if a.access != acc:
+                raise ValueError(f"argument {a.data.name}: access {a.access.name} != kernel's {acc.name}")
+            if a.map is not None:
+                base = self.iterset.superset if isinstance(self.iterset, Subset) else self.iterset
+                if a.map.iterset is not base:
+                    raise MapValueError(f"map {a.map.name} is not defined on the iteration set")
+                if a.map.toset is not a.data.dataset.set:
+                    raise MapValueError(f"map {a.map.name} does not target {a.data.name}'s set")
+
+    # the two compute phases of pyop2/parloop.py:250-253
+    def _compute(self, part):
+        start, end = part
+        if end <= start:
+            return
+        gk = self.global_kernel
+        it = self.iterset
+        layers = it.layers_array.ravel() if it._extruded else None
+        out = self.args[0].data
+        maps = []
+        for a in self.args:
+            if a.map is not None and a.map not in maps:
+                maps.append(a.map)       # distinct maps, first-use order
+        if self.location == "device":
+            subset = None
+            if isinstance(it, Subset):
+                if not hasattr(it, "_dev_idx"):
+                    it._dev_idx = DeviceArray.from_host(it.indices)
+                subset = it._dev_idx.ptr
+            ptrs = [a.data.device_ptr for a in self.args]
+            gk(start, end, layers, subset, ptrs, None, None, [m.device_ptr for m in maps], None,
+               _lib.LOC_DEVICE, False, False)
+            out._device_written()
+        else:
+            subset = it.indices.ctypes.data if isinstance(it, Subset) else None
+            for a in self.args:
+                a.data._sync_host()
+            ptrs = [a.data._data.ctypes.data for a in self.args]
+            nbytes = [a.data._data.nbytes for a in self.args]
+            vers = [a.data.dat_version for a in self.args]
+            gk(start, end, layers, subset, ptrs, nbytes, vers,
+               [m.values_with_halo.ctypes.data for m in maps],
+               [m.values_with_halo.nbytes for m in maps], _lib.LOC_HOST, True, out._is_zero)
+            out.increment_dat_version()      # pyop2/parloop.py:262-272
+            out._is_zero = False
+            out._dev_valid = False
+
+    def __call__(self):
+        self._compute(self.iterset.core_part)
+        self._compute(self.iterset.owned_part)
+
+    compute = __call__
+
+
+def par_loop(kernel: Kernel, iterset: Set, *args, location="device", scatter="atomic"):
+    """``op2.par_loop(kernel, iterset, dat(op2.INC, map), ...)``
+    (pyop2/parloop.py:705-762)."""
+    maps = []
+    for a in args:
+        if a.map is not None and a.map not in maps:
+            maps.append(a.map)
+    base = iterset.superset if isinstance(iterset, Subset) else iterset
+    gk = GlobalKernel(kernel, maps, extruded=base._extruded, subset=isinstance(iterset, Subset),
+                      scatter=scatter)
+    Parloop(gk, iterset, args, location=location)()
+    return gk

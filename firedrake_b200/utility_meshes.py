@@ -1,0 +1,338 @@
+"""Synthetic meshes that produce *Firedrake-shaped* arrays (host side, NumPy only).
+
+Mesh generation itself is out of scope for the engine (SURVEY.md section 2.1
+row 14): in a real deployment these arrays come from Firedrake's DMPlex layer
+(``mesh.coordinates.dat``, ``V.cell_node_map().values_with_halo``,
+``V.cell_node_map().offset``).  This module builds the same data layout for the
+benchmark and test workloads of SURVEY.md section 8(d), so that the launcher is
+exercised with exactly the shapes it would receive behind ``assemble()``:
+
+* extruded meshes store the cell->node map for the BOTTOM cell of each column
+  only, plus a per-dof layer ``offset`` (reference
+  pyop2/codegen/builder.py:80-128, firedrake/extrusion_utils.py:342-366);
+* dofs are numbered contiguously up each column, per base entity, interleaved
+  per layer as [dofs on the level | dofs in the layer interior] (reference
+  firedrake/extrusion_utils.py:236-252, firedrake/mesh.py:1932-1951);
+* the local dof index of a tensor-product element is
+  ``(ax * n + ay) * n + az`` with ax, ay, az the 1-D *entity ordered* dof numbers
+  (0 = left vertex, 1 = right vertex, 2.. = interior);
+* vector spaces are AoS (node major, component fastest).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .fiat_lite import gll_points
+
+IntType = np.int32
+ScalarType = np.float64
+
+__all__ = ["ExtrudedHexMesh", "ExtrudedFunctionSpace", "UnitSquareTriMesh",
+           "QuadMesh"]
+
+
+def _first_touch_rank(keys_per_cell: np.ndarray, nent: int) -> np.ndarray:
+    """Number entities in the order a cell-by-cell closure walk first meets
+    them (the locality DMPlex reordering gives the reference's numbering)."""
+    flat = keys_per_cell.ravel()
+    uniq, first = np.unique(flat, return_index=True)
+    assert len(uniq) == nent
+    order = np.argsort(first, kind="stable")
+    rank = np.empty(nent, dtype=np.int64)
+    rank[uniq[order]] = np.arange(nent)
+    return rank
+
+
+class ExtrudedHexMesh:
+    """nx x ny quadrilateral base mesh on [0,Lx]x[0,Ly] extruded into nz layers.
+
+    Parameters
+    ----------
+    warp : amplitude of the smooth non-affine warp of SURVEY.md section 8(d):
+        ``x += warp * sin(2 pi x) sin(2 pi y) sin(2 pi z)`` applied to every
+        coordinate component, so the Jacobian varies inside each cell.
+    permute_seed : if not None, base cells are visited in a seeded random order
+        (the "unstructured element->dof map" stress case).
+    """
+
+    def __init__(self, nx, ny, nz, Lx=1.0, Ly=1.0, Lz=1.0, warp=0.0,
+                 permute_seed=None):
+        self.nx, self.ny, self.nz = int(nx), int(ny), int(nz)
+        self.Lx, self.Ly, self.Lz = float(Lx), float(Ly), float(Lz)
+        self.warp = float(warp)
+        nx, ny = self.nx, self.ny
+        ncell = nx * ny
+        ix, iy = np.divmod(np.arange(ncell, dtype=np.int64), ny)
+        if permute_seed is not None:
+            perm = np.random.default_rng(permute_seed).permutation(ncell)
+            ix, iy = ix[perm], iy[perm]
+        self.cell_ix, self.cell_iy = ix, iy
+        self.num_base_cells = ncell
+        self.layers = self.nz + 1          # node layers, as in ExtrudedSet
+        # structured base entity ids
+        NV = (nx + 1) * (ny + 1)
+        NEy = (nx + 1) * ny                # edges running along y (point x interval)
+        NEx = nx * (ny + 1)                # edges running along x (interval x point)
+        self._nent = (NV, NEy, NEx, ncell)
+        self._ent_base = np.cumsum([0, NV, NEy, NEx])
+        clo = np.empty((ncell, 9), dtype=np.int64)
+        k = 0
+        for ax in (0, 1):
+            for ay in (0, 1):
+                clo[:, k] = self._vertex(ix + ax, iy + ay); k += 1
+        for ax in (0, 1):
+            clo[:, k] = self._yedge(ix + ax, iy); k += 1
+        for ay in (0, 1):
+            clo[:, k] = self._xedge(ix, iy + ay); k += 1
+        clo[:, k] = self._face(ix, iy)
+        self.closure = clo
+        self.num_entities = NV + NEy + NEx + ncell
+        self._rank = _first_touch_rank(clo, self.num_entities)
+        self._fs_cache = {}
+        # coordinates: VectorFunctionSpace(Q1 x P1, dim=3)
+        V1 = self.function_space(1)
+        self.coord_space = V1
+        self.coord_map = V1.cell_node_map
+        self.coord_offset = V1.offset
+        self.coordinates = self._vertex_coordinates(V1)
+
+    # -- structured entity ids -------------------------------------------
+    def _vertex(self, i, j):
+        return i * (self.ny + 1) + j
+
+    def _yedge(self, i, j):
+        return self._ent_base[1] + i * self.ny + j
+
+    def _xedge(self, i, j):
+        return self._ent_base[2] + i * (self.ny + 1) + j
+
+    def _face(self, i, j):
+        return self._ent_base[3] + i * self.ny + j
+
+    @property
+    def num_cells(self):
+        return self.num_base_cells * self.nz
+
+    def function_space(self, degree: int) -> "ExtrudedFunctionSpace":
+        if degree not in self._fs_cache:
+            self._fs_cache[degree] = ExtrudedFunctionSpace(self, degree)
+        return self._fs_cache[degree]
+
+    def _apply_warp(self, X):
+        if self.warp == 0.0:
+            return X
+        s = self.warp * (np.sin(2 * np.pi * X[:, 0] / self.Lx)
+                         * np.sin(2 * np.pi * X[:, 1] / self.Ly)
+                         * np.sin(2 * np.pi * X[:, 2] / self.Lz))
+        return X + s[:, None]
+
+    def _vertex_coordinates(self, V1):
+        nx, ny, nz = self.nx, self.ny, self.nz
+        NV = self._nent[0]
+        vid = np.arange(NV, dtype=np.int64)
+        vi, vj = np.divmod(vid, ny + 1)
+        start = V1._ent_start[vid]                       # column starts, stride 1
+        X = np.empty((V1.node_count, 3), dtype=ScalarType)
+        lay = np.arange(nz + 1, dtype=np.int64)
+        idx = (start[:, None] + lay[None, :]).ravel()
+        X[idx, 0] = np.repeat(vi * (self.Lx / nx), nz + 1)
+        X[idx, 1] = np.repeat(vj * (self.Ly / ny), nz + 1)
+        X[idx, 2] = np.tile(lay * (self.Lz / nz), NV)
+        return self._apply_warp(X)
+
+
+class ExtrudedFunctionSpace:
+    """Scalar Q_p (x) P_p space on an :class:`ExtrudedHexMesh` (GLL nodes)."""
+
+    def __init__(self, mesh: ExtrudedHexMesh, degree: int):
+        self.mesh = mesh
+        self.degree = p = int(degree)
+        n = p + 1
+        self.n = n
+        self.arity = n ** 3
+        nz = mesh.nz
+        NV, NEy, NEx, NF = mesh._nent
+        nb_kind = np.array([1, p - 1, p - 1, (p - 1) ** 2], dtype=np.int64)
+        nb = np.repeat(nb_kind, [NV, NEy, NEx, NF])      # base dofs per entity
+        colsize = nb * (p * nz + 1)
+        # columns laid out in first-touch order
+        order = np.argsort(mesh._rank, kind="stable")
+        start_sorted = np.concatenate([[0], np.cumsum(colsize[order])[:-1]])
+        ent_start = np.empty(mesh.num_entities, dtype=np.int64)
+        ent_start[order] = start_sorted
+        self._ent_start = ent_start
+        self._ent_nb = nb
+        self.node_count = int(colsize.sum())
+        if self.node_count >= 2 ** 31:
+            raise ValueError("node count exceeds int32 IntType")
+        ix, iy = mesh.cell_ix, mesh.cell_iy
+        cmap = np.empty((mesh.num_base_cells, self.arity), dtype=IntType)
+        off = np.empty(self.arity, dtype=IntType)
+        for ax in range(n):
+            for ay in range(n):
+                if ax < 2 and ay < 2:
+                    ent = mesh._vertex(ix + ax, iy + ay); nbe = 1; eb = 0
+                elif ax < 2:
+                    ent = mesh._yedge(ix + ax, iy); nbe = p - 1; eb = ay - 2
+                elif ay < 2:
+                    ent = mesh._xedge(ix, iy + ay); nbe = p - 1; eb = ax - 2
+                else:
+                    ent = mesh._face(ix, iy); nbe = (p - 1) ** 2
+                    eb = (ax - 2) * (p - 1) + (ay - 2)
+                st = ent_start[ent]
+                for v in range(n):
+                    if v == 0:
+                        pos = eb
+                    elif v == 1:
+                        pos = nbe * p + eb
+                    else:
+                        pos = nbe + eb * (p - 1) + (v - 2)
+                    loc = (ax * n + ay) * n + v
+                    cmap[:, loc] = st + pos
+                    off[loc] = nbe * p
+        self.cell_node_map = cmap
+        self.offset = off
+
+    # ------------------------------------------------------------------
+    def full_cell_node_list(self):
+        """(num_cells, arity) map with the layer loop expanded: row
+        ``c*nz + l`` is column c, layer l (small meshes / tests)."""
+        nz = self.mesh.nz
+        lay = np.arange(nz, dtype=np.int64)
+        full = (self.cell_node_map[:, None, :].astype(np.int64)
+                + lay[None, :, None] * self.offset[None, None, :])
+        return full.reshape(-1, self.arity).astype(IntType)
+
+    def dof_coordinates(self):
+        """Physical positions of all nodes, (node_count, 3).  The geometry is
+        Q1: a node's position is the trilinear image of its reference position.
+        Small meshes only (allocates arity x num_cells)."""
+        mesh = self.mesh
+        n = self.n
+        ref1d = gll_points(self.degree)
+        a2pos = np.array([0, n - 1] + list(range(1, n - 1)))
+        xi = ref1d[a2pos]                                  # by dof number
+        full = self.full_cell_node_list().astype(np.int64)
+        cfull = mesh.coord_space.full_cell_node_list().astype(np.int64)
+        XV = mesh.coordinates[cfull]                       # (ncell, 8, 3)
+        out = np.empty((self.node_count, 3), dtype=ScalarType)
+        for ax in range(n):
+            for ay in range(n):
+                for az in range(n):
+                    pt = np.zeros((full.shape[0], 3))
+                    for bx in (0, 1):
+                        for by in (0, 1):
+                            for bz in (0, 1):
+                                wgt = ((xi[ax] if bx else 1 - xi[ax])
+                                       * (xi[ay] if by else 1 - xi[ay])
+                                       * (xi[az] if bz else 1 - xi[az]))
+                                pt += wgt * XV[:, (bx * 2 + by) * 2 + bz, :]
+                    out[full[:, (ax * n + ay) * n + az]] = pt
+        return out
+
+    def boundary_nodes(self, sub_domain):
+        """Node indices of a Dirichlet boundary (reference
+        firedrake/functionspacedata.py:272-300 for "bottom"/"top"; integer ids
+        1..4 = x==0, x==Lx, y==0, y==Ly as in firedrake/utility_meshes.py)."""
+        mesh = self.mesh
+        p, nz = self.degree, mesh.nz
+        st, nb = self._ent_start, self._ent_nb
+        if sub_domain in ("bottom", "top"):
+            base = st if sub_domain == "bottom" else st + nb * p * nz
+            reps = np.repeat(base, nb)
+            within = np.concatenate([np.arange(k) for k in nb]) if len(nb) else np.array([], dtype=np.int64)
+            return np.sort(reps + within).astype(IntType)
+        nx, ny = mesh.nx, mesh.ny
+        if sub_domain == 1:
+            ents = [mesh._vertex(0, np.arange(ny + 1)), mesh._yedge(0, np.arange(ny))]
+        elif sub_domain == 2:
+            ents = [mesh._vertex(nx, np.arange(ny + 1)), mesh._yedge(nx, np.arange(ny))]
+        elif sub_domain == 3:
+            ents = [mesh._vertex(np.arange(nx + 1), 0), mesh._xedge(np.arange(nx), 0)]
+        elif sub_domain == 4:
+            ents = [mesh._vertex(np.arange(nx + 1), ny), mesh._xedge(np.arange(nx), ny)]
+        else:
+            raise ValueError(f"unknown sub_domain {sub_domain!r}")
+        ents = np.concatenate(ents)
+        size = nb[ents] * (p * nz + 1)
+        idx = np.concatenate([np.arange(s, s + k) for s, k in zip(st[ents], size)])
+        return np.sort(idx).astype(IntType)
+
+
+class UnitSquareTriMesh:
+    """``UnitSquareMesh(nx, ny)``: each cell of the nx x ny grid split with the
+    "left" diagonal (reference firedrake/utility_meshes.py:599-600, 802-812).
+    P1 only: the cell->node map is the vertex list, (ncell, 3)."""
+
+    def __init__(self, nx, ny, L=1.0):
+        self.nx, self.ny = nx, ny
+        xs = np.linspace(0.0, L, nx + 1)
+        ys = np.linspace(0.0, L, ny + 1)
+        X, Y = np.meshgrid(xs, ys, indexing="ij")
+        self.coordinates = np.stack([X.ravel(), Y.ravel()], axis=1).astype(ScalarType)
+        i, j = np.meshgrid(np.arange(nx), np.arange(ny), indexing="ij")
+        i, j = i.ravel(), j.ravel()
+        v = lambda a, b: a * (ny + 1) + b
+        v00, v10, v01, v11 = v(i, j), v(i + 1, j), v(i, j + 1), v(i + 1, j + 1)
+        # "left" diagonal joins (i, j+1) and (i+1, j)
+        t0 = np.stack([v00, v10, v01], axis=1)
+        t1 = np.stack([v10, v11, v01], axis=1)
+        self.cell_node_map = np.concatenate([t0, t1], axis=0).astype(IntType)
+        self.num_cells = self.cell_node_map.shape[0]
+        self.node_count = self.coordinates.shape[0]
+
+    def boundary_nodes(self):
+        X = self.coordinates
+        on = (np.isclose(X[:, 0], 0) | np.isclose(X[:, 0], X[:, 0].max())
+              | np.isclose(X[:, 1], 0) | np.isclose(X[:, 1], X[:, 1].max()))
+        return np.nonzero(on)[0].astype(IntType)
+
+
+class QuadMesh:
+    """nx x ny quadrilateral mesh (non-extruded) with the facet data the DG
+    advection demo needs (reference demos/DG_advection/DG_advection.py.rst):
+
+    * ``coord_map`` (ncell, 4): Q1 vertices, local index ax*2+ay
+    * DQ1 space: 4 dofs per cell, numbered cell*4 + (ax*2+ay)
+    * interior facets: ``int_facet_cells`` (nf, 2) = [cell+, cell-],
+      ``int_facet_local`` (nf, 2) local facet numbers; exterior likewise.
+      Local facet numbering of the reference quad: 0: x==0, 1: x==1, 2: y==0,
+      3: y==1 (edges of FInAT dimension (0,1) first; reference
+      firedrake/cython/dmcommon.pyx:1496-1499).
+    """
+
+    def __init__(self, nx, ny, Lx=1.0, Ly=1.0):
+        self.nx, self.ny = nx, ny
+        xs = np.linspace(0.0, Lx, nx + 1)
+        ys = np.linspace(0.0, Ly, ny + 1)
+        X, Y = np.meshgrid(xs, ys, indexing="ij")
+        self.coordinates = np.stack([X.ravel(), Y.ravel()], axis=1).astype(ScalarType)
+        i, j = np.meshgrid(np.arange(nx), np.arange(ny), indexing="ij")
+        i, j = i.ravel(), j.ravel()
+        v = lambda a, b: a * (ny + 1) + b
+        self.coord_map = np.stack([v(i, j), v(i, j + 1), v(i + 1, j), v(i + 1, j + 1)],
+                                  axis=1).astype(IntType)
+        ncell = nx * ny
+        self.num_cells = ncell
+        self.node_count = self.coordinates.shape[0]
+        self.dg1_map = (np.arange(ncell, dtype=np.int64)[:, None] * 4
+                        + np.arange(4)[None, :]).astype(IntType)
+        cid = lambda a, b: a * ny + b
+        # interior facets normal to x (between (i,j) and (i+1,j)): '+' local 1, '-' local 0
+        a, b = np.meshgrid(np.arange(nx - 1), np.arange(ny), indexing="ij")
+        fx_cells = np.stack([cid(a, b).ravel(), cid(a + 1, b).ravel()], axis=1)
+        fx_loc = np.tile(np.array([1, 0]), (fx_cells.shape[0], 1))
+        a, b = np.meshgrid(np.arange(nx), np.arange(ny - 1), indexing="ij")
+        fy_cells = np.stack([cid(a, b).ravel(), cid(a, b + 1).ravel()], axis=1)
+        fy_loc = np.tile(np.array([3, 2]), (fy_cells.shape[0], 1))
+        self.int_facet_cells = np.concatenate([fx_cells, fy_cells]).astype(IntType)
+        self.int_facet_local = np.concatenate([fx_loc, fy_loc]).astype(np.uint32)
+        ext_cells, ext_loc = [], []
+        b = np.arange(ny)
+        ext_cells += [cid(0, b), cid(nx - 1, b)]
+        ext_loc += [np.full(ny, 0), np.full(ny, 1)]
+        a = np.arange(nx)
+        ext_cells += [cid(a, 0), cid(a, ny - 1)]
+        ext_loc += [np.full(nx, 2), np.full(nx, 3)]
+        self.ext_facet_cells = np.concatenate(ext_cells).astype(IntType)
+        self.ext_facet_local = np.concatenate(ext_loc).astype(np.uint32)

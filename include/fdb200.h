@@ -1,0 +1,207 @@
+/* fdb200.h -- C ABI of the B200-native finite-element assembly engine.
+ *
+ * This is the drop-in boundary for ONE hot path of firedrakeproject/firedrake:
+ * the compiled PyOP2 "global kernel" (gather through the cell->node map, run
+ * the TSFC element kernel, scatter-add into a Dat or a Mat) and the data
+ * movement immediately around it.  Every entry point cites the reference
+ * interface it replaces (paths relative to the reference tree).
+ *
+ * Conventions
+ *   - IntType  = int32 (PETSc default; reference pyop2/datatypes.py:5-9)
+ *   - ScalarType = double (reference tsfc/parameters.py:18-22)
+ *   - all functions return 0 on success, nonzero on failure; the message is
+ *     available from fdb_last_error().  The reference wrapper ignores return
+ *     codes and raises in Python before the launch (pyop2/parloop.py:175-189);
+ *     the Python shim raises on nonzero.
+ *   - one CUDA device and one stream per process (one process per GPU).
+ *   - plain pointers and sizes only; no torch / PETSc types.
+ */
+#ifndef FDB200_H
+#define FDB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int32_t fdb_int;
+
+/* ------------------------------------------------------------------ runtime */
+/* Select the device and create the engine stream.  Idempotent.  Replaces the
+ * implicit "cc + dlopen" environment of pyop2/compilation.py:424-455. */
+int fdb_init(int device);
+int fdb_finalize(void);
+const char *fdb_last_error(void);
+int fdb_synchronize(void);
+/* name, SM count, total memory of the active device */
+int fdb_device_info(char *name, int name_len, int *sm_count, size_t *total_mem);
+/* number of kernels this library has launched since fdb_init (bench.py's
+ * "gpu_launches" claim is read from here, not estimated) */
+uint64_t fdb_launch_count(void);
+
+/* --------------------------------------------------------- device-resident data
+ * Device storage for Dat/Map/Global payloads when the caller keeps data on the
+ * GPU across calls.  Layout is exactly the host
+ * layout of pyop2/types/dat.py:72-96: C-contiguous (total_size, *dim), owned
+ * rows first, ghost rows at the tail, vector spaces AoS. */
+void *fdb_malloc(size_t nbytes);
+int fdb_free(void *dptr);
+int fdb_memset(void *dptr, int value, size_t nbytes);
+int fdb_memcpy_h2d(void *dst_dev, const void *src_host, size_t nbytes);
+int fdb_memcpy_d2h(void *dst_host, const void *src_dev, size_t nbytes);
+int fdb_memcpy_d2d(void *dst_dev, const void *src_dev, size_t nbytes);
+/* pinned host staging (the e2e path copies from/to these) */
+void *fdb_host_alloc(size_t nbytes);
+int fdb_host_free(void *hptr);
+int fdb_host_register(void *hptr, size_t nbytes);
+int fdb_host_unregister(void *hptr);
+
+/* ------------------------------------------------------------- mirror cache
+ * Drop-in mode: the caller hands HOST pointers, exactly what
+ * pyop2/parloop.py:203-212 puts in the arglist.  The engine keeps a device
+ * mirror per (host pointer, nbytes) and re-uploads when `version` differs from
+ * the one it holds -- `version` is DataCarrier.dat_version
+ * (pyop2/types/data_carrier.py:79-97), bumped by the caller on every host
+ * write.  FDB_WRITEBACK copies the mirror back to the host buffer. */
+int fdb_mirror_acquire(const void *host, size_t nbytes, uint64_t version,
+                       int upload, void **dev_out);
+int fdb_mirror_writeback(void *host);
+int fdb_mirror_drop(const void *host);
+int fdb_mirror_drop_all(void);
+
+/* ------------------------------------------------------------ global kernels
+ * fdb_kernel_desc is what PyOP2 folds into the JIT-compiled wrapper as
+ * compile-time constants and therefore into GlobalKernel.cache_key
+ * (pyop2/global_kernel.py:309-317): map arities, offset[], dims, extruded,
+ * constant_layers, subset, access modes -- plus the identity of the local
+ * kernel, which here is a form descriptor instead of generated C (the
+ * reference keys its kernel cache on the UFL form signature,
+ * firedrake/tsfc_interface.py:55-62). */
+
+enum fdb_form {
+    FDB_FORM_HELMHOLTZ = 1,     /* alpha*inner(grad u, grad v)*dx + beta*inner(u, v)*dx;
+                                   Poisson: (1,0)  mass: (0,1)  Helmholtz: (1,1)
+                                   demos/helmholtz/helmholtz.py.rst:52-77,
+                                   demos/matrix_free/poisson.py.rst:13-27        */
+    FDB_FORM_DG_ADVECTION = 2   /* demos/DG_advection/DG_advection.py.rst:182-217 */
+};
+
+enum fdb_cell {
+    FDB_CELL_HEX_EXTRUDED = 1,  /* quad base mesh x layers: map per column + offset */
+    FDB_CELL_HEX = 2,           /* native hex mesh: one map row per cell, no offset  */
+    FDB_CELL_TRIANGLE = 3,      /* affine P1 triangles (config 1)                     */
+    FDB_CELL_QUAD = 4           /* quads (DG advection)                               */
+};
+
+enum fdb_integral {
+    FDB_INTEGRAL_CELL = 0,
+    FDB_INTEGRAL_EXTERIOR_FACET = 1,
+    FDB_INTEGRAL_INTERIOR_FACET = 2
+};
+
+enum fdb_scatter {
+    FDB_SCATTER_ATOMIC = 0,     /* atomicAdd(double); run-to-run order varies      */
+    FDB_SCATTER_COLOURED = 1    /* deterministic: conflict-free colours, no atomics */
+};
+
+#define FDB_MAX_1D 8
+
+typedef struct fdb_kernel_desc {
+    int32_t form;               /* enum fdb_form                                  */
+    int32_t rank;               /* 1: 1-form / action (Dat INC)   2: 2-form (Mat) */
+    int32_t cell;               /* enum fdb_cell                                  */
+    int32_t integral;           /* enum fdb_integral                              */
+    int32_t degree;             /* polynomial degree p of the argument space      */
+    int32_t nq;                 /* 1-D quadrature points (hex kernels: == p+1)    */
+    int32_t cdim;               /* value size of the argument space (AoS)         */
+    int32_t scatter;            /* enum fdb_scatter                               */
+    double alpha, beta;
+    /* 1-D tables in 1-D dof numbering, row-major (nq, p+1); weights and points
+     * on [0,1].  Runtime inputs: the reference gets them from FInAT at kernel
+     * generation time (tsfc/fem.py:330-333, 380-391). */
+    double B[FDB_MAX_1D * FDB_MAX_1D];
+    double D[FDB_MAX_1D * FDB_MAX_1D];
+    double wq[FDB_MAX_1D];
+    double xq[FDB_MAX_1D];
+    /* extruded layer offsets (Map.offset, pyop2/types/map.py:36-56): arity
+     * entries for the argument map, 8 for the Q1 coordinate map.  NULL for
+     * non-extruded cells.  Copied at creation. */
+    const fdb_int *offset0;
+    const fdb_int *offset1;
+} fdb_kernel_desc;
+
+typedef struct fdb_kernel_s *fdb_kernel_t;
+
+/* Replaces pyop2.global_kernel.compile_global_kernel (global_kernel.py:426-456):
+ * "compile" = validate the descriptor, precompute tables, pick the sm_100a
+ * kernel instantiation.  Fails (nonzero) for forms outside the supported set. */
+int fdb_kernel_create(const fdb_kernel_desc *desc, fdb_kernel_t *out);
+int fdb_kernel_destroy(fdb_kernel_t k);
+
+#define FDB_LOC_HOST 0          /* args/maps are host pointers (mirror cache)      */
+#define FDB_LOC_DEVICE 1        /* args/maps are device pointers from fdb_malloc   */
+
+typedef struct fdb_call_args {
+    fdb_int start, end;         /* half-open range into the iteration set          */
+    const fdb_int *layers;      /* HOST int[2] {bottom, top node layer}, extruded
+                                   constant layers (pyop2/types/set.py:336-345);
+                                   NULL otherwise                                   */
+    const fdb_int *subset;      /* subset indices (same location as args) or NULL  */
+    int32_t nargs;              /* TSFC argument order: output, coords, coefficients */
+    void *const *args;
+    const size_t *arg_bytes;    /* host mode: byte size of each arg buffer          */
+    const uint64_t *arg_versions; /* host mode: dat_version per arg, NULL = always upload */
+    int32_t nmaps;              /* distinct maps, first-use order                   */
+    const fdb_int *const *maps;
+    const size_t *map_bytes;    /* host mode                                        */
+    int32_t location;           /* FDB_LOC_HOST | FDB_LOC_DEVICE                    */
+    int32_t writeback;          /* host mode: copy the output Dat back when done;
+                                   the engine then records arg_versions[0]+1 for it,
+                                   matching the dat_version bump PyOP2 applies to
+                                   written args (pyop2/parloop.py:262-272)           */
+    int32_t output_is_zero;     /* host mode: the caller has just zeroed the output
+                                   (firedrake/assemble.py:1042-1047), so the mirror
+                                   is memset on the device instead of uploaded       */
+} fdb_call_args;
+
+/* Replaces the ctypes call fn(start, end, *arglist) of
+ * pyop2/global_kernel.py:327-335 (signature: SURVEY.md section 8b,
+ * pyop2/codegen/builder.py:962-981).  The output is INCREMENTED (caller
+ * zeroes it: firedrake/assemble.py:1042-1047).  Asynchronous on the engine
+ * stream in device mode; host mode returns after the writeback. */
+int fdb_kernel_call(fdb_kernel_t k, const fdb_call_args *a);
+
+/* --------------------------------------------------------- Dat subset ops (K5)
+ * DirichletBC.zero / DirichletBC.set on a node subset (firedrake/bcs.py:192-221,
+ * pyop2/types/dat.py:297-311).  Device pointers. */
+int fdb_dat_zero_nodes(double *dat, int cdim, const fdb_int *nodes, fdb_int n);
+int fdb_dat_set_nodes(double *dat, const double *src, int cdim, const fdb_int *nodes, fdb_int n);
+int fdb_dat_set_nodes_scalar(double *dat, double value, int cdim, const fdb_int *nodes, fdb_int n);
+
+/* ------------------------------------------------------ Dat vector algebra (K6)
+ * pyop2/types/dat.py:354-540 (_op/_iop/inner/axpy/norm).  Device pointers;
+ * reductions return through a host double. */
+int fdb_vec_axpy(size_t n, double a, const double *x, double *y);            /* y += a x       */
+int fdb_vec_aypx(size_t n, double a, const double *x, double *y);            /* y = x + a y    */
+int fdb_vec_scale(size_t n, double a, double *x);
+int fdb_vec_dot(size_t n, const double *x, const double *y, double *out);
+int fdb_vec_pointwise_mult(size_t n, const double *x, const double *y, double *w);
+
+/* ------------------------------------------------------------------ timing
+ * CUDA events on the engine stream (the stream every kernel above is launched
+ * on), for bench.py. */
+typedef struct fdb_timer_s *fdb_timer_t;
+int fdb_timer_create(fdb_timer_t *out);
+int fdb_timer_start(fdb_timer_t t);
+int fdb_timer_stop(fdb_timer_t t, float *ms_out);   /* records, synchronises, returns elapsed */
+int fdb_timer_destroy(fdb_timer_t t);
+/* write `nbytes` of a scratch buffer (> L2) to flush the cache between timed
+ * iterations */
+int fdb_flush_l2(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FDB200_H */

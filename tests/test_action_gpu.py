@@ -1,0 +1,159 @@
+"""GPU parity: the sm_100a Helmholtz-family action kernel, called through the
+C ABI (firedrake_b200.op2 -> fdb_kernel_call), against the CPU oracle on the
+same seeded inputs.  Tolerance: 1e-12 relative in the max norm scaled by
+max|y| (different summation order, -ffast-math on the
+CPU side)."""
+import numpy as np
+import pytest
+
+from firedrake_b200 import op2
+from firedrake_b200.fiat_lite import interval_element
+from firedrake_b200.utility_meshes import ExtrudedHexMesh
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+
+
+def build(mesh, p, cdim=1, seed=1234):
+    V = mesh.function_space(p)
+    cells = op2.ExtrudedSet(op2.Set(mesh.num_base_cells), mesh.layers)
+    nodes = op2.Set(V.node_count)
+    vnodes = op2.Set(mesh.coord_space.node_count)
+    m0 = op2.Map(cells, nodes, V.arity, V.cell_node_map, offset=V.offset)
+    m1 = op2.Map(cells, vnodes, 8, mesh.coord_map, offset=mesh.coord_offset)
+    rng = np.random.default_rng(seed)
+    shape = (V.node_count,) if cdim == 1 else (V.node_count, cdim)
+    x = op2.Dat(op2.DataSet(nodes, cdim), rng.standard_normal(shape))
+    y = op2.Dat(op2.DataSet(nodes, cdim))
+    X = op2.Dat(op2.DataSet(vnodes, 3), mesh.coordinates)
+    return V, cells, m0, m1, x, y, X
+
+
+def oracle_action(oracle, mesh, V, p, xdata, cdim=1, alpha=1.0, beta=0.0, start=0, end=None):
+    yo = np.zeros_like(xdata)
+    oracle.action_extruded(interval_element(p), start, mesh.num_base_cells if end is None else end,
+                           [0, mesh.layers], yo, mesh.coordinates, np.ascontiguousarray(xdata),
+                           V.cell_node_map, V.offset, mesh.coord_map, mesh.coord_offset,
+                           cdim=cdim, alpha=alpha, beta=beta)
+    return yo
+
+
+def relerr(a, b):
+    return np.abs(a - b).max() / np.abs(b).max()
+
+
+@pytest.mark.parametrize("p", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("alpha,beta", [(1.0, 0.0), (1.0, 1.0), (0.0, 1.0)])
+def test_action_matches_oracle(engine, oracle, p, alpha, beta):
+    mesh = ExtrudedHexMesh(5, 4, 7, warp=0.05, permute_seed=0)
+    V, cells, m0, m1, x, y, X = build(mesh, p)
+    k = op2.Kernel("helmholtz", degree=p, alpha=alpha, beta=beta)
+    op2.par_loop(k, cells, y(op2.INC, m0), X(op2.READ, m1), x(op2.READ, m0))
+    yo = oracle_action(oracle, mesh, V, p, x.data_ro, alpha=alpha, beta=beta)
+    assert relerr(y.data_ro, yo) < TOL
+
+
+@pytest.mark.parametrize("p", [1, 3])
+def test_inc_semantics_and_ranges(engine, oracle, p):
+    """The output is INCREMENTED (caller zeroes it), and [start, end) splits
+    (core part / owned part, pyop2/parloop.py:250-253) compose."""
+    mesh = ExtrudedHexMesh(6, 3, 5, warp=0.03)
+    V, cells, m0, m1, x, y, X = build(mesh, p)
+    y0 = np.random.default_rng(7).standard_normal(V.node_count)
+    y.data[:] = y0
+    k = op2.Kernel("helmholtz", degree=p)
+    core = 7
+    cells2 = op2.ExtrudedSet(op2.Set((core, mesh.num_base_cells, mesh.num_base_cells)), mesh.layers)
+    m0b = op2.Map(cells2, m0.toset, V.arity, V.cell_node_map, offset=V.offset)
+    m1b = op2.Map(cells2, m1.toset, 8, mesh.coord_map, offset=mesh.coord_offset)
+    op2.par_loop(k, cells2, y(op2.INC, m0b), X(op2.READ, m1b), x(op2.READ, m0b))
+    yo = oracle_action(oracle, mesh, V, p, x.data_ro)
+    assert relerr(y.data_ro - y0, yo) < 1e-11
+
+
+@pytest.mark.parametrize("p", [2, 3])
+def test_coloured_scatter_is_deterministic(engine, oracle, p):
+    mesh = ExtrudedHexMesh(7, 6, 9, warp=0.05, permute_seed=3)
+    V, cells, m0, m1, x, y, X = build(mesh, p)
+    k = op2.Kernel("helmholtz", degree=p, alpha=1.0, beta=0.5)
+    outs = []
+    for _ in range(2):
+        y.zero()
+        op2.par_loop(k, cells, y(op2.INC, m0), X(op2.READ, m1), x(op2.READ, m0), scatter="coloured")
+        outs.append(y.data_ro.copy())
+    assert np.array_equal(outs[0], outs[1])          # bit-reproducible
+    yo = oracle_action(oracle, mesh, V, p, x.data_ro, alpha=1.0, beta=0.5)
+    assert relerr(outs[0], yo) < TOL
+    # atomics vs colouring: the race oracle of SURVEY.md section 5
+    y.zero()
+    op2.par_loop(k, cells, y(op2.INC, m0), X(op2.READ, m1), x(op2.READ, m0))
+    assert relerr(y.data_ro, outs[0]) < TOL
+
+
+def test_host_pointer_mode(engine, oracle):
+    """Drop-in mode: host pointers + dat_version through the mirror cache."""
+    p = 3
+    mesh = ExtrudedHexMesh(4, 4, 6, warp=0.05)
+    V, cells, m0, m1, x, y, X = build(mesh, p)
+    k = op2.Kernel("helmholtz", degree=p)
+    gk = op2.GlobalKernel(k, [m0, m1], extruded=True)
+    loop = op2.Parloop(gk, cells, [y(op2.INC, m0), X(op2.READ, m1), x(op2.READ, m0)], location="host")
+    loop()
+    yo = oracle_action(oracle, mesh, V, p, x.data_ro)
+    assert relerr(y.data_ro, yo) < TOL
+    # a host write bumps dat_version -> re-upload; a second call accumulates
+    x.data[:] *= 2.0
+    loop()
+    assert relerr(y.data_ro, 3.0 * yo) < TOL
+
+
+def test_vector_space_aos(engine, oracle):
+    """cdim = 3, node-major / component-fastest (vector Helmholtz, config 4)."""
+    p = 2
+    mesh = ExtrudedHexMesh(4, 3, 5, warp=0.05)
+    V, cells, m0, m1, x, y, X = build(mesh, p, cdim=3)
+    k = op2.Kernel("helmholtz", degree=p, alpha=1.0, beta=1.0, cdim=3)
+    op2.par_loop(k, cells, y(op2.INC, m0), X(op2.READ, m1), x(op2.READ, m0))
+    yo = oracle_action(oracle, mesh, V, p, x.data_ro, cdim=3, alpha=1.0, beta=1.0)
+    assert relerr(y.data_ro, yo) < TOL
+
+
+def test_subset_iteration(engine, oracle):
+    p = 2
+    mesh = ExtrudedHexMesh(5, 5, 4, warp=0.02)
+    V, cells, m0, m1, x, y, X = build(mesh, p)
+    idx = np.array([0, 3, 4, 11, 17, 24], dtype=np.int32)
+    sub = op2.Subset(cells, idx)
+    k = op2.Kernel("helmholtz", degree=p)
+    op2.par_loop(k, sub, y(op2.INC, m0), X(op2.READ, m1), x(op2.READ, m0))
+    yo = np.zeros(V.node_count)
+    for c in idx:
+        yo += oracle_action(oracle, mesh, V, p, x.data_ro, start=int(c), end=int(c) + 1)
+    assert relerr(y.data_ro, yo) < TOL
+
+
+def test_patch_test_and_nullspace(engine):
+    """Size-independent properties at a larger size: constants are in the null
+    space of the Poisson operator; 1^T M 1 = |Omega|; linear fields give zero
+    interior residual on a warped (non-affine) mesh."""
+    p = 3
+    mesh = ExtrudedHexMesh(12, 10, 16, warp=0.05, permute_seed=1)
+    V, cells, m0, m1, x, y, X = build(mesh, p)
+    x.data[:] = 1.0
+    op2.par_loop(op2.Kernel("helmholtz", degree=p), cells, y(op2.INC, m0), X(op2.READ, m1), x(op2.READ, m0))
+    assert np.abs(y.data_ro).max() < 1e-11
+    y.zero()
+    op2.par_loop(op2.Kernel("helmholtz", degree=p, alpha=0.0, beta=1.0), cells,
+                 y(op2.INC, m0), X(op2.READ, m1), x(op2.READ, m0))
+    assert abs(y.data_ro.sum() - 1.0) < 1e-12
+
+
+def test_errors_are_loud(engine):
+    mesh = ExtrudedHexMesh(2, 2, 2)
+    V, cells, m0, m1, x, y, X = build(mesh, 1)
+    from firedrake_b200 import EngineError
+    with pytest.raises(EngineError):
+        op2.par_loop(op2.Kernel("helmholtz", degree=7), cells, y(op2.INC, m0), X(op2.READ, m1), x(op2.READ, m0))
+    with pytest.raises(ValueError):
+        op2.par_loop(op2.Kernel("helmholtz", degree=1), cells, y(op2.READ, m0), X(op2.READ, m1), x(op2.READ, m0))
