@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libfdb200.so")
+LIB_PATH = os.environ.get("FDB200_LIB", os.path.join(HERE, "lib", "libfdb200.so"))
 
 MAX_1D = 8
 

@@ -24,6 +24,8 @@
 // point, as TSFC does (reference tsfc/ufl_utils.py:41-85), from the 8 vertex
 // coordinates: cofactor rows r_k of J, det = a.(b x c), and the flux in
 // reference coordinates is  (alpha w / |det|) r_k . (sum_m r_m ghat_m).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -42,7 +44,10 @@ struct HelmParams {
     int col0;                // first column (when collist == NULL)
     int nlay_items;          // layers to process per column
     int lay_first, lay_step; // layer = lay_first + lay_step * k
+    unsigned nlay_rcp;       // floor(2^32 / nlay_items)
     int cdim;
+    int chunk;               // items per work chunk
+    int *counter;            // device work counter (zeroed before the launch)
     double alpha, beta;
     double B[N * N];         // B[q][a]
     double Dt[N * N];        // Dt[q][q']
@@ -130,6 +135,8 @@ struct Tile {
 #pragma unroll
             for (int y = 0; y < N; y++) a[x][y] = base[(x * N + k[y]) * N + r];
     }
+    __device__ __forceinline__ double get_Y(int x, int z) const { return base[(x * N + r) * N + k[z]]; }
+    __device__ __forceinline__ void put_Y(int x, int z, double v) const { base[(x * N + r) * N + k[z]] = v; }
     // lane t == y holds a[x][z]
     __device__ __forceinline__ void store_Y(const double (&a)[N][N]) const
     {
@@ -147,28 +154,87 @@ struct Tile {
     }
 };
 
-constexpr int WARPS_PER_CTA = 4;
+#ifndef FDB_WARPS
+#define FDB_WARPS 4
+#endif
+constexpr int WARPS_PER_CTA = FDB_WARPS;
 
-template <int N, bool MASS, bool ATOMIC>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
+{
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int K>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(K) : "memory");
+}
+
+__device__ __forceinline__ void cp_async4(void *smem, const void *gmem)
+{
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gmem));
+}
+
+// per-warp shared-memory footprint.  Cell strides are padded so that the
+// 16 (64-bit) / 32 (32-bit) lanes of an access phase hit distinct banks.
+template <int N>
+struct WarpSmem {
+    static constexpr int CW = 32 / N;
+    static constexpr int CWS = (32 % N == 0) ? CW : CW + 1;   // idle lanes get a scratch slot
+    static constexpr int ND = N * N * N;
+    static constexpr int US = (N == 4) ? ND + 4 : ((ND % 2) ? ND : ND + 1);   // cell stride
+    static constexpr int CS = 26;                              // coord stride (24 used)
+    static constexpr int TILE = CWS * Tile<N>::STRIDE;         // doubles
+    static constexpr int UBUF = CWS * US;                      // doubles: gathered values (single buffer)
+    static constexpr int COORD = CWS * CS;                     // doubles: vertex coordinates (single buffer)
+    static constexpr int IDX = 2 * CWS * US;                   // ints: global dof index per local dof
+    static constexpr int MAPRAW = CWS * US;                    // ints: bottom-cell map row
+    static constexpr int VIDX = 2 * CWS * 8;                   // ints: bottom-cell vertex row
+    static constexpr int BYTES = (((TILE + UBUF + COORD) * 8 + (IDX + MAPRAW + VIDX) * 4) + 15) / 16 * 16;
+    static constexpr int CTA_BYTES = WARPS_PER_CTA * BYTES + ND * 4 + 32;
+};
+
+// One pipeline unit = (item, component): the cells a warp works on next.
+struct Unit {
+    int item;     // -1: none
+    int comp;
+    int ib;       // item-buffer parity (toggles when the item changes)
+    int cur, end; // chunk bookkeeping (warp uniform)
+    bool valid;   // per lane: this lane's cell exists
+    int col, layer;
+};
+
+template <int N, bool MASS, bool ATOMIC, int MINB>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB)
 helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
 {
-    constexpr int CW = 32 / N;            // cells per warp
+    using WS = WarpSmem<N>;
+    constexpr int CW = WS::CW;
+    constexpr int CWS = WS::CWS;
     constexpr int ND = N * N * N;
-    constexpr int TS = Tile<N>::STRIDE;
-    __shared__ double s_tile[WARPS_PER_CTA][CW * TS];
-    __shared__ double s_coord[WARPS_PER_CTA][CW][24];
-    __shared__ int s_off0[ND];
+    constexpr int US = WS::US;
+    constexpr int CS = WS::CS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *wbase = reinterpret_cast<double *>(smem_raw + (size_t)warp * WS::BYTES);
+    double *s_tile = wbase;
+    double *s_u = s_tile + WS::TILE;                 // [2][CWS][US]
+    double *s_coord = s_u + WS::UBUF;                // [2][CWS][CS]
+    int *s_idx = reinterpret_cast<int *>(s_coord + WS::COORD);   // [2][CWS][US]
+    int *s_mapraw = s_idx + WS::IDX;                 // [CWS][US]
+    int *s_vidx = s_mapraw + WS::MAPRAW;             // [2][CWS][8]
+    int *s_off0 = reinterpret_cast<int *>(smem_raw + (size_t)WARPS_PER_CTA * WS::BYTES);
+    int *s_off1 = s_off0 + ND;
 
     for (int i = threadIdx.x; i < ND; i += blockDim.x) s_off0[i] = P.off0[i];
+    if (threadIdx.x < 8) s_off1[threadIdx.x] = P.off1[threadIdx.x];
     __syncthreads();
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cw = lane / N, t = lane - cw * N;
     const bool lane_active = cw < CW;
-    const int cwc = lane_active ? cw : 0;
-    Tile<N> tile(s_tile[warp], cwc, t);
-    double *sc = s_coord[warp][cwc];
+    Tile<N> tile(s_tile, cw, t);
 
     const int ncells = P.ncols * P.nlay_items;      // < 2^31, checked by the launcher
     const int nitems = (ncells + CW - 1) / CW;
@@ -176,68 +242,165 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
     const double wy_alpha = P.wq[lane_active ? t : 0] * P.alpha;
     const double wy_beta = P.wq[lane_active ? t : 0] * P.beta;
 
-    for (int item = blockIdx.x * WARPS_PER_CTA + warp; item < nitems;
-         item += gridDim.x * WARPS_PER_CTA) {
-        // cells are numbered column-major: consecutive lanes-groups take
-        // consecutive layers of one column (nlay_items == 1 for native hexes)
-        const int lin = item * CW + cw;
-        const bool valid = lane_active && lin < ncells;
-        const int ci = valid ? lin / P.nlay_items : 0;
-        const int kk = valid ? lin - ci * P.nlay_items : 0;
-        const int layer = P.lay_first + P.lay_step * kk;
-        const int col = P.collist ? __ldg(P.collist + ci) : (P.col0 + ci);
-        const int *mrow = P.map0 + (long long)col * ND;
+    // warp-uniform work iterator: chunks of consecutive items (one column's
+    // worth) handed out by an atomic counter -> locality inside a chunk,
+    // dynamic balance across SMs
+    auto advance = [&](Unit u) -> Unit {
+        if (u.item >= 0 && u.comp + 1 < P.cdim) {
+            u.comp++;
+            return u;
+        }
+        u.comp = 0;
+        u.ib ^= 1;
+        if (u.item >= 0 && u.cur + 1 < u.end) {
+            u.cur++;
+            u.item = u.cur;
+            return u;
+        }
+        if (u.item == -2) return u;                  // queue already drained
+        int base = 0;
+        if (lane == 0) base = atomicAdd(P.counter, P.chunk);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= nitems) {
+            u.item = -2;
+            return u;
+        }
+        u.cur = base;
+        u.end = min(base + P.chunk, nitems);
+        u.item = base;
+        return u;
+    };
 
-        // ---- stage the 8 vertex coordinates of each cell in shared memory
-        __syncwarp();
-        if (valid) {
+    // per-lane decode of a unit (cell -> column, layer); division by the
+    // launch-constant layer count through a precomputed reciprocal
+    auto decode = [&](Unit &u) {
+        const int lin = u.item * CW + cw;
+        u.valid = lane_active && u.item >= 0 && lin < ncells;
+        unsigned ci = __umulhi((unsigned)lin, P.nlay_rcp);
+        int kk = lin - (int)ci * P.nlay_items;
+        if (kk >= P.nlay_items) { kk -= P.nlay_items; ci++; }
+        if (!u.valid) { ci = 0; kk = 0; }
+        u.layer = P.lay_first + P.lay_step * kk;
+        u.col = P.collist ? __ldg(P.collist + ci) : (P.col0 + (int)ci);
+    };
+
+    // Three-stage gather pipeline, all through cp.async (no registers held, no
+    // load the warp has to wait for):
+    //   stage A (unit i+2): copy the bottom-cell map row / vertex row to smem
+    //   stage B (unit i+1): indices = row + offset*layer; copy x values and
+    //                       vertex coordinates to smem
+    //   stage C (unit i)  : compute + scatter
+    // Stage B is issued in N slices from inside the quadrature loop so that its
+    // integer/LSU instructions fill issue slots the fp64 pipe leaves free.
+    // Every lane touches only its own slots of s_u / s_idx / s_mapraw; s_vidx and
+    // s_coord are shared by the N lanes of a cell and are read after the
+    // wait + __syncwarp at the top of the loop.
+    auto stageA = [&](const Unit &u) {
+        if (u.valid && u.comp == 0) {
+            const int *mrow = P.map0 + (long long)u.col * ND;
+            int *sm = s_mapraw + cw * US;
+#pragma unroll
+            for (int j = 0; j < N * N; j++) cp_async4(sm + j * N + t, mrow + j * N + t);
+            int *sv = s_vidx + (u.ib * CWS + cw) * 8;
+            for (int v = t; v < 8; v += N) cp_async4(sv + v, P.map1 + (long long)u.col * 8 + v);
+        }
+    };
+    auto stageB_coords = [&](const Unit &u) {
+        if (u.valid && u.comp == 0) {
+            const int *sv = s_vidx + (u.ib * CWS + cw) * 8;
+            double *scd = s_coord + cw * CS;
             for (int i = t; i < 24; i += N) {
                 int v = i / 3, a = i - v * 3;
-                int g = __ldg(P.map1 + (long long)col * 8 + v) + __ldg(P.off1 + v) * layer;
-                sc[i] = __ldg(P.coords + (long long)g * 3 + a);
+                int g = sv[v] + s_off1[v] * u.layer;
+                cp_async8(scd + i, P.coords + (long long)g * 3 + a);
             }
         }
-        __syncwarp();
-        // trilinear coefficients reduced at this lane's eta (see header comment)
-        double A1[3], A3[3], A6[3], c2[3], c4[3], c5[3], c7[3];
+    };
+    auto stageB_part = [&](const Unit &u, int ubuf, int part) {
+        if (u.valid) {
+            double *su = s_u + cw * US;
+            int *si = s_idx + (u.ib * CWS + cw) * US;
+            const int *sm = s_mapraw + cw * US;
+            int g[N];
+            if (u.comp == 0) {
 #pragma unroll
-        for (int a = 0; a < 3; a++) {
-            double X000 = sc[0 * 3 + a], X001 = sc[1 * 3 + a], X010 = sc[2 * 3 + a],
-                   X011 = sc[3 * 3 + a], X100 = sc[4 * 3 + a], X101 = sc[5 * 3 + a],
-                   X110 = sc[6 * 3 + a], X111 = sc[7 * 3 + a];
-            if (!valid) {   // keep idle lanes finite: unit cube
-                X000 = 0; X001 = (a == 2); X010 = (a == 1); X011 = (a >= 1);
-                X100 = (a == 0); X101 = (a != 1); X110 = (a != 2); X111 = 1;
+                for (int j = 0; j < N; j++) {
+                    const int loc = (part * N + j) * N + t;
+                    g[j] = sm[loc] + s_off0[loc] * u.layer;
+                }
+#pragma unroll
+                for (int j = 0; j < N; j++) si[(part * N + j) * N + t] = g[j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < N; j++) g[j] = si[(part * N + j) * N + t];
             }
-            double c1 = X100 - X000;
-            c2[a] = X010 - X000;
-            double c3 = X001 - X000;
-            c4[a] = X110 - X100 - X010 + X000;
-            c5[a] = X011 - X010 - X001 + X000;
-            double c6 = X101 - X100 - X001 + X000;
-            c7[a] = X111 - X110 - X101 - X011 + X100 + X010 + X001 - X000;
-            A1[a] = fma(c4[a], eta, c1);
-            A3[a] = fma(c5[a], eta, c3);
-            A6[a] = fma(c7[a], eta, c6);
+#pragma unroll
+            for (int j = 0; j < N; j++)
+                cp_async8(su + (part * N + j) * N + t, P.x + (long long)g[j] * P.cdim + u.comp);
         }
+    };
 
-        for (int comp = 0; comp < P.cdim; comp++) {
-            // ---- gather, layout Z (lane t == a_z)
+    Unit cur{-1, 0, 0, 0, 0, false, 0, 0};
+    cur = advance(cur);
+    decode(cur);
+    Unit nxt = advance(cur);
+    decode(nxt);
+    stageA(cur);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncwarp();
+    int ubuf = 0;
+    stageB_coords(cur);
+#pragma unroll
+    for (int part = 0; part < N; part++) stageB_part(cur, ubuf, part);
+    stageA(nxt);
+    cp_async_commit();
+    double A1[3], A3[3], A6[3], c2[3], c4[3], c5[3], c7[3];
+
+    while (cur.item >= 0) {
+        cp_async_wait<0>();      // values of `cur`, rows of `nxt` have landed
+        __syncwarp();
+        Unit nn = advance(nxt);
+        decode(nn);
+
+        const bool valid = cur.valid;
+        const int cbuf = cur.ib;
+        const double *sc = s_coord + cw * CS;
+        if (cur.comp == 0) {
+            // trilinear coefficients reduced at this lane's eta (see header comment)
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+                double X000 = sc[0 * 3 + a], X001 = sc[1 * 3 + a], X010 = sc[2 * 3 + a],
+                       X011 = sc[3 * 3 + a], X100 = sc[4 * 3 + a], X101 = sc[5 * 3 + a],
+                       X110 = sc[6 * 3 + a], X111 = sc[7 * 3 + a];
+                if (!valid) {   // keep idle lanes finite: unit cube
+                    X000 = 0; X001 = (a == 2); X010 = (a == 1); X011 = (a >= 1);
+                    X100 = (a == 0); X101 = (a != 1); X110 = (a != 2); X111 = 1;
+                }
+                double c1 = X100 - X000;
+                c2[a] = X010 - X000;
+                double c3 = X001 - X000;
+                c4[a] = X110 - X100 - X010 + X000;
+                c5[a] = X011 - X010 - X001 + X000;
+                double c6 = X101 - X100 - X001 + X000;
+                c7[a] = X111 - X110 - X101 - X011 + X100 + X010 + X001 - X000;
+                A1[a] = fma(c4[a], eta, c1);
+                A3[a] = fma(c5[a], eta, c3);
+                A6[a] = fma(c7[a], eta, c6);
+            }
+        }
+        const int comp = cur.comp;
+        const int *si = s_idx + (cbuf * CWS + cw) * US;
+        {
+            // ---- gathered values, layout Z (lane t == a_z)
+            const double *su = s_u + cw * US;
             double u[N][N];
 #pragma unroll
             for (int x = 0; x < N; x++)
 #pragma unroll
-                for (int yy = 0; yy < N; yy++) {
-                    const int loc = (x * N + yy) * N + t;
-                    double v = 0.0;
-                    if (valid) {
-                        int g = __ldg(mrow + loc) + s_off0[loc] * layer;
-                        v = __ldg(P.x + (long long)g * P.cdim + comp);
-                    }
-                    u[x][yy] = v;
-                }
+                for (int yy = 0; yy < N; yy++) u[x][yy] = valid ? su[(x * N + yy) * N + t] : 0.0;
             // ---- forward: interpolate to the quadrature points
-            double tmp[N][N], U[N][N], Gy[N][N];
+            double tmp[N][N], U[N][N];
             apply_first<N, false>(P.B, u, tmp);          // a_x -> q_x
             apply_second<N, false>(P.B, tmp, u);         // a_y -> q_y     u = w[qx][qy] @ a_z
             __syncwarp();
@@ -253,7 +416,9 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
             __syncwarp();
             tile.store_Z(u);
             __syncwarp();
-            tile.load_Y(Gy);                             // Gy[qx][qz] @ q_y
+            // d/d eta now sits in the tile in layout-Y order; each lane reads its
+            // own slot (qx, qz) inside the quadrature loop and overwrites it
+            // with the eta-flux, which the transpose path picks up from there
 
             // ---- quadrature points (layout Y), fused with the x/z derivative
             //      and its transpose so only U, Gy and Vp stay live
@@ -264,6 +429,10 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
                 for (int j = 0; j < N; j++) Vp[i][j] = 0.0;
 #pragma unroll
             for (int qz = 0; qz < N; qz++) {
+                // single-buffered staging: the values / coordinates of `cur`
+                // were consumed (and a __syncwarp passed) before this point
+                if (qz == 0) stageB_coords(nxt);
+                stageB_part(nxt, ubuf ^ 1, qz);
                 const double zeta = P.xq[qz];
                 double ca[3], pb[3], qb[3];
 #pragma unroll
@@ -289,7 +458,7 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
                         gx = fma(P.Dt[qx * N + q], U[q][qz], gx);
                         gz = fma(P.Dt[qz * N + q], U[qx][q], gz);
                     }
-                    const double gy = Gy[qx][qz];
+                    const double gy = tile.get_Y(qx, qz);
                     // cofactor rows: r0 = b x c, r1 = c x a, r2 = a x b
                     double r0[3], r1[3], r2[3];
                     r0[0] = cb[1] * cc[2] - cb[2] * cc[1];
@@ -310,7 +479,7 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
                     const double fx = s * (r0[0] * h[0] + r0[1] * h[1] + r0[2] * h[2]);
                     const double fy = s * (r1[0] * h[0] + r1[1] * h[1] + r1[2] * h[2]);
                     const double fz = s * (r2[0] * h[0] + r2[1] * h[1] + r2[2] * h[2]);
-                    Gy[qx][qz] = fy;
+                    tile.put_Y(qx, qz, fy);
 #pragma unroll
                     for (int q = 0; q < N; q++) {
                         Vp[q][qz] = fma(P.Dt[qx * N + q], fx, Vp[q][qz]);
@@ -320,9 +489,10 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
                 }
             }
 
-            // ---- backward
-            __syncwarp();
-            tile.store_Y(Gy);                            // Fy[qx][qz] @ q_y
+            stageA(nn);
+            cp_async_commit();
+
+            // ---- backward (the tile holds Fy[qx][qz] @ q_y)
             __syncwarp();
             tile.load_Z(tmp);                            // Fy[qx][qy] @ q_z
             apply_second<N, true>(P.Dt, tmp, u);         // Dt^T along eta
@@ -348,15 +518,76 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
                 for (int x = 0; x < N; x++)
 #pragma unroll
                     for (int yy = 0; yy < N; yy++) {
-                        const int loc = (x * N + yy) * N + t;
-                        int g = __ldg(mrow + loc) + s_off0[loc] * layer;
+                        const int g = si[(x * N + yy) * N + t];
                         double *dst = P.y + (long long)g * P.cdim + comp;
                         if (ATOMIC) atomicAdd(dst, u[x][yy]);
                         else *dst += u[x][yy];
                     }
             }
         }
+        cur = nxt;
+        nxt = nn;
+        ubuf ^= 1;
     }
+    cp_async_wait<0>();
+}
+
+template <int N, bool MASS, bool ATOMIC, int MINB>
+int launch_one(int grid_cap_per_sm, cudaStream_t st, HelmParams<N> &P, int sm_count)
+{
+    using WS = WarpSmem<N>;
+    constexpr int T = WARPS_PER_CTA * 32;
+    auto kern = helmholtz_action_kernel<N, MASS, ATOMIC, MINB>;
+    static bool configured = false;
+    static int occ = 1;
+    if (!configured) {
+        FDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WS::CTA_BYTES));
+        FDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T, WS::CTA_BYTES));
+        if (occ < 1) occ = 1;
+        configured = true;
+    }
+    const int ncells = P.ncols * P.nlay_items;
+    const int nitems = (ncells + WS::CW - 1) / WS::CW;
+    int per_sm = occ;
+    if (grid_cap_per_sm > 0 && grid_cap_per_sm < per_sm) per_sm = grid_cap_per_sm;
+    long long grid = (long long)sm_count * per_sm;
+    long long need = (nitems + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    // chunk: one column's worth of items, bounded so that every resident warp
+    // gets several chunks
+    int chunk = P.nlay_items / WS::CW;
+    if (chunk < 8) chunk = 8;
+    if (chunk > 64) chunk = 64;
+    long long per_warp = nitems / (grid * WARPS_PER_CTA) + 1;
+    if (chunk > per_warp / 4 + 1) chunk = (int)(per_warp / 4 + 1);
+    P.chunk = chunk;
+    P.nlay_rcp = (unsigned)(0x100000000ull / (unsigned long long)P.nlay_items);
+    if (P.nlay_items == 1) P.nlay_rcp = 0xffffffffu;
+    FDB_CUDA(cudaMemsetAsync(P.counter, 0, sizeof(int), st));
+    kern<<<(int)grid, T, WS::CTA_BYTES, st>>>(P);
+    FDB_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int N, bool ATOMIC>
+int launch_variant(bool mass, int minb, int cap, cudaStream_t st, HelmParams<N> &P, int sm_count)
+{
+    if (N == 4 && minb == 3) {
+        if (mass) return launch_one<N, true, ATOMIC, (N == 4 ? 3 : 2)>(cap, st, P, sm_count);
+        return launch_one<N, false, ATOMIC, (N == 4 ? 3 : 2)>(cap, st, P, sm_count);
+    }
+    if (N == 4 && minb == 4) {
+        if (mass) return launch_one<N, true, ATOMIC, (N == 4 ? 4 : 2)>(cap, st, P, sm_count);
+        return launch_one<N, false, ATOMIC, (N == 4 ? 4 : 2)>(cap, st, P, sm_count);
+    }
+    if (N == 4 && minb == 1) {
+        if (mass) return launch_one<N, true, ATOMIC, 1>(cap, st, P, sm_count);
+        return launch_one<N, false, ATOMIC, 1>(cap, st, P, sm_count);
+    }
+    constexpr int DEF = (N >= 5) ? 1 : 2;
+    if (mass) return launch_one<N, true, ATOMIC, DEF>(cap, st, P, sm_count);
+    return launch_one<N, false, ATOMIC, DEF>(cap, st, P, sm_count);
 }
 
 template <int N>
@@ -385,15 +616,9 @@ int launch_n(fdb_kernel_s *k, fdb_int start, fdb_int end, int nlay, const fdb_in
         P.xq[i] = k->desc.xq[i];
     }
     const bool mass = k->desc.beta != 0.0;
-    constexpr int CW = 32 / N;
-    auto grid_for = [&](long long ncols, int nitems_lay) {
-        long long nitems = (ncols * nitems_lay + CW - 1) / CW;
-        long long blocks = (nitems + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-        long long cap = (long long)c.sm_count * 16;
-        if (blocks > cap) blocks = cap;
-        if (blocks < 1) blocks = 1;
-        return (int)blocks;
-    };
+    static const int minb = getenv("FDB_MINB") ? atoi(getenv("FDB_MINB")) : 2;
+    static const int cap = getenv("FDB_CTAS_PER_SM") ? atoi(getenv("FDB_CTAS_PER_SM")) : 0;
+    P.counter = c.work_counter;
     if (k->desc.scatter == FDB_SCATTER_ATOMIC) {
         P.collist = subset;
         P.col0 = start;
@@ -402,13 +627,7 @@ int launch_n(fdb_kernel_s *k, fdb_int start, fdb_int end, int nlay, const fdb_in
         P.lay_first = 0;
         P.lay_step = 1;
         if (P.ncols <= 0 || nlay <= 0) return 0;
-        int grid = grid_for(P.ncols, nlay);
-        if (mass)
-            helmholtz_action_kernel<N, true, true><<<grid, WARPS_PER_CTA * 32, 0, c.stream>>>(P);
-        else
-            helmholtz_action_kernel<N, false, true><<<grid, WARPS_PER_CTA * 32, 0, c.stream>>>(P);
-        FDB_LAUNCH_CHECK();
-        return 0;
+        return launch_variant<N, true>(mass, minb, cap, c.stream, P, c.sm_count);
     }
     // deterministic: one launch per (colour, layer parity); within a launch no
     // two cells share a dof, so plain read-modify-write is race free and the
@@ -427,12 +646,7 @@ int launch_n(fdb_kernel_s *k, fdb_int start, fdb_int end, int nlay, const fdb_in
             P.lay_step = 2;
             P.nlay_items = (nlay - par + 1) / 2;
             if (P.ncols <= 0 || P.nlay_items <= 0) continue;
-            int grid = grid_for(P.ncols, P.nlay_items);
-            if (mass)
-                helmholtz_action_kernel<N, true, false><<<grid, WARPS_PER_CTA * 32, 0, c.stream>>>(P);
-            else
-                helmholtz_action_kernel<N, false, false><<<grid, WARPS_PER_CTA * 32, 0, c.stream>>>(P);
-            FDB_LAUNCH_CHECK();
+            if (launch_variant<N, false>(mass, minb, cap, c.stream, P, c.sm_count)) return 1;
         }
     }
     return 0;

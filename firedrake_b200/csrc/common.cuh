@@ -19,6 +19,7 @@ struct Context {
     size_t flush_bytes = 0;
     double *reduce_scratch = nullptr;   // device scratch for reductions
     double *reduce_host = nullptr;      // pinned
+    int *work_counter = nullptr;        // device work-queue counter of the persistent kernels
 };
 
 Context &ctx();

@@ -80,6 +80,7 @@ int fdb_init(int device)
     c.sm_count = prop.multiProcessorCount;
     FDB_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
     FDB_CUDA(cudaMalloc(&c.reduce_scratch, 4096 * sizeof(double)));
+    FDB_CUDA(cudaMalloc(&c.work_counter, 64 * sizeof(int)));
     FDB_CUDA(cudaHostAlloc((void **)&c.reduce_host, 64 * sizeof(double), cudaHostAllocDefault));
     c.ready = true;
     return 0;
@@ -94,6 +95,7 @@ int fdb_finalize(void)
     g_mirrors.clear();
     if (c.flush_buf) cudaFree(c.flush_buf);
     cudaFree(c.reduce_scratch);
+    cudaFree(c.work_counter);
     cudaFreeHost(c.reduce_host);
     cudaStreamDestroy(c.stream);
     c = Context();

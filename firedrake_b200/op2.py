@@ -277,7 +277,10 @@ class Dat:
     # -- host access (pyop2/types/dat.py data / data_ro / data_with_halos)
     def _sync_host(self):
         if not self._host_valid:
-            self._dev.to_host(self._data)
+            if self._is_zero:
+                self._data[...] = 0          # a lazy zero() materialises here
+            else:
+                self._dev.to_host(self._data)
             self._host_valid = True
 
     @property
@@ -346,15 +349,12 @@ class Dat:
             else:
                 self.data_with_halos[subset.indices] = 0
             return
-        if self._dev is not None and self._dev_valid and not self._host_valid:
-            _lib.check(_lib.lib().fdb_memset(self._dev.ptr, 0, self._data.nbytes), "memset")
-            self.increment_dat_version()
-        else:
-            self._data[...] = 0
-            self._host_valid = True
-            self._dev_valid = False
-            self.increment_dat_version()
+        # lazy: neither copy is touched until somebody needs it (the assembler
+        # zeroes the tensor right before a parloop that overwrites it anyway)
+        self._host_valid = False
+        self._dev_valid = False
         self._is_zero = True
+        self.increment_dat_version()
 
     def _vec_op(self, other, fn, *scalars):
         L = _lib.lib()
@@ -586,8 +586,10 @@ class Parloop:
             out._device_written()
         else:
             subset = it.indices.ctypes.data if isinstance(it, Subset) else None
+            lazy_zero = out._is_zero and not out._host_valid
             for a in self.args:
-                a.data._sync_host()
+                if not (a.data is out and lazy_zero):
+                    a.data._sync_host()
             ptrs = [a.data._data.ctypes.data for a in self.args]
             nbytes = [a.data._data.nbytes for a in self.args]
             vers = [a.data.dat_version for a in self.args]
@@ -596,6 +598,7 @@ class Parloop:
                [m.values_with_halo.nbytes for m in maps], _lib.LOC_HOST, True, out._is_zero)
             out.increment_dat_version()      # pyop2/parloop.py:262-272
             out._is_zero = False
+            out._host_valid = True           # written back by the engine
             out._dev_valid = False
 
     def __call__(self):
