@@ -101,27 +101,37 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------- workload
-def make_problem(args, nx, pinned):
+def make_problem(args, rank, world, pinned):
+    """Rank-local slab of the n^3 mesh in Firedrake-shaped arrays, wrapped in
+    the PyOP2-mirror objects (sets ordered core | owned | ghost)."""
     from firedrake_b200 import op2
-    from firedrake_b200.utility_meshes import ExtrudedHexMesh
+    from firedrake_b200.halo import Halo
+    from firedrake_b200.partition import SlabPartition
     n, p = args.n, args.degree
-    mesh = ExtrudedHexMesh(nx, n, n, Lx=nx / n, warp=args.warp,
-                           permute_seed=None if args.permute < 0 else args.permute)
-    V = mesh.function_space(p)
-    cells = op2.ExtrudedSet(op2.Set(mesh.num_base_cells), mesh.layers)
-    nodes = op2.Set(V.node_count)
+    if args.permute >= 0 and world > 1:
+        raise SystemExit("--permute is a single-GPU stress option")
+    part = SlabPartition(n, n, n, p, rank, world, warp=args.warp)
+    mesh, V = part.mesh, part.V
+    if args.permute >= 0:
+        from firedrake_b200.utility_meshes import ExtrudedHexMesh
+        mesh = ExtrudedHexMesh(n, n, n, warp=args.warp, permute_seed=args.permute)
+        V = mesh.function_space(p)
+    halo = Halo(part.neighbours) if world > 1 else None
+    cells = op2.ExtrudedSet(op2.Set(part.cell_sizes), mesh.layers)
+    nodes = op2.Set(part.node_sizes)
     vnodes = op2.Set(mesh.coord_space.node_count)
     m0 = op2.Map(cells, nodes, V.arity, V.cell_node_map, offset=V.offset)
     m1 = op2.Map(cells, vnodes, 8, mesh.coord_map, offset=mesh.coord_offset)
-    x = op2.Dat(nodes, pinned=pinned)
-    rng = np.random.default_rng(1234)
+    dnodes = op2.DataSet(nodes, 1, halo=halo)
+    x = op2.Dat(dnodes, pinned=pinned)
+    rng = np.random.default_rng(1234 + rank)
     xa = x.data_with_halos
     chunk = 1 << 24
     for i in range(0, V.node_count, chunk):
         xa[i:i + chunk] = rng.standard_normal(min(chunk, V.node_count - i))
-    y = op2.Dat(nodes, pinned=pinned)
+    y = op2.Dat(dnodes, pinned=pinned)
     X = op2.Dat(op2.DataSet(vnodes, 3), mesh.coordinates)
-    return mesh, V, cells, m0, m1, x, y, X
+    return part, mesh, V, cells, m0, m1, x, y, X
 
 
 def algorithmic_bytes(V, mesh):
@@ -212,24 +222,41 @@ def main():
             run_reference(args)
         return
     if world != args.gpus:
-        if args.gpus != 1 or world != 1:
-            raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun")
-    if world > 1:
-        raise SystemExit("multi-GPU bench: see firedrake_b200.halo (not wired into this revision)")
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with "
+                         "python -m torch.distributed.run --nproc-per-node N bench.py --gpus N")
 
     import ctypes as C
     from firedrake_b200 import _lib, op2
-    L = _lib.init(int(os.environ.get("LOCAL_RANK", "0")))
+    from firedrake_b200.halo import comm_init_from_env
+    rank, world, dist = comm_init_from_env()
+    L = _lib.lib()
     n, p = args.n, args.degree
     t_setup = time.perf_counter()
-    mesh, V, cells, m0, m1, x, y, X = make_problem(args, n, pinned=not args.no_e2e)
-    ndof = V.node_count
+    part, mesh, V, cells, m0, m1, x, y, X = make_problem(args, rank, world, pinned=not args.no_e2e)
+    ndof_owned = V.owned_node_count
+    ndof_global = (n * p + 1) ** 3
     kern = op2.Kernel("helmholtz", degree=p, alpha=1.0, beta=0.0)
     gk = op2.GlobalKernel(kern, [m0, m1], extruded=True)
     loop = op2.Parloop(gk, cells, [y(op2.INC, m0), X(op2.READ, m1), x(op2.READ, m0)], location="device")
     t_setup = time.perf_counter() - t_setup
 
+    def barrier():
+        _lib.check(L.fdb_synchronize())
+        if dist is not None:
+            dist.barrier()
+
+    def maxreduce(v):
+        if dist is None:
+            return v
+        import torch
+        t = torch.tensor([v], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     def step():
+        # one assembly: zero the tensor, refresh ghost x, core cells overlapped
+        # with the exchange, owned cells, ghost contributions back to owners
+        x.halo_valid = world == 1      # x changes every solver iteration
         y.zero()
         loop()
 
@@ -237,7 +264,7 @@ def main():
     x.device_ptr; y.device_ptr; X.device_ptr; m0.device_ptr; m1.device_ptr
     for _ in range(max(args.warmup, 3)):
         step()
-    _lib.check(L.fdb_synchronize())
+    barrier()
 
     tm = C.c_void_p(); tk = C.c_void_p()
     _lib.check(L.fdb_timer_create(C.byref(tm)))
@@ -247,25 +274,32 @@ def main():
     time.sleep(0.3)
     launches0 = L.fdb_launch_count()
     ms = C.c_float()
-    _lib.check(L.fdb_synchronize())
+    barrier()
     _lib.check(L.fdb_timer_start(tm))
     for _ in range(args.steps):
         step()
     _lib.check(L.fdb_timer_stop(tm, C.byref(ms)))
-    total_ms = ms.value
+    barrier()
+    total_ms = maxreduce(ms.value)
     launches = L.fdb_launch_count() - launches0
-    # kernel-only duration (CUDA events around the global kernel alone, same stream)
+    # kernel-only duration (CUDA events around the global kernel alone, same
+    # stream); single-GPU figure used for the roofline
     kms = []
+    kloop = op2.Parloop(gk, cells, [y(op2.INC, m0), X(op2.READ, m1), x(op2.READ, m0)], location="device")
     for _ in range(args.steps):
         y.zero()
+        y.device_ptr
+        x.halo_valid = True
+        y.frozen_halo = True
         _lib.check(L.fdb_timer_start(tk))
-        loop()
+        kloop()
         _lib.check(L.fdb_timer_stop(tk, C.byref(ms)))
+        y.frozen_halo = False
         kms.append(ms.value)
     clocks = sampler.stop()
     ms_per_step = total_ms / args.steps
-    value = ndof / (ms_per_step * 1e-3)
-    kernel_ms = float(np.mean(kms))
+    value = ndof_global / (ms_per_step * 1e-3)
+    kernel_ms = maxreduce(float(np.mean(kms)))
 
     peaks = {}
     try:
@@ -275,51 +309,70 @@ def main():
     peak_gbs = peaks.get("hbm_gbs", 6650.0)
     abytes = algorithmic_bytes(V, mesh)
     achieved = abytes / (kernel_ms * 1e-3) / 1e9
+    FP64_PEAK = 37.1   # TFLOP/s: tools/microbench_fp64.cu on this pool (DFMA 34.2, DMMA 37.1, shared pipe)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                 "frac": achieved / peak_gbs, "traffic": None,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
-                "kernel": "helmholtz_action_kernel<4,false,true>", "kernel_ms": kernel_ms,
-                "algorithmic_bytes": abytes,
-                "note": "kernel is fp64-pipe-bound, not HBM-bound (DESIGN.md): fp64 fraction reported in fp64",
-                "fp64": {"flops_per_cell": kern.num_flops, "achieved_tflops":
+                "kernel": f"helmholtz_action_kernel<{p + 1},false,true,2>", "kernel_ms": kernel_ms,
+                "algorithmic_bytes_per_launch": abytes,
+                "note": "this kernel is fp64-pipe-bound, not HBM-bound (DESIGN.md section 4): the binding "
+                        "fraction is fp64.frac; the HBM fraction is reported because the contract asks for it",
+                "fp64": {"flop_per_cell": kern.num_flops, "achieved_tflops":
                          kern.num_flops * mesh.num_cells / (kernel_ms * 1e-3) / 1e12,
-                         "peak_tflops_nominal": 37.2}}
-    roofline["fp64"]["frac"] = roofline["fp64"]["achieved_tflops"] / 37.2
+                         "peak_tflops": FP64_PEAK, "peak_source": "measured DMMA/DFMA microbenchmark, profiles/"}}
+    roofline["fp64"]["frac"] = roofline["fp64"]["achieved_tflops"] / FP64_PEAK
 
     e2e = None
     if not args.no_e2e:
-        hloop = op2.Parloop(gk, cells, [y(op2.INC, m0), X(op2.READ, m1), x(op2.READ, m0)], location="host")
         nst = max(1, min(args.steps, 5))
-        def hstep():
-            x.data_with_halos[0] += 0.0      # host write: bumps dat_version -> H2D of x
-            y.zero()                         # host memset, as assemble() does
-            hloop()                          # H2D x, device memset y, kernel, D2H y
-            return float(y._data[0])
+        if world == 1:
+            hloop = op2.Parloop(gk, cells, [y(op2.INC, m0), X(op2.READ, m1), x(op2.READ, m0)], location="host")
+            def hstep():
+                x.data_with_halos[0] += 0.0      # host write: bumps dat_version -> H2D of x
+                y.zero()                         # assemble() zeroes the tensor (lazy here)
+                hloop()                          # H2D x, device memset y, kernel, D2H y
+                return float(y._data[0])
+            path = ("op2.Parloop(location='host') -> fdb_kernel_call(FDB_LOC_HOST): pinned host Dats, "
+                    "H2D of x and D2H of y inside the timed region")
+        else:
+            def hstep():
+                x.data_with_halos[0] += 0.0      # host write -> H2D of the local x
+                y.zero()
+                loop()                           # exchanges + kernels on device-resident mirrors
+                return float(y.data_ro[0])       # D2H of the local y
+            path = ("per rank: pinned host Dat -> H2D, halo exchanges + kernels, D2H of the local y; "
+                    "op2.Parloop(location='device') with lazy host sync")
         hstep()
+        barrier()
         t0 = time.perf_counter()
         for _ in range(nst):
             hstep()
-        t = (time.perf_counter() - t0) / nst
-        e2e = {"value": ndof / t, "unit": "DoFs/s", "h2d_bytes_per_step": x.nbytes,
-               "d2h_bytes_per_step": y.nbytes, "ms_per_step": t * 1e3, "steps": nst,
-               "path": "op2.Parloop(location='host') -> fdb_kernel_call(FDB_LOC_HOST): pinned host "
-                       "Dats, includes the host-side zero of y"}
+        barrier()
+        t = maxreduce((time.perf_counter() - t0) / nst)
+        e2e = {"value": ndof_global / t, "unit": "DoFs/s", "h2d_bytes_per_step": x.nbytes,
+               "d2h_bytes_per_step": y.nbytes, "ms_per_step": t * 1e3, "steps": nst, "path": path,
+               "bytes_are": "per rank"}
 
+    if rank != 0:
+        return
     line = {
-        "metric": METRIC, "value": value, "unit": "DoFs/s", "n_gpus": 1, "steps": args.steps,
+        "metric": METRIC, "value": value, "unit": "DoFs/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"Poisson CG{p} 1-form assemble(action(a,u)) on {n}^3 extruded hexes "
-                               f"({mesh.num_cells} cells, {ndof} DoFs), Q1 geometry warp={args.warp}, "
+                               f"({n ** 3} cells, {ndof_global} DoFs), Q1 geometry warp={args.warp}, "
                                f"base-cell order={'lexicographic' if args.permute < 0 else 'random seed %d' % args.permute}",
                    "quadrature": f"Gauss-Legendre {p + 1}^3 (dx(degree={2 * p}))",
-                   "l2": "inputs (x,y: %.1f GB) exceed the 126 MB L2; no flush needed" % (2 * 8 * ndof / 1e9),
+                   "parallelism": f"{world} slab(s) along x, NCCL halo exchange of one {n * p + 1}^2-dof face per neighbour"
+                                  if world > 1 else "single GPU",
+                   "l2": "inputs (x,y: %.1f GB per rank) exceed the 126 MB L2; no flush needed"
+                         % (2 * 8 * V.node_count / 1e9),
                    "setup_s": t_setup},
         "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline,
     }
     if e2e:
         line["e2e"] = e2e
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:
         line["cpu_baseline"] = cpu_baseline(args, args.cpu_seconds)
     print(json.dumps(line))
 

@@ -90,6 +90,19 @@ SIGNATURES = {
     "fdb_vec_scale": (C.c_int, [C.c_size_t, C.c_double, C.c_void_p]),
     "fdb_vec_dot": (C.c_int, [C.c_size_t, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]),
     "fdb_vec_pointwise_mult": (C.c_int, [C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fdb_comm_get_unique_id": (C.c_int, [C.c_char_p]),
+    "fdb_comm_init": (C.c_int, [C.c_int, C.c_int, C.c_char_p]),
+    "fdb_comm_finalize": (C.c_int, []),
+    "fdb_comm_rank": (C.c_int, []),
+    "fdb_comm_size": (C.c_int, []),
+    "fdb_halo_create": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_int, C.POINTER(C.c_void_p)]),
+    "fdb_halo_destroy": (C.c_int, [C.c_void_p]),
+    "fdb_halo_global_to_local_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "fdb_halo_global_to_local_end": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "fdb_halo_local_to_global_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "fdb_halo_local_to_global_end": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "fdb_allreduce": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "fdb_timer_create": (C.c_int, [C.POINTER(C.c_void_p)]),
     "fdb_timer_start": (C.c_int, [C.c_void_p]),
     "fdb_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
+
 #include <string>
 
 #include "../../include/fdb200.h"

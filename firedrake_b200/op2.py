@@ -137,11 +137,15 @@ class Subset(Set):
 
 
 class DataSet:
-    def __init__(self, iter_set: Set, dim=1, name=None):
+    """``halo``: a firedrake_b200.halo.Halo describing which rows of the set
+    are ghost copies (reference pyop2/types/dataset.py + firedrake/halo.py)."""
+
+    def __init__(self, iter_set: Set, dim=1, name=None, halo=None):
         self.set = iter_set
         self.dim = (dim,) if isinstance(dim, (int, np.integer)) else tuple(dim)
         self.cdim = int(np.prod(self.dim))
         self.name = name or "dset"
+        self.halo = halo
 
 
 def _as_dataset(s):
@@ -264,6 +268,7 @@ class Dat:
         self._dev_valid = False
         self._is_zero = data is None
         self.halo_valid = True
+        self.frozen_halo = False     # pyop2/types/dat.py:680-712 (skip l2g inside an assembly)
 
     # -- shape helpers
     @property
@@ -303,6 +308,7 @@ class Dat:
         self.increment_dat_version()
         self._dev_valid = False
         self._is_zero = False
+        self.halo_valid = False      # pyop2/types/dat.py:622-678
         return self._data[:self.dataset.set.size]
 
     @property
@@ -602,8 +608,25 @@ class Parloop:
             out._dev_valid = False
 
     def __call__(self):
+        """pyop2/parloop.py:243-260: halo begin -> core -> halo end -> owned ->
+        local-to-global reduce of INC Dats."""
+        reads = [a.data for a in self.args
+                 if a.access == READ and isinstance(a.data, Dat) and a.data.dataset.halo is not None
+                 and not a.data.halo_valid]
+        if reads and self.location != "device":
+            raise NotImplementedError("halo exchanges run on device-resident Dats")
+        for d in reads:
+            d.dataset.halo.global_to_local_begin(d)
         self._compute(self.iterset.core_part)
+        for d in reads:
+            d.dataset.halo.global_to_local_end(d)
         self._compute(self.iterset.owned_part)
+        for a in self.args:
+            d = a.data
+            if a.access == INC and isinstance(d, Dat) and d.dataset.halo is not None \
+                    and not d.frozen_halo:
+                d.dataset.halo.local_to_global_begin(d)
+                d.dataset.halo.local_to_global_end(d)
 
     compute = __call__
 

@@ -56,16 +56,32 @@ class ExtrudedHexMesh:
     """
 
     def __init__(self, nx, ny, nz, Lx=1.0, Ly=1.0, Lz=1.0, warp=0.0,
-                 permute_seed=None):
+                 permute_seed=None, ix0=0, nx_global=None, ghost_left=False):
+        """``ix0``/``nx_global``/``ghost_left`` describe one slab of a larger
+        mesh partitioned along x (firedrake_b200.partition): this mesh holds
+        base cells ix0 .. ix0+nx-1 of an nx_global-wide mesh of x-extent Lx;
+        with ``ghost_left`` the entities on the slab's left face belong to the
+        neighbouring rank: their dof columns are numbered LAST (the ghost tail
+        of pyop2/types/set.py:38-52) and the cells touching them come last in
+        the cell order (owned-but-not-core cells, pyop2/types/set.py:119-125)."""
         self.nx, self.ny, self.nz = int(nx), int(ny), int(nz)
         self.Lx, self.Ly, self.Lz = float(Lx), float(Ly), float(Lz)
         self.warp = float(warp)
+        self.ix0 = int(ix0)
+        self.nx_global = int(nx_global) if nx_global is not None else self.nx
+        self.ghost_left = bool(ghost_left)
         nx, ny = self.nx, self.ny
         ncell = nx * ny
         ix, iy = np.divmod(np.arange(ncell, dtype=np.int64), ny)
         if permute_seed is not None:
             perm = np.random.default_rng(permute_seed).permutation(ncell)
             ix, iy = ix[perm], iy[perm]
+        if self.ghost_left:
+            order = np.argsort(ix == 0, kind="stable")      # ix == 0 cells last
+            ix, iy = ix[order], iy[order]
+            self.num_core_cells = int((ix != 0).sum())
+        else:
+            self.num_core_cells = ncell
         self.cell_ix, self.cell_iy = ix, iy
         self.num_base_cells = ncell
         self.layers = self.nz + 1          # node layers, as in ExtrudedSet
@@ -88,6 +104,19 @@ class ExtrudedHexMesh:
         self.closure = clo
         self.num_entities = NV + NEy + NEx + ncell
         self._rank = _first_touch_rank(clo, self.num_entities)
+        self.ghost_entities = np.zeros(0, dtype=np.int64)
+        if self.ghost_left:
+            # canonical plane order: vertices iy = 0..ny, then y-edges iy = 0..ny-1
+            ghosts = self.plane_entities(0)
+            is_ghost = np.zeros(self.num_entities, dtype=bool)
+            is_ghost[ghosts] = True
+            owned = np.nonzero(~is_ghost)[0]
+            owned = owned[np.argsort(self._rank[owned], kind="stable")]
+            rank = np.empty(self.num_entities, dtype=np.int64)
+            rank[owned] = np.arange(len(owned))
+            rank[ghosts] = len(owned) + np.arange(len(ghosts))
+            self._rank = rank
+            self.ghost_entities = ghosts
         self._fs_cache = {}
         # coordinates: VectorFunctionSpace(Q1 x P1, dim=3)
         V1 = self.function_space(1)
@@ -113,6 +142,11 @@ class ExtrudedHexMesh:
     def num_cells(self):
         return self.num_base_cells * self.nz
 
+    def plane_entities(self, i):
+        """Base entities on the plane x-index ``i`` (local), canonical order."""
+        return np.concatenate([self._vertex(i, np.arange(self.ny + 1)),
+                               self._yedge(i, np.arange(self.ny))]).astype(np.int64)
+
     def function_space(self, degree: int) -> "ExtrudedFunctionSpace":
         if degree not in self._fs_cache:
             self._fs_cache[degree] = ExtrudedFunctionSpace(self, degree)
@@ -135,7 +169,7 @@ class ExtrudedHexMesh:
         X = np.empty((V1.node_count, 3), dtype=ScalarType)
         lay = np.arange(nz + 1, dtype=np.int64)
         idx = (start[:, None] + lay[None, :]).ravel()
-        X[idx, 0] = np.repeat(vi * (self.Lx / nx), nz + 1)
+        X[idx, 0] = np.repeat((vi + self.ix0) * (self.Lx / self.nx_global), nz + 1)
         X[idx, 1] = np.repeat(vj * (self.Ly / ny), nz + 1)
         X[idx, 2] = np.tile(lay * (self.Lz / nz), NV)
         return self._apply_warp(X)
@@ -162,7 +196,10 @@ class ExtrudedFunctionSpace:
         ent_start[order] = start_sorted
         self._ent_start = ent_start
         self._ent_nb = nb
+        self._ent_colsize = colsize
         self.node_count = int(colsize.sum())
+        self.ghost_node_count = int(colsize[mesh.ghost_entities].sum())
+        self.owned_node_count = self.node_count - self.ghost_node_count
         if self.node_count >= 2 ** 31:
             raise ValueError("node count exceeds int32 IntType")
         ix, iy = mesh.cell_ix, mesh.cell_iy
@@ -228,6 +265,33 @@ class ExtrudedFunctionSpace:
                                        * (xi[az] if bz else 1 - xi[az]))
                                 pt += wgt * XV[:, (bx * 2 + by) * 2 + bz, :]
                     out[full[:, (ax * n + ay) * n + az]] = pt
+        return out
+
+    def plane_nodes(self, i):
+        """All nodes on the plane x-index ``i`` in canonical order (entity by
+        entity, bottom to top): the send/recv lists of the slab halo."""
+        ents = self.mesh.plane_entities(i)
+        st, sz = self._ent_start[ents], self._ent_colsize[ents]
+        return np.concatenate([np.arange(a, a + b) for a, b in zip(st, sz)]).astype(IntType)
+
+    def dof_lattice(self):
+        """Integer position of every node on the global p-refined lattice,
+        (node_count, 3): identifies dofs across partitions (tests)."""
+        mesh, n, p = self.mesh, self.n, self.degree
+        a2pos = np.array([0, n - 1] + list(range(1, n - 1)))
+        full = self.full_cell_node_list().astype(np.int64)
+        nz = mesh.nz
+        cix = np.repeat(mesh.cell_ix + mesh.ix0, nz)
+        ciy = np.repeat(mesh.cell_iy, nz)
+        ciz = np.tile(np.arange(nz), mesh.num_base_cells)
+        out = np.empty((self.node_count, 3), dtype=np.int64)
+        for ax in range(n):
+            for ay in range(n):
+                for az in range(n):
+                    idx = full[:, (ax * n + ay) * n + az]
+                    out[idx, 0] = cix * p + a2pos[ax]
+                    out[idx, 1] = ciy * p + a2pos[ay]
+                    out[idx, 2] = ciz * p + a2pos[az]
         return out
 
     def boundary_nodes(self, sub_domain):

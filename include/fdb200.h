@@ -189,6 +189,39 @@ int fdb_vec_scale(size_t n, double a, double *x);
 int fdb_vec_dot(size_t n, const double *x, const double *y, double *out);
 int fdb_vec_pointwise_mult(size_t n, const double *x, const double *y, double *w);
 
+/* ---------------------------------------------------- communicator and halos
+ * One process per GPU.  The NCCL communicator replaces the MPI communicator of
+ * pyop2/mpi.py; the 128-byte unique id is created on rank 0 and distributed by
+ * the host launcher (torch.distributed / MPI / a file -- plumbing).
+ *
+ * A halo replaces firedrake.halo.Halo (firedrake/halo.py:87-172): per
+ * neighbour, `send` lists the OWNED dofs that are ghosts on that neighbour and
+ * `recv` lists MY ghost dofs owned by it (both in the same canonical order on
+ * the two sides).  Index arrays are host pointers, copied at creation.
+ *   global_to_local  : owner values -> ghost copies      (PetscSF bcast, REPLACE)
+ *   local_to_global  : ghost contributions += into owner (PetscSF reduce, SUM)
+ * begin() is asynchronous on a communication stream; kernels launched on the
+ * engine stream between begin() and end() overlap the exchange
+ * (pyop2/parloop.py:250-253). */
+int fdb_comm_get_unique_id(char *out128);
+int fdb_comm_init(int rank, int nranks, const char *id128);
+int fdb_comm_finalize(void);
+int fdb_comm_rank(void);
+int fdb_comm_size(void);
+
+typedef struct fdb_halo_s *fdb_halo_t;
+int fdb_halo_create(int nneigh, const int *ranks, const fdb_int *send_counts,
+                    const fdb_int *send_idx, const fdb_int *recv_counts, const fdb_int *recv_idx,
+                    int max_cdim, fdb_halo_t *out);
+int fdb_halo_destroy(fdb_halo_t h);
+int fdb_halo_global_to_local_begin(fdb_halo_t h, double *dat, int cdim);
+int fdb_halo_global_to_local_end(fdb_halo_t h, double *dat, int cdim);
+int fdb_halo_local_to_global_begin(fdb_halo_t h, double *dat, int cdim);
+int fdb_halo_local_to_global_end(fdb_halo_t h, double *dat, int cdim);
+/* in-place all-reduce of n doubles on the device, op 0 sum / 1 min / 2 max
+ * (pyop2/parloop.py:411-442 Iallreduce of Globals) */
+int fdb_allreduce(double *dev, int n, int op);
+
 /* ------------------------------------------------------------------ timing
  * CUDA events on the engine stream (the stream every kernel above is launched
  * on), for bench.py. */

@@ -1,0 +1,67 @@
+"""torchrun worker: distributed device action (NCCL halos) vs the serial oracle.
+Run by tests/test_halo_gpu.py with one process per GPU."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from firedrake_b200 import op2                              # noqa: E402
+from firedrake_b200.fiat_lite import interval_element       # noqa: E402
+from firedrake_b200.halo import Halo, comm_init_from_env    # noqa: E402
+from firedrake_b200.partition import SlabPartition          # noqa: E402
+from firedrake_b200.utility_meshes import ExtrudedHexMesh   # noqa: E402
+from oracle import oracle                                   # noqa: E402
+
+rank, world, dist = comm_init_from_env()
+worst = 0.0
+for p, (nx, ny, nz) in [(1, (6, 4, 5)), (3, (7, 5, 9)), (2, (9, 3, 4))]:
+    part = SlabPartition(nx, ny, nz, p, rank, world, warp=0.05)
+    mesh, V = part.mesh, part.V
+    halo = Halo(part.neighbours)
+    cells = op2.ExtrudedSet(op2.Set(part.cell_sizes), mesh.layers)
+    nodes = op2.Set(part.node_sizes)
+    vnodes = op2.Set(mesh.coord_space.node_count)
+    m0 = op2.Map(cells, nodes, V.arity, V.cell_node_map, offset=V.offset)
+    m1 = op2.Map(cells, vnodes, 8, mesh.coord_map, offset=mesh.coord_offset)
+    dn = op2.DataSet(nodes, 1, halo=halo)
+    lat = V.dof_lattice()
+    f = lambda Lq: np.sin(0.37 * Lq[:, 0]) + 0.11 * Lq[:, 1] * Lq[:, 2] - 0.05 * Lq[:, 0] * Lq[:, 2]
+    xv = f(lat)
+    xv[V.owned_node_count:] = 1e30            # stale ghosts: the exchange must repair them
+    x = op2.Dat(dn, xv)
+    x.halo_valid = False
+    y = op2.Dat(dn)
+    X = op2.Dat(op2.DataSet(vnodes, 3), mesh.coordinates)
+    k = op2.Kernel("helmholtz", degree=p, alpha=1.0, beta=0.5)
+    op2.par_loop(k, cells, y(op2.INC, m0), X(op2.READ, m1), x(op2.READ, m0))
+    gm = ExtrudedHexMesh(nx, ny, nz, warp=0.05)
+    gV = gm.function_space(p)
+    glat = gV.dof_lattice()
+    gy = np.zeros(gV.node_count)
+    oracle.action_extruded(interval_element(p), 0, gm.num_base_cells, [0, gm.layers], gy,
+                           gm.coordinates, f(glat), gV.cell_node_map, gV.offset, gm.coord_map,
+                           gm.coord_offset, alpha=1.0, beta=0.5)
+    key = lambda Lq: (Lq[:, 0] * 1000 + Lq[:, 1]) * 1000 + Lq[:, 2]
+    lookup = dict(zip(key(glat).tolist(), gy.tolist()))
+    no = V.owned_node_count
+    ref = np.array([lookup[kk] for kk in key(lat[:no]).tolist()])
+    err = np.abs(y.data_ro[:no] - ref).max() / np.abs(gy).max()
+    worst = max(worst, err)
+    # global reduction (C3): x.x summed over owned dofs of all ranks
+    xo = op2.Dat(op2.Set(no), f(lat)[:no])
+    import ctypes as C
+    from firedrake_b200 import _lib
+    L = _lib.lib()
+    loc = xo.inner(xo)
+    d = op2.DeviceArray.from_host(np.array([loc]))
+    _lib.check(L.fdb_allreduce(d.ptr, 1, 0))
+    tot = d.to_host(np.zeros(1))[0]
+    assert abs(tot - (f(glat) ** 2).sum()) < 1e-9 * abs(tot), (tot, (f(glat) ** 2).sum())
+print(f"rank {rank}/{world}: worst rel err {worst:.2e}")
+assert worst < 1e-12
+if dist is not None:
+    dist.barrier()
+print("HALO_OK")

@@ -1,0 +1,310 @@
+"""Pins the CPU oracle (oracle/) against every value-level anchor the reference
+holds for this path -- golden arrays at the PyOP2
+boundary, and the analytic invariants of the Firedrake regression tests --
+plus an independent dense NumPy evaluation of the element tensors.  CPU only.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from firedrake_b200.fiat_lite import gauss_legendre, gll_points, interval_element
+from firedrake_b200.utility_meshes import ExtrudedHexMesh, UnitSquareTriMesh
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return json.load(open(os.path.join(HERE, "golden", "pyop2_test_matrices.json")))
+
+
+def dense(rowptr, colidx, vals, n):
+    A = np.zeros((n, n))
+    for r in range(n):
+        A[r, colidx[rowptr[r]:rowptr[r + 1]]] = vals[rowptr[r]:rowptr[r + 1]]
+    return A
+
+
+# ---- 1. PyOP2 golden arrays (reference tests/pyop2/test_matrices.py:637-658)
+def test_pyop2_mass_matrix_and_rhs_golden(oracle, golden):
+    cmap = np.array(golden["elem_node_map"], dtype=np.int32)
+    coords = np.array(golden["coords"])
+    tab = (6, np.ascontiguousarray(golden["CG1"], dtype=float),
+           np.ascontiguousarray(golden["d_CG1"], dtype=float), np.array(golden["w"]))
+    rowptr, colidx = oracle.build_sparsity(4, cmap)
+    vals = np.zeros(len(colidx))
+    oracle.tri_matrix("mass", 0, 2, rowptr, colidx, vals, coords, cmap, tab, use_abs=0)
+    M = dense(rowptr, colidx, vals, 4)
+    np.testing.assert_allclose(M, np.array(golden["expected_matrix"]), atol=golden["expected_matrix_eps"])
+    b = np.zeros(4)
+    oracle.tri_rhs(0, 2, b, coords, np.array(golden["f"]), cmap, tab, use_abs=0)
+    np.testing.assert_allclose(b, np.array(golden["expected_rhs"]), rtol=golden["expected_rhs_eps"])
+    # test_solve (:660-666): M x = b recovers f
+    np.testing.assert_allclose(np.linalg.solve(M, b), golden["f"], rtol=1e-8)
+
+
+# ---- 2. wrapper semantics: indirect INC, extruded layer loop
+def test_indirect_inc_counts(oracle):
+    """reference tests/pyop2/test_indirect_loop.py:150-156: every element
+    increments one shared entry -> nelems."""
+    nelems = 4096
+    cmap = np.zeros((nelems, 1), dtype=np.int32)
+    u = np.zeros(1)
+    oracle.indirect_inc(0, nelems, cmap, np.ones(nelems), u)
+    assert u[0] == nelems
+
+
+def test_extruded_layer_loop_and_offsets(oracle):
+    """reference tests/pyop2/test_extrusion.py:363-370 (a direct INC over an
+    ExtrudedSet with 10 node layers touches each entry layers-1 = 9 times) and
+    pyop2/codegen/builder.py:100-123 (index = map + offset*layer)."""
+    mesh = ExtrudedHexMesh(3, 2, 9)
+    V = mesh.function_space(1)
+    el = interval_element(1)
+    # mass action on ones: each cell adds its volume share; column sums tell
+    # how many layers were visited
+    y = np.zeros(V.node_count)
+    oracle.action_extruded(el, 0, mesh.num_base_cells, [0, mesh.layers], y, mesh.coordinates,
+                           np.ones(V.node_count), V.cell_node_map, V.offset, mesh.coord_map,
+                           mesh.coord_offset, alpha=0.0, beta=1.0)
+    assert abs(y.sum() - 1.0) < 1e-13
+    full = V.full_cell_node_list()
+    assert full.shape == (3 * 2 * 9, 8)
+    # offsets: P1 columns advance by one node per layer
+    assert np.all(V.offset == 1)
+    np.testing.assert_array_equal(full[1] - full[0], V.offset)
+
+
+def test_extruded_dof_layout_q3():
+    """Column layout of SURVEY.md section 9.3: Q3 x P3 vertex / edge / face
+    columns have layer strides 3 / 6 / 12 and hold n0*L + n1*(L-1) dofs."""
+    nz = 5
+    mesh = ExtrudedHexMesh(2, 2, nz)
+    V = mesh.function_space(3)
+    assert sorted(set(V.offset.tolist())) == [3, 6, 12]
+    assert V.node_count == (2 * 3 + 1) ** 2 * (nz * 3 + 1)
+    full = V.full_cell_node_list()
+    # every node is reached, the top of layer l is the bottom of layer l+1
+    assert np.array_equal(np.unique(full), np.arange(V.node_count))
+    n = 4
+    for b in range(n * n):
+        top = full[0::nz][:, b * n + 1]       # layer 0, vertical dof 1 (top vertex)
+        bot_next = full[1::nz][:, b * n + 0]  # layer 1, vertical dof 0
+        assert np.array_equal(top, bot_next)
+
+
+# ---- 3. independent dense evaluation of the element tensors
+def dense_element_matrix(p, X, alpha, beta):
+    """B^T D B with explicitly tabulated 3-D basis gradients (NumPy)."""
+    el = interval_element(p)
+    n, B, D, wq, xq = el.ndof, el.B, el.D, el.wq, el.xq
+    nd = n ** 3
+    A = np.zeros((nd, nd))
+    for qx in range(n):
+        for qy in range(n):
+            for qz in range(n):
+                xi = np.array([xq[qx], xq[qy], xq[qz]])
+                J = np.zeros((3, 3))
+                for bx in (0, 1):
+                    for by in (0, 1):
+                        for bz in (0, 1):
+                            s = [(xi[d] if b else 1 - xi[d]) for d, b in enumerate((bx, by, bz))]
+                            ds = [(1.0 if b else -1.0) for b in (bx, by, bz)]
+                            g = np.array([ds[0] * s[1] * s[2], s[0] * ds[1] * s[2], s[0] * s[1] * ds[2]])
+                            J += np.outer(X[(bx * 2 + by) * 2 + bz], g)
+                K = np.linalg.inv(J)
+                dw = abs(np.linalg.det(J)) * wq[qx] * wq[qy] * wq[qz]
+                gref = np.zeros((nd, 3))
+                val = np.zeros(nd)
+                for ax in range(n):
+                    for ay in range(n):
+                        for az in range(n):
+                            i = (ax * n + ay) * n + az
+                            gref[i] = [D[qx, ax] * B[qy, ay] * B[qz, az],
+                                       B[qx, ax] * D[qy, ay] * B[qz, az],
+                                       B[qx, ax] * B[qy, ay] * D[qz, az]]
+                            val[i] = B[qx, ax] * B[qy, ay] * B[qz, az]
+                G = gref @ K                      # physical gradients
+                A += dw * (alpha * G @ G.T + beta * np.outer(val, val))
+    return A
+
+
+@pytest.mark.parametrize("p", [1, 2, 3])
+def test_cell_kernels_vs_dense_numpy(oracle, p):
+    rng = np.random.default_rng(p)
+    X = np.array([[bx, by, bz] for bx in (0, 1) for by in (0, 1) for bz in (0, 1)], dtype=float)
+    X = X * [1.0, 0.7, 1.3] + 0.12 * rng.standard_normal((8, 3))      # non-affine hex
+    el = interval_element(p)
+    for alpha, beta in [(1.0, 0.0), (0.0, 1.0), (1.0, 1.0)]:
+        Aref = dense_element_matrix(p, X, alpha, beta)
+        A = oracle.cell_matrix(el, X.ravel(), alpha, beta)
+        scale = np.abs(Aref).max()
+        assert np.abs(A - Aref).max() < 1e-13 * scale
+        w = rng.standard_normal(el.ndof ** 3)
+        y = oracle.cell_action(el, X.ravel(), w, alpha, beta)
+        assert np.abs(y - Aref @ w).max() < 1e-12 * scale * np.abs(w).max()
+        assert np.abs(A - A.T).max() < 1e-13 * scale              # symmetry
+
+
+def test_tabulation_tables():
+    for p in range(1, 6):
+        el = interval_element(p)
+        assert np.allclose(el.B.sum(axis=1), 1.0, atol=1e-14)       # partition of unity
+        assert np.allclose(el.D.sum(axis=1), 0.0, atol=1e-12)
+        assert abs(el.wq.sum() - 1.0) < 1e-15
+        # nodes are GLL points in entity order: endpoints first
+        assert el.nodes[0] == 0.0 and el.nodes[1] == 1.0
+        assert np.allclose(np.sort(el.nodes), gll_points(p))
+        # the rule integrates degree 2p+1 exactly
+        x, w = gauss_legendre(p + 1)
+        assert abs((w * x ** (2 * p + 1)).sum() - 1.0 / (2 * p + 2)) < 1e-15
+
+
+# ---- 4. Firedrake regression invariants
+def assemble_matrix(oracle, mesh, V, p, alpha, beta, row_lgmap=None, col_lgmap=None):
+    rowptr, colidx = oracle.build_sparsity(V.node_count, V.cell_node_map, V.offset, mesh.nz)
+    vals = np.zeros(len(colidx))
+    oracle.matrix_extruded(interval_element(p), 0, mesh.num_base_cells, [0, mesh.layers], rowptr,
+                           colidx, vals, mesh.coordinates, V.cell_node_map, V.offset,
+                           mesh.coord_map, mesh.coord_offset, row_lgmap, col_lgmap, alpha, beta)
+    return rowptr, colidx, vals
+
+
+def action(oracle, mesh, V, p, x, alpha, beta):
+    y = np.zeros(V.node_count)
+    oracle.action_extruded(interval_element(p), 0, mesh.num_base_cells, [0, mesh.layers], y,
+                           mesh.coordinates, x, V.cell_node_map, V.offset, mesh.coord_map,
+                           mesh.coord_offset, alpha=alpha, beta=beta)
+    return y
+
+
+@pytest.mark.parametrize("p", [1, 2, 3])
+def test_mass_action_integrates_x(oracle, p):
+    """reference tests/firedrake/regression/test_assemble.py:60-73:
+    sum(assemble(action(M, f))) == 0.5 for f = x on the unit domain (1e-12)."""
+    mesh = ExtrudedHexMesh(3, 4, 2, warp=0.04)
+    V = mesh.function_space(p)
+    f = V.dof_coordinates()[:, 0].copy()
+    # integral of x over the unit cube, warp vanishes on the boundary but moves
+    # interior mass: compare against the warped-mesh value from quadrature
+    y = action(oracle, mesh, V, p, f, 0.0, 1.0)
+    ref_mesh = ExtrudedHexMesh(3, 4, 2, warp=0.0)
+    Vr = ref_mesh.function_space(p)
+    yr = action(oracle, ref_mesh, Vr, p, Vr.dof_coordinates()[:, 0].copy(), 0.0, 1.0)
+    assert abs(yr.sum() - 0.5) < 1e-12
+    # divergence theorem: int x dV = int x^2/2 n_x dS, and the warp is zero on
+    # the boundary, so the warped value is 0.5 as well
+    assert abs(y.sum() - 0.5) < 1e-12
+
+
+@pytest.mark.parametrize("p", [1, 2])
+@pytest.mark.parametrize("bcs", [False, True])
+def test_assembled_matvec_equals_matfree_action(oracle, p, bcs):
+    """reference tests/firedrake/regression/test_matrix_free.py:98-127:
+    A.mult(x) of the assembled matrix == the matrix-free action, with and
+    without Dirichlet conditions.  BC semantics (SURVEY.md section 8a row
+    A6/A10/A12): masked rows/cols (lgmap = -1) are dropped, then the diagonal
+    is set to 1; matrix-free: zero the BC entries of x, apply, then copy x on
+    the BC rows."""
+    mesh = ExtrudedHexMesh(3, 3, 3, warp=0.05, permute_seed=2)
+    V = mesh.function_space(p)
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal(V.node_count)
+    lg = None
+    if bcs:
+        bnodes = np.union1d(V.boundary_nodes("bottom"), V.boundary_nodes("top"))
+        lg = np.arange(V.node_count, dtype=np.int32)
+        lg[bnodes] = -1
+    rowptr, colidx, vals = assemble_matrix(oracle, mesh, V, p, 1.0, 1.0, lg, lg)
+    A = dense(rowptr, colidx, vals, V.node_count)
+    if bcs:
+        A[bnodes, bnodes] = 1.0                       # set_local_diagonal_entries
+        xin = x.copy()
+        xin[bnodes] = 0.0
+        y = action(oracle, mesh, V, p, xin, 1.0, 1.0)
+        y[bnodes] = x[bnodes]
+    else:
+        y = action(oracle, mesh, V, p, x, 1.0, 1.0)
+    assert np.abs(A @ x - y).max() < 1e-12 * np.abs(y).max()
+    assert np.abs(A - A.T).max() < 1e-13 * np.abs(A).max()
+
+
+def test_poisson_strong_bcs_extrusion_exact(oracle):
+    """reference tests/firedrake/extrusion/test_poisson_strong_bcs_extrusion.py:
+    21-52: u = 42 z is in the space, so (K u)_i = 0 on every row that is not on
+    the bottom/top Dirichlet boundary (natural BCs on the sides)."""
+    for p in (1, 2, 3):
+        mesh = ExtrudedHexMesh(3, 2, 4, warp=0.0)
+        V = mesh.function_space(p)
+        u = 42.0 * V.dof_coordinates()[:, 2]
+        r = action(oracle, mesh, V, p, u, 1.0, 0.0)
+        interior = np.ones(V.node_count, bool)
+        interior[np.union1d(V.boundary_nodes("bottom"), V.boundary_nodes("top"))] = False
+        assert np.abs(r[interior]).max() < 1e-11
+
+
+def test_poisson_nullspace_and_rowsums(oracle):
+    mesh = ExtrudedHexMesh(3, 3, 2, warp=0.06)
+    V = mesh.function_space(2)
+    rowptr, colidx, vals = assemble_matrix(oracle, mesh, V, 2, 1.0, 0.0)
+    A = dense(rowptr, colidx, vals, V.node_count)
+    assert np.abs(A.sum(axis=1)).max() < 1e-12 * np.abs(A).max()
+    M = dense(*assemble_matrix(oracle, mesh, V, 2, 0.0, 1.0), V.node_count)
+    assert abs(M.sum() - 1.0) < 1e-13                     # 1^T M 1 = |Omega|
+    # diagonal == Mat diagonal (reference test_assemble.py:188-206): action on e_i
+    e = np.zeros(V.node_count)
+    e[7] = 1.0
+    assert abs(action(oracle, mesh, V, 2, e, 1.0, 0.0)[7] - A[7, 7]) < 1e-13 * abs(A[7, 7])
+
+
+def test_sparsity_semantics(oracle):
+    """reference pyop2/sparsity.pyx:106-160, 198-204, 347-373: union of
+    rowmap x colmap over cells and layers, diagonal always allocated."""
+    mesh = ExtrudedHexMesh(2, 1, 3)
+    V = mesh.function_space(1)
+    rowptr, colidx = oracle.build_sparsity(V.node_count, V.cell_node_map, V.offset, mesh.nz)
+    full = V.full_cell_node_list()
+    pat = set()
+    for row in full:
+        for i in row:
+            for j in row:
+                pat.add((int(i), int(j)))
+    for r in range(V.node_count):
+        pat.add((r, r))
+    got = {(r, int(c)) for r in range(V.node_count) for c in colidx[rowptr[r]:rowptr[r + 1]]}
+    assert got == pat
+    # columns sorted within rows (binary search in MatSetValues restatement)
+    for r in range(V.node_count):
+        c = colidx[rowptr[r]:rowptr[r + 1]]
+        assert np.all(np.diff(c) > 0)
+
+
+def test_config1_p1_triangles(oracle):
+    """BASELINE.json configs[0]: Poisson CG1 on UnitSquareMesh(64, 64),
+    bilinear form -> CSR on the CPU.  Pins: 8192 cells / 4225 dofs, symmetry,
+    constants in the null space, x^T K x = |grad x|^2 area for linear x, and
+    matrix-vs-action agreement."""
+    mesh = UnitSquareTriMesh(64, 64)
+    assert mesh.num_cells == 8192 and mesh.node_count == 4225
+    tab = oracle.tri_table_fiat()
+    rowptr, colidx = oracle.build_sparsity(mesh.node_count, mesh.cell_node_map)
+    vals = np.zeros(len(colidx))
+    oracle.tri_matrix("laplace", 0, mesh.num_cells, rowptr, colidx, vals, mesh.coordinates,
+                      mesh.cell_node_map, tab)
+    import scipy.sparse as sp
+    K = sp.csr_matrix((vals, colidx, rowptr), shape=(4225, 4225))
+    assert abs(K - K.T).max() < 1e-14
+    assert np.abs(K @ np.ones(4225)).max() < 1e-12
+    u = 3 * mesh.coordinates[:, 0] - 2 * mesh.coordinates[:, 1]
+    assert abs(u @ (K @ u) - 13.0) < 1e-11
+    y = np.zeros(4225)
+    x = np.random.default_rng(0).standard_normal(4225)
+    oracle.tri_action(0, mesh.num_cells, y, mesh.coordinates, x, mesh.cell_node_map, tab)
+    assert np.abs(y - K @ x).max() < 1e-12 * np.abs(y).max()
+    # mass: 1^T M 1 = 1, and the P1 mass matrix of the reference golden test
+    vals[:] = 0
+    oracle.tri_matrix("mass", 0, mesh.num_cells, rowptr, colidx, vals, mesh.coordinates,
+                      mesh.cell_node_map, tab)
+    assert abs(vals.sum() - 1.0) < 1e-13
