@@ -82,6 +82,15 @@ SIGNATURES = {
     "fdb_kernel_create": (C.c_int, [C.POINTER(KernelDesc), C.POINTER(C.c_void_p)]),
     "fdb_kernel_destroy": (C.c_int, [C.c_void_p]),
     "fdb_kernel_call": (C.c_int, [C.c_void_p, C.POINTER(CallArgs)]),
+    "fdb_mat_create": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_int, C.c_void_p, C.c_int,
+                                 C.POINTER(C.c_void_p)]),
+    "fdb_mat_destroy": (C.c_int, [C.c_void_p]),
+    "fdb_mat_nnz": (C.c_int, [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_int32)]),
+    "fdb_mat_zero": (C.c_int, [C.c_void_p]),
+    "fdb_mat_set_lgmaps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fdb_mat_set_diagonal": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_double]),
+    "fdb_mat_mult": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fdb_mat_get_csr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fdb_dat_zero_nodes": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int32]),
     "fdb_dat_set_nodes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int32]),
     "fdb_dat_set_nodes_scalar": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_int32]),

@@ -25,6 +25,7 @@
 // coordinates: cofactor rows r_k of J, det = a.(b x c), and the flux in
 // reference coordinates is  (alpha w / |det|) r_k . (sum_m r_m ghat_m).
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -46,6 +47,13 @@ struct HelmParams {
     int lay_first, lay_step; // layer = lay_first + lay_step * k
     unsigned nlay_rcp;       // floor(2^32 / nlay_items)
     int cdim;
+    // matrix mode (rank 2): CSR destination; each unit computes one column j of
+    // the element tensor as the action on the unit vector e_j
+    const long long *rowptr;
+    const int *colidx;
+    double *vals;
+    const int *row_lg;       // -1 = row dropped (Dirichlet), NULL = identity
+    const int *col_lg;
     int chunk;               // items per work chunk
     int *counter;            // device work counter (zeroed before the launch)
     double alpha, beta;
@@ -206,7 +214,7 @@ struct Unit {
     int col, layer;
 };
 
-template <int N, bool MASS, bool ATOMIC, int MINB>
+template <int N, bool MASS, bool ATOMIC, int MINB, bool MATRIX = false>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB)
 helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
 {
@@ -334,9 +342,11 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
 #pragma unroll
                 for (int j = 0; j < N; j++) g[j] = si[(part * N + j) * N + t];
             }
+            if (!MATRIX) {
 #pragma unroll
-            for (int j = 0; j < N; j++)
-                cp_async8(su + (part * N + j) * N + t, P.x + (long long)g[j] * P.cdim + u.comp);
+                for (int j = 0; j < N; j++)
+                    cp_async8(su + (part * N + j) * N + t, P.x + (long long)g[j] * P.cdim + u.comp);
+            }
         }
     };
 
@@ -398,7 +408,10 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
 #pragma unroll
             for (int x = 0; x < N; x++)
 #pragma unroll
-                for (int yy = 0; yy < N; yy++) u[x][yy] = valid ? su[(x * N + yy) * N + t] : 0.0;
+                for (int yy = 0; yy < N; yy++) {
+                    if (MATRIX) u[x][yy] = ((x * N + yy) * N + t == comp) ? 1.0 : 0.0;
+                    else u[x][yy] = valid ? su[(x * N + yy) * N + t] : 0.0;
+                }
             // ---- forward: interpolate to the quadrature points
             double tmp[N][N], U[N][N];
             apply_first<N, false>(P.B, u, tmp);          // a_x -> q_x
@@ -513,7 +526,29 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
             apply_second<N, true>(P.B, tmp, u);          // q_y -> a_y     R[ax][ay] @ a_z
 
             // ---- scatter-add, layout Z
-            if (valid) {
+            if (MATRIX) {
+                // MatSetValuesLocal(ADD_VALUES): column = trial dof `comp`, rows = this
+                // lane's test dofs; negative (BC-masked) indices are dropped
+                int gcol = valid ? si[comp] : -1;
+                if (gcol >= 0 && P.col_lg) gcol = __ldg(P.col_lg + gcol);
+                if (gcol >= 0) {
+#pragma unroll
+                    for (int x = 0; x < N; x++)
+#pragma unroll
+                        for (int yy = 0; yy < N; yy++) {
+                            int grow = si[(x * N + yy) * N + t];
+                            if (P.row_lg) grow = __ldg(P.row_lg + grow);
+                            if (grow < 0) continue;
+                            long long lo = __ldg(P.rowptr + grow), hi = __ldg(P.rowptr + grow + 1);
+                            while (hi - lo > 1) {
+                                long long mid = (lo + hi) >> 1;
+                                if (__ldg(P.colidx + mid) <= gcol) lo = mid; else hi = mid;
+                            }
+                            if (ATOMIC) atomicAdd(P.vals + lo, u[x][yy]);
+                            else P.vals[lo] += u[x][yy];
+                        }
+                }
+            } else if (valid) {
 #pragma unroll
                 for (int x = 0; x < N; x++)
 #pragma unroll
@@ -532,12 +567,12 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
     cp_async_wait<0>();
 }
 
-template <int N, bool MASS, bool ATOMIC, int MINB>
+template <int N, bool MASS, bool ATOMIC, int MINB, bool MATRIX = false>
 int launch_one(int grid_cap_per_sm, cudaStream_t st, HelmParams<N> &P, int sm_count)
 {
     using WS = WarpSmem<N>;
     constexpr int T = WARPS_PER_CTA * 32;
-    auto kern = helmholtz_action_kernel<N, MASS, ATOMIC, MINB>;
+    auto kern = helmholtz_action_kernel<N, MASS, ATOMIC, MINB, MATRIX>;
     static bool configured = false;
     static int occ = 1;
     if (!configured) {
@@ -652,7 +687,57 @@ int launch_n(fdb_kernel_s *k, fdb_int start, fdb_int end, int nlay, const fdb_in
     return 0;
 }
 
+template <int N>
+int launch_matrix_n(fdb_kernel_s *k, fdb_int start, fdb_int end, int nlay, const fdb_int *subset,
+                    fdb_mat_t mat, const double *coords, const fdb_int *map0, const fdb_int *map1)
+{
+    fdb::Context &c = fdb::ctx();
+    HelmParams<N> P;
+    memset(&P, 0, sizeof(P));
+    P.coords = coords;
+    P.map0 = map0;
+    P.map1 = map1;
+    P.off0 = k->d_off0;
+    P.off1 = k->d_off1;
+    P.cdim = N * N * N;          // one pipeline unit per trial dof
+    P.alpha = k->desc.alpha;
+    P.beta = k->desc.beta;
+    for (int i = 0; i < N * N; i++) {
+        P.B[i] = k->desc.B[i];
+        P.Dt[i] = k->Dt[i];
+    }
+    for (int i = 0; i < N; i++) {
+        P.wq[i] = k->desc.wq[i];
+        P.xq[i] = k->desc.xq[i];
+    }
+    fdb_mat_device_view(mat, &P.rowptr, &P.colidx, &P.vals, &P.row_lg, &P.col_lg);
+    P.counter = c.work_counter;
+    P.collist = subset;
+    P.col0 = start;
+    P.ncols = end - start;
+    P.nlay_items = nlay;
+    P.lay_first = 0;
+    P.lay_step = 1;
+    if (P.ncols <= 0 || nlay <= 0) return 0;
+    constexpr int DEF = (N >= 5) ? 1 : 2;
+    if (k->desc.beta != 0.0) return launch_one<N, true, true, DEF, true>(0, c.stream, P, c.sm_count);
+    return launch_one<N, false, true, DEF, true>(0, c.stream, P, c.sm_count);
+}
+
 }  // namespace
+
+int fdb_launch_helmholtz_matrix(fdb_kernel_s *k, fdb_int start, fdb_int end, int nlay,
+                                const fdb_int *subset, fdb_mat_t mat, const double *coords,
+                                const fdb_int *map0, const fdb_int *map1)
+{
+    switch (k->n1d) {
+    case 2: return launch_matrix_n<2>(k, start, end, nlay, subset, mat, coords, map0, map1);
+    case 3: return launch_matrix_n<3>(k, start, end, nlay, subset, mat, coords, map0, map1);
+    case 4: return launch_matrix_n<4>(k, start, end, nlay, subset, mat, coords, map0, map1);
+    }
+    fdb::set_error("helmholtz matrix: degree %d not instantiated (1..3)", k->n1d - 1);
+    return 1;
+}
 
 int fdb_launch_helmholtz_action(fdb_kernel_s *k, fdb_int start, fdb_int end, int nlay,
                                 const fdb_int *subset, double *y, const double *coords,

@@ -70,6 +70,13 @@ struct fdb_kernel_s {
 
 extern "C" int fdb_mirror_set_version(const void *host, uint64_t version);
 
+typedef struct fdb_mat_s *fdb_mat_t;
+int fdb_mat_device_view(fdb_mat_t m, const long long **rowptr, const fdb_int **colidx, double **vals,
+                        const fdb_int **row_lg, const fdb_int **col_lg);
+int fdb_launch_helmholtz_matrix(fdb_kernel_s *k, fdb_int start, fdb_int end, int nlay,
+                                const fdb_int *subset, fdb_mat_t mat, const double *coords,
+                                const fdb_int *map0, const fdb_int *map1);
+
 // launchers implemented in the kernel translation units
 int fdb_launch_helmholtz_action(fdb_kernel_s *k, fdb_int start, fdb_int end, int nlay,
                                 const fdb_int *subset, double *y, const double *coords,

@@ -201,9 +201,46 @@ int fdb_kernel_call(fdb_kernel_t k, const fdb_call_args *a)
         set_error("fdb_kernel_call: iteration set too large for IntType");
         return 1;
     }
-    if (k->desc.rank != 1) {
-        set_error("fdb_kernel_call: rank-2 kernels are called through fdb_mat_assemble");
-        return 1;
+    if (k->desc.rank == 2) {
+        // 2-form: args = [Mat handle (INC), coords (READ)], maps = [V map, coord map]
+        // (the reference passes the PETSc Mat handle in the same slot:
+        // pyop2/types/mat.py:621-623)
+        if (a->nargs != 2 || a->nmaps != 2) {
+            set_error("fdb_kernel_call: 2-form expects 2 args (mat, coords) and 2 maps");
+            return 1;
+        }
+        if (k->desc.cdim != 1) {
+            set_error("fdb_kernel_call: matrix assembly of vector spaces is not implemented");
+            return 1;
+        }
+        if (k->desc.scatter != FDB_SCATTER_ATOMIC) {
+            set_error("fdb_kernel_call: coloured scatter is not implemented for matrices");
+            return 1;
+        }
+        const double *dcoords;
+        const fdb_int *dm[2];
+        const fdb_int *dsub = a->subset;
+        if (a->location == FDB_LOC_HOST) {
+            void *p;
+            uint64_t ver = a->arg_versions ? a->arg_versions[1] : 0;
+            if (!a->arg_versions) fdb_mirror_drop(a->args[1]);
+            if (fdb_mirror_acquire(a->args[1], a->arg_bytes[1], ver, 1, &p)) return 1;
+            dcoords = (const double *)p;
+            for (int i = 0; i < 2; i++) {
+                if (fdb_mirror_acquire(a->maps[i], a->map_bytes[i], 0, 1, &p)) return 1;
+                dm[i] = (const fdb_int *)p;
+            }
+            if (a->subset) {
+                if (fdb_mirror_acquire(a->subset, sizeof(fdb_int) * (size_t)a->end, 0, 1, &p)) return 1;
+                dsub = (const fdb_int *)p;
+            }
+        } else {
+            dcoords = (const double *)a->args[1];
+            dm[0] = a->maps[0];
+            dm[1] = a->maps[1];
+        }
+        return fdb_launch_helmholtz_matrix(k, a->start, a->end, nlay, dsub, (fdb_mat_t)a->args[0],
+                                           dcoords, dm[0], dm[1]);
     }
     // 1-form: args = [y (INC), coords (READ), x (READ)], maps = [V map, coord map]
     if (a->nargs != 3 || a->nmaps != 2) {

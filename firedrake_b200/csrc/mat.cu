@@ -1,0 +1,289 @@
+// Device CSR matrices: sparsity construction (K7 / A8), zero, BC lgmaps and
+// diagonal (A6 / A10), SpMV, export.
+//
+// Reference semantics:
+//   * pattern = union over cells (and layers) of rowmap x colmap, the diagonal is
+//     always allocated, all entries zero-filled so later adds never allocate
+//     (pyop2/sparsity.pyx:106-160, 198-204, 347-373; pyop2/types/mat.py:741-804)
+//   * Dirichlet rows/columns are removed by local-to-global maps whose entries
+//     are -1: MatSetValuesLocal drops negative indices
+//     (firedrake/functionspaceimpl.py:854-926, pyop2/parloop.py:279-314)
+//   * afterwards the diagonal of constrained rows is set
+//     (pyop2/types/mat.py:897-937 set_local_diagonal_entries)
+// Construction: (row, col) keys of every cell -> thrust sort + unique -> CSR
+// with sorted columns per row.  The element-tensor scatter finds a position by
+// binary search inside the row (the cost model of PETSc's MatSetValues, here
+// in parallel and hitting L2).
+#include <thrust/device_ptr.h>
+#include <thrust/execution_policy.h>
+#include <thrust/scan.h>
+#include <thrust/sort.h>
+#include <thrust/unique.h>
+
+#include "common.cuh"
+
+using namespace fdb;
+
+struct fdb_mat_s {
+    fdb_int nrows = 0;
+    long long nnz = 0;
+    long long *d_rowptr = nullptr;
+    fdb_int *d_colidx = nullptr;
+    double *d_vals = nullptr;
+    fdb_int *d_row_lgmap = nullptr, *d_col_lgmap = nullptr;   // NULL = identity
+};
+
+namespace {
+
+__global__ void k_gen_keys(const fdb_int *__restrict__ map, const fdb_int *__restrict__ off,
+                           fdb_int ncols, int arity, int nlay, fdb_int nrows,
+                           unsigned long long *__restrict__ keys)
+{
+    const long long per_cell = (long long)arity * arity;
+    const long long total = (long long)ncols * nlay * per_cell;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long cell = i / per_cell;
+        int e = (int)(i - cell * per_cell);
+        int a = e / arity, b = e - a * arity;
+        fdb_int c = (fdb_int)(cell / nlay);
+        int l = (int)(cell - (long long)c * nlay);
+        unsigned long long r = map[(long long)c * arity + a] + (off ? off[a] * l : 0);
+        unsigned long long cc = map[(long long)c * arity + b] + (off ? off[b] * l : 0);
+        keys[i] = r * (unsigned long long)nrows + cc;
+    }
+    // diagonal entries
+    long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; j < nrows; j += (long long)gridDim.x * blockDim.x)
+        keys[total + j] = (unsigned long long)j * nrows + j;
+}
+
+__global__ void k_count_rows(const unsigned long long *__restrict__ keys, long long n, fdb_int nrows,
+                             long long *__restrict__ counts, fdb_int *__restrict__ colidx)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i < n; i += (long long)gridDim.x * blockDim.x) {
+        unsigned long long k = keys[i];
+        unsigned long long r = k / (unsigned long long)nrows;
+        colidx[i] = (fdb_int)(k - r * nrows);
+        atomicAdd((unsigned long long *)&counts[r], 1ull);
+    }
+}
+
+__global__ void k_spmv(fdb_int nrows, const long long *__restrict__ rowptr,
+                       const fdb_int *__restrict__ colidx, const double *__restrict__ vals,
+                       const double *__restrict__ x, double *__restrict__ y)
+{
+    // one warp per row
+    long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long r = w; r < nrows; r += nw) {
+        double s = 0.0;
+        for (long long k = rowptr[r] + lane; k < rowptr[r + 1]; k += 32) s = fma(vals[k], x[colidx[k]], s);
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) y[r] = s;
+    }
+}
+
+__global__ void k_set_diag(const long long *__restrict__ rowptr, const fdb_int *__restrict__ colidx,
+                           double *__restrict__ vals, const fdb_int *__restrict__ rows, fdb_int n,
+                           double value)
+{
+    fdb_int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fdb_int r = rows[i];
+    long long lo = rowptr[r], hi = rowptr[r + 1];
+    while (hi - lo > 1) {
+        long long mid = (lo + hi) >> 1;
+        if (colidx[mid] <= r) lo = mid; else hi = mid;
+    }
+    if (colidx[lo] == r) vals[lo] = value;
+}
+
+int grid1d(long long n)
+{
+    long long b = (n + 255) / 256;
+    long long cap = (long long)ctx().sm_count * 16;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+}  // namespace
+
+// used by the element-tensor scatter in action_hex.cu / tri_p1.cu
+int fdb_mat_device_view(fdb_mat_t m, const long long **rowptr, const fdb_int **colidx, double **vals,
+                        const fdb_int **row_lg, const fdb_int **col_lg)
+{
+    *rowptr = m->d_rowptr;
+    *colidx = m->d_colidx;
+    *vals = m->d_vals;
+    *row_lg = m->d_row_lgmap;
+    *col_lg = m->d_col_lgmap;
+    return 0;
+}
+
+extern "C" {
+
+int fdb_mat_create(fdb_int nrows, const fdb_int *map_host, fdb_int ncolumns, int arity,
+                   const fdb_int *offset_host, int nlayers, fdb_mat_t *out)
+{
+    if (require_init()) return 1;
+    if (nlayers < 1 || arity < 1 || nrows < 1) {
+        set_error("fdb_mat_create: bad sizes");
+        return 1;
+    }
+    cudaStream_t st = ctx().stream;
+    const long long npairs = (long long)ncolumns * nlayers * arity * arity + nrows;
+    size_t free_b = 0, total_b = 0;
+    FDB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    // keys + radix-sort scratch + CSR
+    if ((double)npairs * 8.0 * 2.3 > (double)free_b * 0.9) {
+        set_error("fdb_mat_create: %lld (row,col) pairs need %.1f GB to sort, %.1f GB free: assemble "
+                  "matrix-free instead (SURVEY.md fact 5)",
+                  npairs, npairs * 8.0 * 2.3 / 1e9, free_b / 1e9);
+        return 1;
+    }
+    fdb_int *d_map = nullptr, *d_off = nullptr;
+    unsigned long long *keys = nullptr;
+    FDB_CUDA(cudaMalloc(&d_map, sizeof(fdb_int) * (size_t)ncolumns * arity));
+    FDB_CUDA(cudaMemcpyAsync(d_map, map_host, sizeof(fdb_int) * (size_t)ncolumns * arity,
+                             cudaMemcpyHostToDevice, st));
+    if (offset_host) {
+        FDB_CUDA(cudaMalloc(&d_off, sizeof(fdb_int) * arity));
+        FDB_CUDA(cudaMemcpyAsync(d_off, offset_host, sizeof(fdb_int) * arity, cudaMemcpyHostToDevice, st));
+    }
+    FDB_CUDA(cudaMalloc(&keys, sizeof(unsigned long long) * (size_t)npairs));
+    k_gen_keys<<<grid1d(npairs), 256, 0, st>>>(d_map, d_off, ncolumns, arity, nlayers, nrows, keys);
+    FDB_LAUNCH_CHECK();
+    long long nnz = 0;
+    try {
+        thrust::device_ptr<unsigned long long> kp(keys);
+        thrust::sort(thrust::cuda::par.on(st), kp, kp + npairs);
+        nnz = thrust::unique(thrust::cuda::par.on(st), kp, kp + npairs) - kp;
+    } catch (const std::exception &e) {
+        set_error("fdb_mat_create: thrust failed: %s", e.what());
+        cudaFree(keys);
+        cudaFree(d_map);
+        cudaFree(d_off);
+        return 1;
+    }
+    fdb_mat_s *m = new fdb_mat_s;
+    m->nrows = nrows;
+    m->nnz = nnz;
+    FDB_CUDA(cudaMalloc(&m->d_rowptr, sizeof(long long) * ((size_t)nrows + 1)));
+    FDB_CUDA(cudaMalloc(&m->d_colidx, sizeof(fdb_int) * (size_t)nnz));
+    FDB_CUDA(cudaMalloc(&m->d_vals, sizeof(double) * (size_t)nnz));
+    FDB_CUDA(cudaMemsetAsync(m->d_rowptr, 0, sizeof(long long) * ((size_t)nrows + 1), st));
+    k_count_rows<<<grid1d(nnz), 256, 0, st>>>(keys, nnz, nrows, m->d_rowptr + 1, m->d_colidx);
+    FDB_LAUNCH_CHECK();
+    try {
+        thrust::device_ptr<long long> rp(m->d_rowptr);
+        thrust::inclusive_scan(thrust::cuda::par.on(st), rp, rp + nrows + 1, rp);
+    } catch (const std::exception &e) {
+        set_error("fdb_mat_create: scan failed: %s", e.what());
+        return 1;
+    }
+    FDB_CUDA(cudaMemsetAsync(m->d_vals, 0, sizeof(double) * (size_t)nnz, st));
+    FDB_CUDA(cudaStreamSynchronize(st));
+    cudaFree(keys);
+    cudaFree(d_map);
+    if (d_off) cudaFree(d_off);
+    *out = m;
+    return 0;
+}
+
+int fdb_mat_destroy(fdb_mat_t m)
+{
+    if (!m) return 0;
+    if (ctx().ready) {
+        cudaStreamSynchronize(ctx().stream);
+        cudaFree(m->d_rowptr);
+        cudaFree(m->d_colidx);
+        cudaFree(m->d_vals);
+        cudaFree(m->d_row_lgmap);
+        cudaFree(m->d_col_lgmap);
+    }
+    delete m;
+    return 0;
+}
+
+int fdb_mat_nnz(fdb_mat_t m, long long *nnz, fdb_int *nrows)
+{
+    if (nnz) *nnz = m->nnz;
+    if (nrows) *nrows = m->nrows;
+    return 0;
+}
+
+int fdb_mat_zero(fdb_mat_t m)
+{
+    if (require_init()) return 1;
+    FDB_CUDA(cudaMemsetAsync(m->d_vals, 0, sizeof(double) * (size_t)m->nnz, ctx().stream));
+    return 0;
+}
+
+int fdb_mat_get_csr(fdb_mat_t m, long long *rowptr, fdb_int *colidx, double *vals)
+{
+    if (require_init()) return 1;
+    cudaStream_t st = ctx().stream;
+    if (rowptr)
+        FDB_CUDA(cudaMemcpyAsync(rowptr, m->d_rowptr, sizeof(long long) * ((size_t)m->nrows + 1),
+                                 cudaMemcpyDeviceToHost, st));
+    if (colidx)
+        FDB_CUDA(cudaMemcpyAsync(colidx, m->d_colidx, sizeof(fdb_int) * (size_t)m->nnz,
+                                 cudaMemcpyDeviceToHost, st));
+    if (vals)
+        FDB_CUDA(cudaMemcpyAsync(vals, m->d_vals, sizeof(double) * (size_t)m->nnz, cudaMemcpyDeviceToHost, st));
+    FDB_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int fdb_mat_set_lgmaps(fdb_mat_t m, const fdb_int *row_lgmap_host, const fdb_int *col_lgmap_host)
+{
+    if (require_init()) return 1;
+    cudaStream_t st = ctx().stream;
+    const fdb_int *src[2] = {row_lgmap_host, col_lgmap_host};
+    fdb_int **dst[2] = {&m->d_row_lgmap, &m->d_col_lgmap};
+    for (int i = 0; i < 2; i++) {
+        if (!src[i]) {
+            if (*dst[i]) {
+                FDB_CUDA(cudaStreamSynchronize(st));
+                cudaFree(*dst[i]);
+                *dst[i] = nullptr;
+            }
+            continue;
+        }
+        if (!*dst[i]) FDB_CUDA(cudaMalloc(dst[i], sizeof(fdb_int) * (size_t)m->nrows));
+        FDB_CUDA(cudaMemcpyAsync(*dst[i], src[i], sizeof(fdb_int) * (size_t)m->nrows,
+                                 cudaMemcpyHostToDevice, st));
+    }
+    FDB_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int fdb_mat_set_diagonal(fdb_mat_t m, const fdb_int *rows_host, fdb_int n, double value)
+{
+    if (require_init()) return 1;
+    if (n <= 0) return 0;
+    cudaStream_t st = ctx().stream;
+    fdb_int *d_rows = nullptr;
+    FDB_CUDA(cudaMalloc(&d_rows, sizeof(fdb_int) * (size_t)n));
+    FDB_CUDA(cudaMemcpyAsync(d_rows, rows_host, sizeof(fdb_int) * (size_t)n, cudaMemcpyHostToDevice, st));
+    k_set_diag<<<(n + 255) / 256, 256, 0, st>>>(m->d_rowptr, m->d_colidx, m->d_vals, d_rows, n, value);
+    FDB_LAUNCH_CHECK();
+    FDB_CUDA(cudaStreamSynchronize(st));
+    cudaFree(d_rows);
+    return 0;
+}
+
+int fdb_mat_mult(fdb_mat_t m, const double *x, double *y)
+{
+    if (require_init()) return 1;
+    long long threads = (long long)m->nrows * 32;
+    k_spmv<<<grid1d(threads), 256, 0, ctx().stream>>>(m->nrows, m->d_rowptr, m->d_colidx, m->d_vals, x, y);
+    FDB_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

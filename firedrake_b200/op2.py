@@ -386,6 +386,114 @@ class Dat:
         return LegacyArg(self, access, path)
 
 
+class Sparsity:
+    """``op2.Sparsity((row_dset, col_dset), [(rmap, cmap, None)])``
+    (pyop2/types/mat.py:27-292).  Only square single-block sparsities whose row
+    and column maps coincide are supported (every form of the supported set)."""
+
+    def __init__(self, dsets, maps_and_regions, name=None):
+        if isinstance(dsets, DataSet) or isinstance(dsets, Set):
+            dsets = (dsets, dsets)
+        self.dsets = tuple(_as_dataset(d) for d in dsets)
+        if self.dsets[0].set is not self.dsets[1].set:
+            raise NotImplementedError("rectangular sparsities are not supported")
+        if any(d.cdim != 1 for d in self.dsets):
+            raise NotImplementedError("vector-valued matrices are not supported yet")
+        self.maps = []
+        for entry in maps_and_regions:
+            rmap, cmap = entry[0], entry[1]
+            if rmap is not cmap:
+                raise NotImplementedError("row and column maps must coincide")
+            if rmap.toset is not self.dsets[0].set:
+                raise MapValueError("sparsity map does not target the data set")
+            self.maps.append(rmap)
+        if len(self.maps) != 1:
+            raise NotImplementedError("exactly one (rmap, cmap) pair is supported")
+        self.name = name or "sparsity"
+
+    @property
+    def shape(self):
+        n = self.dsets[0].set.total_size
+        return (n, n)
+
+
+class Mat:
+    """``op2.Mat(sparsity)`` (pyop2/types/mat.py:607-985) backed by a device CSR
+    matrix instead of a PETSc AIJ one.  ``mat(op2.INC, (rmap, cmap), lgmaps=...)``
+    builds the parloop argument; ``lgmaps`` = ``(row_lgmap, col_lgmap)`` NumPy
+    arrays, identity except -1 on Dirichlet rows / columns."""
+    _ids = itertools.count()
+
+    def __init__(self, sparsity: Sparsity, dtype=ScalarType, name=None):
+        self.sparsity = sparsity
+        self.name = name or f"mat_{next(Mat._ids)}"
+        m = sparsity.maps[0]
+        it = m.iterset
+        nlay = (it.layers - 1) if it._extruded else 1
+        off = m.offset
+        h = C.c_void_p()
+        L = _lib.lib()
+        _lib.check(L.fdb_mat_create(sparsity.shape[0], m.values_with_halo.ctypes.data, it.total_size,
+                                    m.arity, None if off is None else off.ctypes.data, nlay,
+                                    C.byref(h)), "fdb_mat_create")
+        self.handle = h
+        self.dat_version = 0
+        nnz = C.c_longlong()
+        nr = C.c_int32()
+        L.fdb_mat_nnz(h, C.byref(nnz), C.byref(nr))
+        self.nnz = nnz.value
+        self.nrows = nr.value
+
+    def __call__(self, access, path, lgmaps=None):
+        rmap, cmap = path
+        a = LegacyArg(self, access, rmap)
+        a.lgmaps = lgmaps
+        return a
+
+    def zero(self):
+        _lib.check(_lib.lib().fdb_mat_zero(self.handle), "fdb_mat_zero")
+        self.dat_version += 1
+
+    def assemble(self):
+        """MatAssemblyBegin/End: nothing is stashed here (single address space
+        per GPU, owner-computes across GPUs); just drain the stream."""
+        _lib.check(_lib.lib().fdb_synchronize())
+
+    def set_local_diagonal_entries(self, rows, diag_val=1.0):
+        rows = np.ascontiguousarray(rows, dtype=IntType)
+        _lib.check(_lib.lib().fdb_mat_set_diagonal(self.handle, rows.ctypes.data, len(rows),
+                                                   float(diag_val)), "fdb_mat_set_diagonal")
+        self.dat_version += 1
+
+    def csr(self):
+        rowptr = np.empty(self.nrows + 1, dtype=np.int64)
+        colidx = np.empty(self.nnz, dtype=IntType)
+        vals = np.empty(self.nnz, dtype=ScalarType)
+        _lib.check(_lib.lib().fdb_mat_get_csr(self.handle, rowptr.ctypes.data, colidx.ctypes.data,
+                                              vals.ctypes.data), "fdb_mat_get_csr")
+        return rowptr, colidx, vals
+
+    @property
+    def values(self):
+        """Dense copy (small matrices / tests), as ``Mat.values`` in PyOP2."""
+        rowptr, colidx, vals = self.csr()
+        A = np.zeros((self.nrows, self.nrows))
+        for r in range(self.nrows):
+            A[r, colidx[rowptr[r]:rowptr[r + 1]]] = vals[rowptr[r]:rowptr[r + 1]]
+        return A
+
+    def mult(self, x: "Dat", y: "Dat"):
+        _lib.check(_lib.lib().fdb_mat_mult(self.handle, x.device_ptr, y.device_ptr), "fdb_mat_mult")
+        y._device_written()
+
+    def __del__(self):
+        try:
+            if self.handle is not None and _lib._initialised is not None:
+                _lib._lib.fdb_mat_destroy(self.handle)
+        except Exception:
+            pass
+
+
 class Global:
     def __init__(self, dim, data=None, dtype=ScalarType, name=None, comm=None):
         self.dim = (dim,) if isinstance(dim, (int, np.integer)) else tuple(dim)
@@ -412,6 +520,7 @@ class LegacyArg:
     data: object
     access: Access
     map: object = None
+    lgmaps: object = None
 
 
 # ------------------------------------------------------------------- kernels
@@ -436,6 +545,12 @@ class Kernel:
     accesses: tuple = (INC, READ, READ)
     # tabulation: a fiat_lite.Interval1D, or None for the default GLL/Gauss pair
     element: object = field(default=None, compare=False, hash=False)
+
+    def __post_init__(self):
+        if self.rank == 2 and self.accesses == (INC, READ, READ):
+            object.__setattr__(self, "accesses", (INC, READ))
+            if self.name == "form0_cell_integral":
+                object.__setattr__(self, "name", "form00_cell_integral")
 
     @property
     def num_flops(self):
@@ -564,7 +679,9 @@ class Parloop:
                 base = self.iterset.superset if isinstance(self.iterset, Subset) else self.iterset
                 if a.map.iterset is not base:
                     raise MapValueError(f"map {a.map.name} is not defined on the iteration set")
-                if a.map.toset is not a.data.dataset.set:
+                toset = (a.data.sparsity.dsets[0].set if isinstance(a.data, Mat)
+                         else a.data.dataset.set)
+                if a.map.toset is not toset:
                     raise MapValueError(f"map {a.map.name} does not target {a.data.name}'s set")
 
     # the two compute phases of pyop2/parloop.py:250-253
@@ -580,6 +697,27 @@ class Parloop:
         for a in self.args:
             if a.map is not None and a.map not in maps:
                 maps.append(a.map)       # distinct maps, first-use order
+        if isinstance(out, Mat):
+            # replace_lgmaps (pyop2/parloop.py:279-314): BC-masked maps for this loop only
+            L = _lib.lib()
+            lg = self.args[0].lgmaps
+            if lg is not None:
+                r, c = (np.ascontiguousarray(v, dtype=IntType) for v in lg)
+                _lib.check(L.fdb_mat_set_lgmaps(out.handle, r.ctypes.data, c.ctypes.data))
+            subset = None
+            if isinstance(it, Subset):
+                if not hasattr(it, "_dev_idx"):
+                    it._dev_idx = DeviceArray.from_host(it.indices)
+                subset = it._dev_idx.ptr
+            coords = self.args[1].data
+            try:
+                gk(start, end, layers, subset, [out.handle.value, coords.device_ptr], None, None,
+                   [m.device_ptr for m in maps], None, _lib.LOC_DEVICE, False, False)
+            finally:
+                if lg is not None:
+                    _lib.check(L.fdb_mat_set_lgmaps(out.handle, None, None))
+            out.dat_version += 1
+            return
         if self.location == "device":
             subset = None
             if isinstance(it, Subset):

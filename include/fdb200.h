@@ -173,6 +173,32 @@ typedef struct fdb_call_args {
  * stream in device mode; host mode returns after the writeback. */
 int fdb_kernel_call(fdb_kernel_t k, const fdb_call_args *a);
 
+/* --------------------------------------------------------------- matrices
+ * Device CSR replacing op2.Sparsity + op2.Mat over PETSc AIJ
+ * (pyop2/types/mat.py:27-292, 607-985; pyop2/sparsity.pyx:106-389).
+ * fdb_mat_create = Sparsity construction + Mat allocation + zero fill for a
+ * square block whose row and column maps are the same cell->node map
+ * (`map_host`: HOST (ncolumns, arity) IntType, `offset_host`: extruded layer
+ * offsets or NULL, `nlayers`: cells per column, 1 if not extruded).  The
+ * diagonal is always allocated.  A rank-2 fdb_kernel_call takes the fdb_mat_t
+ * as args[0] where the reference passes the PETSc Mat handle.
+ * lgmaps: HOST arrays of nrows entries, identity except -1 on Dirichlet
+ * rows/columns (masked LGMaps, firedrake/functionspaceimpl.py:854-926); NULL
+ * restores the identity (pyop2/parloop.py:279-314 swaps them per parloop). */
+typedef struct fdb_mat_s *fdb_mat_t;
+int fdb_mat_create(fdb_int nrows, const fdb_int *map_host, fdb_int ncolumns, int arity,
+                   const fdb_int *offset_host, int nlayers, fdb_mat_t *out);
+int fdb_mat_destroy(fdb_mat_t m);
+int fdb_mat_nnz(fdb_mat_t m, long long *nnz, fdb_int *nrows);
+int fdb_mat_zero(fdb_mat_t m);
+int fdb_mat_set_lgmaps(fdb_mat_t m, const fdb_int *row_lgmap_host, const fdb_int *col_lgmap_host);
+/* Mat.set_local_diagonal_entries (pyop2/types/mat.py:897-937) */
+int fdb_mat_set_diagonal(fdb_mat_t m, const fdb_int *rows_host, fdb_int n, double value);
+/* y = A x on device pointers (cross-check of assembled vs matrix-free action) */
+int fdb_mat_mult(fdb_mat_t m, const double *x, double *y);
+/* copy the CSR arrays to the host (any pointer may be NULL); rowptr is int64 */
+int fdb_mat_get_csr(fdb_mat_t m, long long *rowptr, fdb_int *colidx, double *vals);
+
 /* --------------------------------------------------------- Dat subset ops (K5)
  * DirichletBC.zero / DirichletBC.set on a node subset (firedrake/bcs.py:192-221,
  * pyop2/types/dat.py:297-311).  Device pointers. */
