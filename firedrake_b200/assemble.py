@@ -1,0 +1,249 @@
+"""The assembly surface: ``assemble()`` for the supported forms, Dirichlet
+conditions, and the matrix-free operator context.
+
+Mirrors (same names / call protocol, thin Python over the engine):
+
+* ``firedrake.assemble.assemble`` for 1-forms (``OneFormAssembler``:
+  zero tensor -> parloops -> ``bc.zero``; firedrake/assemble.py:1197-1293) and
+  2-forms (``ExplicitMatrixAssembler``: sparsity + Mat allocation, parloop with
+  BC-masked lgmaps, unit diagonal on BC rows; :1296-1307, 1377-1409, 1484-1525)
+* ``firedrake.bcs.DirichletBC.zero/set/apply`` (firedrake/bcs.py:192-221, 404-457)
+* ``firedrake.matrix_free.operators.ImplicitMatrixContext`` (operators.py:74-242)
+
+Forms are described by :class:`Form` (the Helmholtz family on a
+:class:`FunctionSpace`) instead of UFL: UFL/TSFC are not available here, and the
+engine keys its kernels on a form descriptor.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import op2
+from .halo import Halo
+
+
+class FunctionSpace:
+    """Scalar/vector CG_p space on an extruded hex mesh, bundling the PyOP2
+    objects ``assemble`` needs (node set, cell set, maps, coordinates), i.e.
+    what ``V.cell_node_map()``, ``mesh.coordinates.dat`` and friends give in
+    Firedrake (firedrake/functionspaceimpl.py:803-812)."""
+
+    def __init__(self, mesh, degree, cdim=1, partition=None):
+        self.mesh, self.degree, self.cdim = mesh, degree, cdim
+        self.V = V = mesh.function_space(degree)
+        if partition is not None:
+            cell_sizes, node_sizes = partition.cell_sizes, partition.node_sizes
+            halo = Halo(partition.halo_lists(V), max_cdim=cdim) if partition.nranks > 1 else None
+        else:
+            cell_sizes, node_sizes, halo = mesh.num_base_cells, V.node_count, None
+        self.cell_set = op2.ExtrudedSet(op2.Set(cell_sizes), mesh.layers)
+        self.node_set = op2.Set(node_sizes)
+        self.dof_dset = op2.DataSet(self.node_set, cdim, halo=halo)
+        self.vertex_set = op2.Set(mesh.coord_space.node_count)
+        self.cell_node_map = op2.Map(self.cell_set, self.node_set, V.arity, V.cell_node_map,
+                                     offset=V.offset)
+        self.coord_map = op2.Map(self.cell_set, self.vertex_set, 8, mesh.coord_map,
+                                 offset=mesh.coord_offset)
+        self.coordinates = op2.Dat(op2.DataSet(self.vertex_set, 3), mesh.coordinates)
+
+    def dat(self, data=None, pinned=False):
+        return op2.Dat(self.dof_dset, data, pinned=pinned)
+
+    @property
+    def node_count(self):
+        return self.V.node_count
+
+    def boundary_nodes(self, sub_domain):
+        return self.V.boundary_nodes(sub_domain)
+
+
+class DirichletBC:
+    """``DirichletBC(V, g, sub_domain)``: node subset + value
+    (firedrake/bcs.py:260-457)."""
+
+    def __init__(self, V: FunctionSpace, g, sub_domain):
+        self.V = V
+        subs = sub_domain if isinstance(sub_domain, (list, tuple)) else [sub_domain]
+        nodes = np.unique(np.concatenate([V.boundary_nodes(s) for s in subs])).astype(np.int32)
+        self.nodes = nodes
+        self.node_set = op2.Subset(V.node_set, nodes)
+        self.g = g
+
+    def zero(self, dat):
+        dat.zero(self.node_set)
+
+    def set(self, dat, val):
+        """dat[nodes] = val[nodes] (val a Dat) or the scalar val."""
+        from . import _lib
+        L = _lib.lib()
+        if not hasattr(self, "_dev_nodes"):
+            self._dev_nodes = op2.DeviceArray.from_host(self.nodes)
+        if isinstance(val, op2.Dat):
+            _lib.check(L.fdb_dat_set_nodes(dat.device_ptr, val.device_ptr, dat.cdim,
+                                           self._dev_nodes.ptr, len(self.nodes)))
+        else:
+            _lib.check(L.fdb_dat_set_nodes_scalar(dat.device_ptr, float(val), dat.cdim,
+                                                  self._dev_nodes.ptr, len(self.nodes)))
+        dat._device_written()
+
+    def apply(self, dat):
+        self.set(dat, self.g)
+
+    def lgmap(self):
+        lg = np.arange(self.V.node_count, dtype=np.int32)
+        lg[self.nodes] = -1
+        return lg
+
+
+@dataclass
+class Form:
+    """alpha*inner(grad(u), grad(v))*dx + beta*inner(u, v)*dx on ``V``."""
+    V: FunctionSpace
+    alpha: float = 1.0
+    beta: float = 0.0
+
+    def kernel(self, rank):
+        return op2.Kernel("helmholtz", degree=self.V.degree, alpha=self.alpha, beta=self.beta,
+                          rank=rank, cdim=self.V.cdim)
+
+
+def poisson(V):
+    return Form(V, 1.0, 0.0)
+
+
+def helmholtz(V):
+    return Form(V, 1.0, 1.0)
+
+
+def mass(V):
+    return Form(V, 0.0, 1.0)
+
+
+class OneFormAssembler:
+    """Cached assembler of ``action(a, u)`` (firedrake/assemble.py:950-977,
+    1073-1096: parloops are built once and re-run)."""
+
+    def __init__(self, form: Form, u: op2.Dat, bcs=(), scatter="atomic"):
+        self.form, self.u, self.bcs = form, u, tuple(bcs)
+        V = form.V
+        self._gk = op2.GlobalKernel(form.kernel(1), [V.cell_node_map, V.coord_map], extruded=True,
+                                    scatter=scatter)
+        self._loop = None
+
+    def assemble(self, tensor=None):
+        V = self.form.V
+        if tensor is None:
+            tensor = V.dat()
+        if self._loop is None or self._tensor is not tensor:
+            self._tensor = tensor
+            self._loop = op2.Parloop(self._gk, V.cell_set,
+                                     [tensor(op2.INC, V.cell_node_map),
+                                      V.coordinates(op2.READ, V.coord_map),
+                                      self.u(op2.READ, V.cell_node_map)], location="device")
+        tensor.zero()
+        self._loop()
+        for bc in self.bcs:
+            bc.zero(tensor)
+        return tensor
+
+
+def assemble(form: Form, u=None, tensor=None, bcs=(), mat_type="aij"):
+    """``assemble(action(a, u))`` when ``u`` is given (-> Dat), else the
+    bilinear form: ``mat_type="aij"`` -> :class:`op2.Mat`, ``"matfree"`` ->
+    :class:`ImplicitMatrixContext`."""
+    V = form.V
+    bcs = tuple(bcs)
+    if u is not None:
+        return OneFormAssembler(form, u, bcs).assemble(tensor)
+    if mat_type == "matfree":
+        return ImplicitMatrixContext(form, bcs)
+    if tensor is None:
+        tensor = op2.Mat(op2.Sparsity((V.node_set, V.node_set),
+                                      [(V.cell_node_map, V.cell_node_map, None)]))
+    tensor.zero()
+    lg = None
+    if bcs:
+        lgm = np.arange(V.node_count, dtype=np.int32)
+        for bc in bcs:
+            lgm[bc.nodes] = -1
+        lg = (lgm, lgm)
+    op2.par_loop(form.kernel(2), V.cell_set,
+                 tensor(op2.INC, (V.cell_node_map, V.cell_node_map), lgmaps=lg),
+                 V.coordinates(op2.READ, V.coord_map))
+    for bc in bcs:
+        tensor.set_local_diagonal_entries(bc.nodes, 1.0)
+    tensor.assemble()
+    return tensor
+
+
+class ImplicitMatrixContext:
+    """Matrix-free operator (firedrake/matrix_free/operators.py:74-242): ``mult``
+    = zero the column-BC entries of x, assemble ``action(a, x)``, write x back on
+    the row-BC entries (identity on constrained rows).  x and y stay on the
+    device across calls."""
+
+    def __init__(self, form: Form, bcs=()):
+        self.form, self.bcs = form, tuple(bcs)
+        V = form.V
+        self._x = V.dat()
+        self._assembler = OneFormAssembler(form, self._x, ())
+
+    def mult(self, X: op2.Dat, Y: op2.Dat):
+        from . import _lib
+        L = _lib.lib()
+        _lib.check(L.fdb_memcpy_d2d(self._x.device_ptr, X.device_ptr, X.nbytes))
+        self._x._device_written()
+        self._x.halo_valid = False
+        for bc in self.bcs:
+            bc.zero(self._x)
+        self._assembler.assemble(tensor=Y)
+        for bc in self.bcs:
+            bc.set(Y, X)
+        return Y
+
+
+def cg(A, b: op2.Dat, x: op2.Dat, rtol=1e-8, atol=0.0, maxit=1000, allreduce=None):
+    """Unpreconditioned conjugate gradients on device-resident Dats (the solve
+    of demos/matrix_free/poisson.py.rst:38-47 with ``ksp_type cg, pc_type
+    none``).  ``A`` needs ``mult(X, Y)``.  Returns (iterations, residual norms).
+    ``allreduce``: callable summing a scalar over ranks (owned dofs only)."""
+    V = b.dataset
+    r = op2.Dat(V)
+    p = op2.Dat(V)
+    Ap = op2.Dat(V)
+    n_owned = b.dataset.set.size * b.cdim
+
+    def dot(a, c):
+        import ctypes as C
+        from . import _lib
+        out = C.c_double()
+        _lib.check(_lib.lib().fdb_vec_dot(n_owned, a.device_ptr, c.device_ptr, C.byref(out)))
+        return allreduce(out.value) if allreduce else out.value
+
+    from . import _lib
+    L = _lib.lib()
+    n = b._data.size
+    A.mult(x, Ap)
+    _lib.check(L.fdb_memcpy_d2d(r.device_ptr, b.device_ptr, b.nbytes))
+    r._device_written()
+    _lib.check(L.fdb_vec_axpy(n, -1.0, Ap.device_ptr, r.device_ptr))
+    _lib.check(L.fdb_memcpy_d2d(p.device_ptr, r.device_ptr, r.nbytes))
+    p._device_written()
+    rr = dot(r, r)
+    r0 = np.sqrt(rr)
+    hist = [r0]
+    it = 0
+    while it < maxit and np.sqrt(rr) > max(rtol * r0, atol):
+        A.mult(p, Ap)
+        alpha = rr / dot(p, Ap)
+        _lib.check(L.fdb_vec_axpy(n, alpha, p.device_ptr, x.device_ptr))
+        _lib.check(L.fdb_vec_axpy(n, -alpha, Ap.device_ptr, r.device_ptr))
+        rr_new = dot(r, r)
+        _lib.check(L.fdb_vec_aypx(n, rr_new / rr, r.device_ptr, p.device_ptr))   # p = r + beta p
+        rr = rr_new
+        hist.append(np.sqrt(rr))
+        it += 1
+    x._device_written()
+    return it, hist

@@ -1,0 +1,68 @@
+"""The assemble()/DirichletBC/ImplicitMatrixContext surface on the device
+ and the device CG of config 5."""
+import numpy as np
+import pytest
+
+from firedrake_b200 import op2
+from firedrake_b200.assemble import (DirichletBC, FunctionSpace, ImplicitMatrixContext, assemble, cg,
+                                     helmholtz, poisson)
+from firedrake_b200.utility_meshes import ExtrudedHexMesh
+
+pytestmark = pytest.mark.gpu
+
+
+def test_matfree_equals_assembled_with_bcs(engine):
+    """reference tests/firedrake/regression/test_matrix_free.py:98-127."""
+    mesh = ExtrudedHexMesh(4, 4, 5, warp=0.05, permute_seed=0)
+    V = FunctionSpace(mesh, 2)
+    bcs = [DirichletBC(V, 0.0, ["bottom", "top"])]
+    a = helmholtz(V)
+    A = assemble(a, bcs=bcs)
+    Amf = assemble(a, bcs=bcs, mat_type="matfree")
+    assert isinstance(Amf, ImplicitMatrixContext)
+    x = V.dat(np.random.default_rng(0).standard_normal(V.node_count))
+    y1, y2 = V.dat(), V.dat()
+    A.mult(x, y1)
+    Amf.mult(x, y2)
+    assert np.abs(y1.data_ro - y2.data_ro).max() < 1e-12 * np.abs(y1.data_ro).max()
+
+
+def test_poisson_solve_strong_bcs_extrusion(engine):
+    """reference tests/firedrake/extrusion/test_poisson_strong_bcs_extrusion.py:
+    -div grad u = 0, u = 0 on the bottom, u = 42 on the top  =>  u = 42 z.
+    Solved matrix-free with device CG (lifting of the boundary values)."""
+    for p in (1, 3):
+        mesh = ExtrudedHexMesh(3, 3, 6, warp=0.0)
+        V = FunctionSpace(mesh, p)
+        z = V.V.dof_coordinates()[:, 2]
+        bcs = [DirichletBC(V, 0.0, ["bottom", "top"])]
+        a = poisson(V)
+        # lift: u = u0 + g with g = 42 on the top nodes;  A u0 = -K g on free rows
+        g = np.zeros(V.node_count)
+        g[V.boundary_nodes("top")] = 42.0
+        Kg = assemble(a, u=V.dat(g.copy()))
+        b = V.dat(-Kg.data_ro)
+        bcs[0].zero(b)
+        A = assemble(a, bcs=bcs, mat_type="matfree")
+        u0 = V.dat()
+        its, hist = cg(A, b, u0, rtol=1e-12, maxit=500)
+        u = u0.data_ro + g
+        assert np.abs(u - 42.0 * z).max() < 1e-6, (p, its, hist[-1])
+
+
+def test_cg_matches_scipy(engine):
+    mesh = ExtrudedHexMesh(4, 3, 4, warp=0.05)
+    V = FunctionSpace(mesh, 2)
+    a = helmholtz(V)
+    A = assemble(a)
+    Amf = assemble(a, mat_type="matfree")
+    rng = np.random.default_rng(5)
+    bv = rng.standard_normal(V.node_count)
+    x = V.dat()
+    its, hist = cg(Amf, V.dat(bv.copy()), x, rtol=1e-11, maxit=2000)
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    ro, co, va = A.csr()
+    xs = spla.spsolve(sp.csr_matrix((va, co, ro), shape=(V.node_count,) * 2).tocsc(), bv)
+    assert np.abs(x.data_ro - xs).max() < 1e-8 * np.abs(xs).max()
+    assert hist[-1] < 1e-10 * hist[0]

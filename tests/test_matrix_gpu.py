@@ -83,10 +83,10 @@ def test_bc_lgmaps_diagonal_and_matvec(engine, oracle):
     # SpMV vs matrix-free action with BCs
     rng = np.random.default_rng(3)
     xv = rng.standard_normal(V.node_count)
-    x = op2.Dat(nodes, xv)
+    x = op2.Dat(nodes, xv.copy())
     y = op2.Dat(nodes)
     mat.mult(x, y)
-    xin = op2.Dat(nodes, xv)
+    xin = op2.Dat(nodes, xv.copy())
     xin.zero(op2.Subset(nodes, bnodes))                    # bc.zero(x)
     ymf = op2.Dat(nodes)
     k1 = op2.Kernel("helmholtz", degree=p, alpha=1.0, beta=1.0)
