@@ -1,0 +1,116 @@
+#!/usr/bin/env python
+"""Secondary measurements for the other BASELINE.json configs (not the driver's
+bench line): one JSON object per line on stdout.
+
+    python benchmarks/run_configs.py [--quick]
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from firedrake_b200 import _lib, op2                                   # noqa: E402
+from firedrake_b200.assemble import (DirichletBC, FunctionSpace, assemble, cg, helmholtz,  # noqa: E402
+                                     poisson, OneFormAssembler, Form)
+from firedrake_b200.utility_meshes import ExtrudedHexMesh              # noqa: E402
+
+
+def timed(fn, steps=5, warm=2):
+    L = _lib.lib()
+    for _ in range(warm):
+        fn()
+    t = C.c_void_p()
+    L.fdb_timer_create(C.byref(t))
+    ms = C.c_float()
+    _lib.check(L.fdb_synchronize())
+    L.fdb_timer_start(t)
+    for _ in range(steps):
+        fn()
+    L.fdb_timer_stop(t, C.byref(ms))
+    L.fdb_timer_destroy(t)
+    return ms.value / steps
+
+
+def action_case(name, n, p, cdim=1, alpha=1.0, beta=0.0, warp=0.05, permute=None, steps=5):
+    mesh = ExtrudedHexMesh(n, n, n, warp=warp, permute_seed=permute)
+    V = FunctionSpace(mesh, p, cdim=cdim)
+    shape = (V.node_count,) if cdim == 1 else (V.node_count, cdim)
+    u = V.dat(np.random.default_rng(0).standard_normal(shape))
+    y = V.dat()
+    asm = OneFormAssembler(Form(V, alpha, beta), u)
+    ms = timed(lambda: asm.assemble(y), steps)
+    ndof = V.node_count * cdim
+    return {"case": name, "n": n, "degree": p, "cdim": cdim, "cells": mesh.num_cells, "dofs": ndof,
+            "ms": ms, "dofs_per_s": ndof / ms * 1e3, "permute": permute, "warp": warp}
+
+
+def matrix_case(name, n, p, steps=3):
+    mesh = ExtrudedHexMesh(n, n, n, warp=0.05)
+    V = FunctionSpace(mesh, p)
+    t0 = time.perf_counter()
+    mat = op2.Mat(op2.Sparsity((V.node_set, V.node_set), [(V.cell_node_map, V.cell_node_map, None)]))
+    _lib.check(_lib.lib().fdb_synchronize())
+    t_sparsity = time.perf_counter() - t0
+    a = poisson(V)
+    ms = timed(lambda: assemble(a, tensor=mat), steps, warm=1)
+    return {"case": name, "n": n, "degree": p, "dofs": V.node_count, "nnz": mat.nnz,
+            "sparsity_s": t_sparsity, "assemble_ms": ms, "dofs_per_s": V.node_count / ms * 1e3,
+            "csr_GB": mat.nnz * 12 / 1e9}
+
+
+def cg_case(name, n, p, iters=20):
+    mesh = ExtrudedHexMesh(n, n, n, warp=0.05)
+    V = FunctionSpace(mesh, p)
+    bcs = [DirichletBC(V, 0.0, ["bottom", "top"])]
+    A = assemble(poisson(V), bcs=bcs, mat_type="matfree")
+    b = V.dat(np.random.default_rng(1).standard_normal(V.node_count))
+    bcs[0].zero(b)
+    x = V.dat()
+    cg(A, b, x, rtol=0.0, maxit=2)
+    _lib.check(_lib.lib().fdb_synchronize())
+    x.zero()
+    t0 = time.perf_counter()
+    its, hist = cg(A, b, x, rtol=0.0, maxit=iters)
+    _lib.check(_lib.lib().fdb_synchronize())
+    t = time.perf_counter() - t0
+    return {"case": name, "n": n, "degree": p, "dofs": V.node_count, "iterations": its,
+            "s_per_iteration": t / its, "dof_iterations_per_s": V.node_count * its / t,
+            "residual_reduction": hist[-1] / hist[0]}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true")
+    args = ap.parse_args()
+    _lib.init(0)
+    q = args.quick
+    jobs = [
+        lambda: action_case("config2 Poisson CG3 action, lexicographic", 64 if q else 256, 3),
+        lambda: action_case("config2 Poisson CG3 action, random base-cell order", 64 if q else 256, 3, permute=0),
+        lambda: action_case("config2 Poisson CG3 action, affine mesh (warp 0)", 64 if q else 256, 3, warp=0.0),
+        lambda: action_case("Poisson CG1 action", 64 if q else 256, 1),
+        lambda: action_case("Poisson CG2 action", 64 if q else 256, 2),
+        lambda: action_case("config4 vector Helmholtz CG4 action (cdim 3)", 16 if q else 64, 4, cdim=3, beta=1.0),
+        lambda: action_case("config5 Poisson CG5 action", 32 if q else 128, 5),
+        lambda: cg_case("config5 Poisson CG5 matrix-free CG", 32 if q else 128, 5, iters=10 if q else 20),
+        lambda: matrix_case("Poisson CG1 matrix", 32 if q else 128, 1),
+        lambda: matrix_case("Poisson CG2 matrix", 16 if q else 48, 2),
+        lambda: matrix_case("Poisson CG3 matrix", 8 if q else 32, 3),
+    ]
+    for j in jobs:
+        try:
+            print(json.dumps(j()), flush=True)
+        except Exception as e:                       # keep going: report the failure
+            print(json.dumps({"error": repr(e)[:300]}), flush=True)
+        _lib.lib().fdb_mirror_drop_all()
+
+
+if __name__ == "__main__":
+    main()
