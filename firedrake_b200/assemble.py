@@ -247,3 +247,66 @@ def cg(A, b: op2.Dat, x: op2.Dat, rtol=1e-8, atol=0.0, maxit=1000, allreduce=Non
         it += 1
     x._device_written()
     return it, hist
+
+
+class DGAdvection:
+    """Right-hand side ``assemble(L1)`` of the DG advection demo (reference
+    demos/DG_advection/DG_advection.py.rst:182-217) on a :class:`QuadMesh`:
+    three parloops -- cells, exterior facets, interior facets -- exactly the
+    kernels ``OneFormAssembler`` would run (firedrake/assemble.py:1069-1096)."""
+
+    def __init__(self, mesh, dt, q_in=1.0, nq=3):
+        self.mesh = mesh
+        C_ = mesh.num_cells
+        self.cell_set = op2.Set(C_)
+        self.dq_nodes = op2.Set(4 * C_)
+        self.vertices = op2.Set(mesh.node_count)
+        self.ext_set = op2.Set(len(mesh.ext_facet_cells))
+        self.int_set = op2.Set(len(mesh.int_facet_cells))
+        dg, cg = mesh.dg1_map, mesh.coord_map
+        self.cell_dq = op2.Map(self.cell_set, self.dq_nodes, 4, dg)
+        self.cell_cg = op2.Map(self.cell_set, self.vertices, 4, cg)
+        # facet->node maps: the nodes of cell '+' then of cell '-'
+        # (firedrake/cython/dmcommon.pyx:1636-1677)
+        self.ext_dq = op2.Map(self.ext_set, self.dq_nodes, 4, dg[mesh.ext_facet_cells])
+        self.ext_cg = op2.Map(self.ext_set, self.vertices, 4, cg[mesh.ext_facet_cells])
+        ic = mesh.int_facet_cells
+        self.int_dq = op2.Map(self.int_set, self.dq_nodes, 8, np.concatenate([dg[ic[:, 0]], dg[ic[:, 1]]], axis=1))
+        self.int_cg = op2.Map(self.int_set, self.vertices, 8, np.concatenate([cg[ic[:, 0]], cg[ic[:, 1]]], axis=1))
+        self.ext_facet = op2.Dat(op2.DataSet(self.ext_set, 1), mesh.ext_facet_local, dtype=np.uint32)
+        self.int_facet = op2.Dat(op2.DataSet(self.int_set, 2), mesh.int_facet_local, dtype=np.uint32)
+        self.coordinates = op2.Dat(op2.DataSet(self.vertices, 2), mesh.coordinates)
+        self.consts = op2.Global(2, [dt, q_in])
+        self.nq = nq
+        self._loops = None
+
+    def function(self, data=None):
+        return op2.Dat(self.dq_nodes, data)
+
+    def velocity(self, data):
+        return op2.Dat(op2.DataSet(self.vertices, 2), data)
+
+    def assemble(self, q, u, tensor=None):
+        if tensor is None:
+            tensor = self.function()
+        key = (id(q), id(u), id(tensor))
+        if self._loops is None or self._key != key:
+            self._key = key
+            mk = lambda integral: op2.Kernel("dg_advection", degree=1, integral=integral, nq=self.nq)
+            X, G = self.coordinates, self.consts
+            gk = lambda k, maps: op2.GlobalKernel(k, maps, extruded=False)
+            self._loops = [
+                op2.Parloop(gk(mk("cell"), [self.cell_dq, self.cell_cg]), self.cell_set,
+                            [tensor(op2.INC, self.cell_dq), X(op2.READ, self.cell_cg), q(op2.READ, self.cell_dq),
+                             u(op2.READ, self.cell_cg), G(op2.READ)]),
+                op2.Parloop(gk(mk("exterior_facet"), [self.ext_dq, self.ext_cg]), self.ext_set,
+                            [tensor(op2.INC, self.ext_dq), X(op2.READ, self.ext_cg), q(op2.READ, self.ext_dq),
+                             u(op2.READ, self.ext_cg), G(op2.READ), self.ext_facet(op2.READ)]),
+                op2.Parloop(gk(mk("interior_facet"), [self.int_dq, self.int_cg]), self.int_set,
+                            [tensor(op2.INC, self.int_dq), X(op2.READ, self.int_cg), q(op2.READ, self.int_dq),
+                             u(op2.READ, self.int_cg), G(op2.READ), self.int_facet(op2.READ)]),
+            ]
+        tensor.zero()
+        for loop in self._loops:
+            loop()
+        return tensor

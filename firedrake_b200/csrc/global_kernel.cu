@@ -103,6 +103,20 @@ int fdb_kernel_create(const fdb_kernel_desc *d, fdb_kernel_t *out)
         set_error("fdb_kernel_create: NULL argument");
         return 1;
     }
+    if (d->form == FDB_FORM_DG_ADVECTION) {
+        if (d->cell != FDB_CELL_QUAD || d->rank != 1 || d->degree != 1 || d->cdim != 1 ||
+            d->nq < 1 || d->nq > FDB_MAX_1D || d->integral < 0 || d->integral > 2) {
+            set_error("fdb_kernel_create: DG advection is DQ1 on quads, rank 1, nq <= %d", FDB_MAX_1D);
+            return 1;
+        }
+        fdb_kernel_s *k = new fdb_kernel_s;
+        k->desc = *d;
+        k->n1d = 2;
+        k->arity = d->integral == FDB_INTEGRAL_INTERIOR_FACET ? 8 : 4;
+        k->desc.offset0 = k->desc.offset1 = nullptr;
+        *out = k;
+        return 0;
+    }
     if (d->form != FDB_FORM_HELMHOLTZ) {
         set_error("fdb_kernel_create: form %d is not in the supported set", d->form);
         return 1;
@@ -168,8 +182,8 @@ int fdb_kernel_destroy(fdb_kernel_t k)
     if (!k) return 0;
     if (ctx().ready) {
         cudaStreamSynchronize(ctx().stream);
-        cudaFree(k->d_off0);
-        cudaFree(k->d_off1);
+        if (k->d_off0) cudaFree(k->d_off0);
+        if (k->d_off1) cudaFree(k->d_off1);
         if (k->d_colour_cols) cudaFree(k->d_colour_cols);
     }
     delete k;
@@ -182,6 +196,24 @@ int fdb_kernel_call(fdb_kernel_t k, const fdb_call_args *a)
     if (!k || !a) {
         set_error("fdb_kernel_call: NULL argument");
         return 1;
+    }
+    if (k->desc.form == FDB_FORM_DG_ADVECTION) {
+        // args = [out (INC), coords, q, u, consts (HOST double[2] {dtc, q_in}), facet numbers]
+        // maps = [DQ1 (facet-)node map, CG1 (facet-)node map]
+        const bool facets = k->desc.integral != FDB_INTEGRAL_CELL;
+        if (a->nargs != (facets ? 6 : 5) || a->nmaps != 2) {
+            set_error("fdb_kernel_call: DG advection expects %d args and 2 maps", facets ? 6 : 5);
+            return 1;
+        }
+        if (a->location != FDB_LOC_DEVICE) {
+            set_error("fdb_kernel_call: DG advection kernels take device-resident Dats");
+            return 1;
+        }
+        return fdb_launch_dg_advection(k, a->start, a->end, a->subset, (double *)a->args[0],
+                                       (const double *)a->args[1], (const double *)a->args[2],
+                                       (const double *)a->args[3], (const double *)a->args[4],
+                                       facets ? (const unsigned *)a->args[5] : nullptr, a->maps[0],
+                                       a->maps[1]);
     }
     const bool extruded = k->desc.cell == FDB_CELL_HEX_EXTRUDED;
     if (extruded && !a->layers) {

@@ -541,12 +541,19 @@ class Kernel:
     beta: float = 0.0
     rank: int = 1
     cdim: int = 1
+    integral: str = "cell"          # "cell" | "exterior_facet" | "interior_facet"
+    nq: int = 0                     # 1-D quadrature points (0: the form's default)
     name: str = "form0_cell_integral"
     accesses: tuple = (INC, READ, READ)
     # tabulation: a fiat_lite.Interval1D, or None for the default GLL/Gauss pair
     element: object = field(default=None, compare=False, hash=False)
 
     def __post_init__(self):
+        if self.form == "dg_advection":
+            # args: out, coordinates, q, u, constants (dtc, q_in) [, local facet numbers]
+            acc = (INC, READ, READ, READ, READ) + ((READ,) if self.integral != "cell" else ())
+            object.__setattr__(self, "accesses", acc)
+            object.__setattr__(self, "name", f"form0_{self.integral}_integral")
         if self.rank == 2 and self.accesses == (INC, READ, READ):
             object.__setattr__(self, "accesses", (INC, READ))
             if self.name == "form0_cell_integral":
@@ -558,7 +565,9 @@ class Kernel:
         return 2 * 6 * n ** 4 * 2 + 130 * n ** 3
 
 
-_FORMS = {"helmholtz": _lib.FORM_HELMHOLTZ}
+_FORMS = {"helmholtz": _lib.FORM_HELMHOLTZ, "dg_advection": _lib.FORM_DG_ADVECTION}
+_INTEGRALS = {"cell": _lib.INTEGRAL_CELL, "exterior_facet": _lib.INTEGRAL_EXTERIOR_FACET,
+              "interior_facet": _lib.INTEGRAL_INTERIOR_FACET}
 
 
 class GlobalKernel:
@@ -586,8 +595,27 @@ class GlobalKernel:
     def compile(self):
         if self._handle is not None:
             return self._handle
-        from .fiat_lite import interval_element
+        from .fiat_lite import gauss_legendre, interval_element
         lk = self.local_kernel
+        if lk.form == "dg_advection":
+            nq = lk.nq or 3
+            d = _lib.KernelDesc()
+            d.form, d.rank, d.cell = _FORMS[lk.form], 1, _lib.CELL_QUAD
+            d.integral = _INTEGRALS[lk.integral]
+            d.degree, d.nq, d.cdim, d.scatter = 1, nq, 1, _lib.SCATTER_ATOMIC
+            xq, wq = gauss_legendre(nq)
+            for i in range(nq):
+                d.xq[i], d.wq[i] = xq[i], wq[i]
+            # DQ1: default "spectral" variant = Gauss-Legendre nodes on the interval
+            el = lk.element or interval_element(1, 2, "gl")
+            Bend, _ = el.tabulate([0.0, 1.0])
+            for e in range(2):
+                for i in range(2):
+                    d.B[e * 2 + i] = Bend[e, i]
+            h = C.c_void_p()
+            _lib.check(_lib.lib().fdb_kernel_create(C.byref(d), C.byref(h)), "fdb_kernel_create")
+            self._handle = h
+            return h
         el = lk.element or interval_element(lk.degree)
         n = lk.degree + 1
         if el.ndof != n:
@@ -724,7 +752,8 @@ class Parloop:
                 if not hasattr(it, "_dev_idx"):
                     it._dev_idx = DeviceArray.from_host(it.indices)
                 subset = it._dev_idx.ptr
-            ptrs = [a.data.device_ptr for a in self.args]
+            ptrs = [a.data._data.ctypes.data if isinstance(a.data, Global) else a.data.device_ptr
+                    for a in self.args]
             gk(start, end, layers, subset, ptrs, None, None, [m.device_ptr for m in maps], None,
                _lib.LOC_DEVICE, False, False)
             out._device_written()

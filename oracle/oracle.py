@@ -24,7 +24,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 BUILD = os.path.join(HERE, "_build")
-SRC = [os.path.join(HERE, "oracle.c")]
+SRC = [os.path.join(HERE, "oracle.c"), os.path.join(HERE, "dg_advection.c")]
 BASE_FLAGS = ["-O3", "-ffast-math", "-fPIC", "-shared", "-std=gnu11", "-fopenmp",
               "-fno-math-errno"]
 
@@ -246,3 +246,39 @@ def action_workers(el, problems, cdim=1, alpha=1.0, beta=0.0, native=True):
 
 def num_threads():
     return lib().orc_num_threads()
+
+
+# -- DG advection (reference demos/DG_advection) ------------------------------
+c_up = ctypes.POINTER(ctypes.c_uint32)
+
+
+def dq1_end_values(variant="gl"):
+    """(2, 2): DQ1 1-D basis (nodes = 2 Gauss points for the default spectral
+    variant, interval ends for "equispaced") evaluated at x = 0 and x = 1."""
+    from firedrake_b200.fiat_lite import interval_element
+    el = interval_element(1, 2, variant)
+    B, _ = el.tabulate([0.0, 1.0])
+    return np.ascontiguousarray(B)
+
+
+def dg_rhs(mesh, q, u, dt, q_in=1.0, nq=3, variant="gl", out=None):
+    """assemble(L1) of the DG advection demo: cell + exterior + interior facets."""
+    from firedrake_b200.fiat_lite import gauss_legendre
+    L = lib()
+    xq, wq = gauss_legendre(nq)
+    Bend = dq1_end_values(variant)
+    if out is None:
+        out = np.zeros(mesh.num_cells * 4)
+    uu = np.ascontiguousarray(u, dtype=np.float64)
+    fl_e = np.ascontiguousarray(mesh.ext_facet_local, dtype=np.uint32)
+    fl_i = np.ascontiguousarray(mesh.int_facet_local, dtype=np.uint32)
+    L.orc_dg_cells(0, mesh.num_cells, _d(out), _d(mesh.coordinates), _d(q), _d(uu), _i(mesh.dg1_map),
+                   _i(mesh.coord_map), nq, _d(Bend), _d(wq), _d(xq), ctypes.c_double(dt))
+    L.orc_dg_exterior_facets(0, len(mesh.ext_facet_cells), _d(out), _d(mesh.coordinates), _d(q), _d(uu),
+                             _i(mesh.ext_facet_cells), fl_e.ctypes.data_as(c_up), _i(mesh.dg1_map),
+                             _i(mesh.coord_map), nq, _d(Bend), _d(wq), _d(xq), ctypes.c_double(dt),
+                             ctypes.c_double(q_in))
+    L.orc_dg_interior_facets(0, len(mesh.int_facet_cells), _d(out), _d(mesh.coordinates), _d(q), _d(uu),
+                             _i(mesh.int_facet_cells), fl_i.ctypes.data_as(c_up), _i(mesh.dg1_map),
+                             _i(mesh.coord_map), nq, _d(Bend), _d(wq), _d(xq), ctypes.c_double(dt))
+    return out
