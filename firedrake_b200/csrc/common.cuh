@@ -77,6 +77,8 @@ int fdb_launch_helmholtz_matrix(fdb_kernel_s *k, fdb_int start, fdb_int end, int
                                 const fdb_int *subset, fdb_mat_t mat, const double *coords,
                                 const fdb_int *map0, const fdb_int *map1);
 
+int fdb_launch_tri_p1(fdb_kernel_s *k, fdb_int start, fdb_int end, const fdb_int *subset, double *y,
+                      const double *coords, const double *x, const fdb_int *map, fdb_mat_t mat);
 int fdb_launch_dg_advection(fdb_kernel_s *k, fdb_int start, fdb_int end, const fdb_int *subset,
                             double *out, const double *coords, const double *q, const double *u,
                             const double *consts_host, const unsigned *facet, const fdb_int *dgmap,

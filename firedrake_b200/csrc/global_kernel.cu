@@ -117,6 +117,21 @@ int fdb_kernel_create(const fdb_kernel_desc *d, fdb_kernel_t *out)
         *out = k;
         return 0;
     }
+    if (d->form == FDB_FORM_HELMHOLTZ && d->cell == FDB_CELL_TRIANGLE) {
+        // affine P1 triangles: B = basis table (3, nq), D = reference gradients (3, 2)
+        if (d->degree != 1 || d->cdim != 1 || d->nq < 1 || d->nq > FDB_MAX_1D ||
+            (d->rank != 1 && d->rank != 2) || d->integral != FDB_INTEGRAL_CELL) {
+            set_error("fdb_kernel_create: triangle kernels are P1, scalar, nq <= %d", FDB_MAX_1D);
+            return 1;
+        }
+        fdb_kernel_s *k = new fdb_kernel_s;
+        k->desc = *d;
+        k->n1d = 2;
+        k->arity = 3;
+        k->desc.offset0 = k->desc.offset1 = nullptr;
+        *out = k;
+        return 0;
+    }
     if (d->form != FDB_FORM_HELMHOLTZ) {
         set_error("fdb_kernel_create: form %d is not in the supported set", d->form);
         return 1;
@@ -214,6 +229,21 @@ int fdb_kernel_call(fdb_kernel_t k, const fdb_call_args *a)
                                        (const double *)a->args[3], (const double *)a->args[4],
                                        facets ? (const unsigned *)a->args[5] : nullptr, a->maps[0],
                                        a->maps[1]);
+    }
+    if (k->desc.cell == FDB_CELL_TRIANGLE) {
+        // rank 1: args = [y, coords, x]; rank 2: args = [mat, coords]; maps[0] = cell->vertex map
+        // (V and the P1 coordinate space share it; a second identical map is accepted)
+        const int want = k->desc.rank == 1 ? 3 : 2;
+        if (a->nargs != want || a->nmaps < 1 || a->location != FDB_LOC_DEVICE) {
+            set_error("fdb_kernel_call: P1 triangle kernel expects %d device args and 1-2 maps", want);
+            return 1;
+        }
+        if (k->desc.rank == 1)
+            return fdb_launch_tri_p1(k, a->start, a->end, a->subset, (double *)a->args[0],
+                                     (const double *)a->args[1], (const double *)a->args[2], a->maps[0],
+                                     nullptr);
+        return fdb_launch_tri_p1(k, a->start, a->end, a->subset, nullptr, (const double *)a->args[1],
+                                 nullptr, a->maps[0], (fdb_mat_t)a->args[0]);
     }
     const bool extruded = k->desc.cell == FDB_CELL_HEX_EXTRUDED;
     if (extruded && !a->layers) {

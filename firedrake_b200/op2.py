@@ -542,6 +542,7 @@ class Kernel:
     rank: int = 1
     cdim: int = 1
     integral: str = "cell"          # "cell" | "exterior_facet" | "interior_facet"
+    cell: str = "hex"               # "hex" (extruded or native) | "triangle" (affine P1)
     nq: int = 0                     # 1-D quadrature points (0: the form's default)
     name: str = "form0_cell_integral"
     accesses: tuple = (INC, READ, READ)
@@ -612,6 +613,23 @@ class GlobalKernel:
             for e in range(2):
                 for i in range(2):
                     d.B[e * 2 + i] = Bend[e, i]
+            h = C.c_void_p()
+            _lib.check(_lib.lib().fdb_kernel_create(C.byref(d), C.byref(h)), "fdb_kernel_create")
+            self._handle = h
+            return h
+        if lk.cell == "triangle":
+            # P1 on affine triangles, FIAT basis order (1-x-y, x, y), 3-point
+            # edge-midpoint rule (degree 2, exact for the P1 mass matrix)
+            d = _lib.KernelDesc()
+            d.form, d.rank, d.cell = _FORMS[lk.form], lk.rank, _lib.CELL_TRIANGLE
+            d.integral, d.degree, d.nq, d.cdim, d.scatter = _lib.INTEGRAL_CELL, 1, 3, 1, _lib.SCATTER_ATOMIC
+            d.alpha, d.beta = lk.alpha, lk.beta
+            pts = [(0.5, 0.0), (0.5, 0.5), (0.0, 0.5)]
+            for q, (x, y) in enumerate(pts):
+                d.B[0 * 3 + q], d.B[1 * 3 + q], d.B[2 * 3 + q] = 1 - x - y, x, y
+                d.wq[q] = 1.0 / 6.0
+            for i, g in enumerate([(-1.0, -1.0), (1.0, 0.0), (0.0, 1.0)]):
+                d.D[i * 2], d.D[i * 2 + 1] = g
             h = C.c_void_p()
             _lib.check(_lib.lib().fdb_kernel_create(C.byref(d), C.byref(h)), "fdb_kernel_create")
             self._handle = h

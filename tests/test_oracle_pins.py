@@ -308,3 +308,31 @@ def test_config1_p1_triangles(oracle):
     oracle.tri_matrix("mass", 0, mesh.num_cells, rowptr, colidx, vals, mesh.coordinates,
                       mesh.cell_node_map, tab)
     assert abs(vals.sum() - 1.0) < 1e-13
+
+
+def test_dg_advection_oracle_invariants(oracle):
+    """DG advection restatement (oracle/dg_advection.c): with q == q_in and a
+    divergence-free velocity the cell, exterior-facet and interior-facet terms
+    cancel exactly (divergence theorem) even on distorted quads; interior
+    fluxes cancel in the sum over test functions (mass conservation,
+    reference tests/firedrake/regression/test_dg_advection.py:62-75)."""
+    from firedrake_b200.utility_meshes import QuadMesh
+    m = QuadMesh(8, 6)
+    rng = np.random.default_rng(0)
+    X = m.coordinates
+    inner = (X[:, 0] > 1e-9) & (X[:, 0] < 1 - 1e-9) & (X[:, 1] > 1e-9) & (X[:, 1] < 1 - 1e-9)
+    X[inner] += 0.02 * rng.standard_normal((inner.sum(), 2))
+    u = np.stack([0.5 - X[:, 1], X[:, 0] - 0.5], axis=1)
+    r = oracle.dg_rhs(m, np.ones(m.num_cells * 4), u, dt=0.1, q_in=1.0)
+    assert np.abs(r).max() < 1e-15
+    # sum_i L1_i = -dt * (boundary flux): independent of interior cell values
+    q = 1 + rng.random(m.num_cells * 4)
+    s0 = oracle.dg_rhs(m, q, u, dt=0.1).sum()
+    bcells = set(m.ext_facet_cells.tolist())
+    q2 = q.copy()
+    for c in range(m.num_cells):
+        if c not in bcells:
+            q2[4 * c:4 * c + 4] += 0.7
+    assert abs(oracle.dg_rhs(m, q2, u, dt=0.1).sum() - s0) < 1e-13
+    # facet bookkeeping of the synthetic mesh
+    assert len(m.int_facet_cells) == 7 * 6 + 8 * 5 and len(m.ext_facet_cells) == 2 * (8 + 6)
