@@ -172,6 +172,11 @@ __device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
     unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem));
 }
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int K>
 __device__ __forceinline__ void cp_async_wait()
@@ -212,6 +217,7 @@ struct Unit {
     int cur, end; // chunk bookkeeping (warp uniform)
     bool valid;   // per lane: this lane's cell exists
     int col, layer;
+    int src;      // cell slot holding this column's staged map rows
 };
 
 template <int N, bool MASS, bool ATOMIC, int MINB, bool MATRIX = false>
@@ -290,6 +296,11 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
         if (!u.valid) { ci = 0; kk = 0; }
         u.layer = P.lay_first + P.lay_step * kk;
         u.col = P.collist ? __ldg(P.collist + ci) : (P.col0 + (int)ci);
+        // cells of the warp that sit in the same column share one staged copy of
+        // the map / vertex rows: the lowest such cell (leader) copies, the
+        // others read its slot
+        const unsigned peers = __match_any_sync(0xffffffffu, u.valid ? u.col : -1 - cw);
+        u.src = (__ffs(peers) - 1) / N;
     };
 
     // Three-stage gather pipeline, all through cp.async (no registers held, no
@@ -304,18 +315,23 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
     // s_coord are shared by the N lanes of a cell and are read after the
     // wait + __syncwarp at the top of the loop.
     auto stageA = [&](const Unit &u) {
-        if (u.valid && u.comp == 0) {
+        if (u.valid && u.comp == 0 && u.src == cw) {
             const int *mrow = P.map0 + (long long)u.col * ND;
             int *sm = s_mapraw + cw * US;
+            if ((ND % 4) == 0 && (US % 4) == 0) {
+                // rows are 16-byte aligned: 128-bit copies
+                for (int j = t; j < ND / 4; j += N) cp_async16(sm + 4 * j, mrow + 4 * j);
+            } else {
 #pragma unroll
-            for (int j = 0; j < N * N; j++) cp_async4(sm + j * N + t, mrow + j * N + t);
+                for (int j = 0; j < N * N; j++) cp_async4(sm + j * N + t, mrow + j * N + t);
+            }
             int *sv = s_vidx + (u.ib * CWS + cw) * 8;
             for (int v = t; v < 8; v += N) cp_async4(sv + v, P.map1 + (long long)u.col * 8 + v);
         }
     };
     auto stageB_coords = [&](const Unit &u) {
         if (u.valid && u.comp == 0) {
-            const int *sv = s_vidx + (u.ib * CWS + cw) * 8;
+            const int *sv = s_vidx + (u.ib * CWS + u.src) * 8;
             double *scd = s_coord + cw * CS;
             for (int i = t; i < 24; i += N) {
                 int v = i / 3, a = i - v * 3;
@@ -328,7 +344,7 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
         if (u.valid) {
             double *su = s_u + cw * US;
             int *si = s_idx + (u.ib * CWS + cw) * US;
-            const int *sm = s_mapraw + cw * US;
+            const int *sm = s_mapraw + u.src * US;
             int g[N];
             if (u.comp == 0) {
 #pragma unroll
@@ -350,7 +366,7 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
         }
     };
 
-    Unit cur{-1, 0, 0, 0, 0, false, 0, 0};
+    Unit cur{-1, 0, 0, 0, 0, false, 0, 0, 0};
     cur = advance(cur);
     decode(cur);
     Unit nxt = advance(cur);
@@ -502,6 +518,7 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
                 }
             }
 
+            __syncwarp();            // all lanes are done reading the staged rows of `nxt`
             stageA(nn);
             cp_async_commit();
 

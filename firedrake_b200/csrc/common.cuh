@@ -69,6 +69,7 @@ struct fdb_kernel_s {
 };
 
 extern "C" int fdb_mirror_set_version(const void *host, uint64_t version);
+bool fdb_mirror_is_current(const void *host, size_t nbytes, uint64_t version);
 
 typedef struct fdb_mat_s *fdb_mat_t;
 int fdb_mat_device_view(fdb_mat_t m, const long long **rowptr, const fdb_int **colidx, double **vals,

@@ -4,6 +4,7 @@
 // creation validates the descriptor against the set of hand-written sm_100a
 // kernels and precomputes the tables they need.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -89,6 +90,136 @@ int build_colouring(fdb_kernel_s *k, const fdb_int *h_map, fdb_int ncols)
     FDB_CUDA(cudaMemcpyAsync(k->d_colour_cols, sorted.data(), sizeof(fdb_int) * ncols,
                              cudaMemcpyHostToDevice, ctx().stream));
     FDB_CUDA(cudaStreamSynchronize(ctx().stream));
+    return 0;
+}
+
+// Drop-in (host pointer) call of a 1-form with the output just zeroed by the
+// assembler: instead of "upload x, compute, download y" back to back, the
+// iteration range is cut into chunks of columns and three streams overlap
+//     H2D of the x rows chunk k+1 needs  |  kernel on chunk k  |  D2H of the
+//     y rows no later chunk can touch
+// (PCIe is full duplex, so the end-to-end time tends to max(H2D, D2H) instead
+// of their sum).  Which rows a chunk touches is read off the map on the host:
+// with Firedrake's cell-closure numbering the touched range grows monotonically
+// with the chunk index; for an arbitrary numbering the schedule degenerates to
+// the monolithic one by construction (everything uploaded before chunk 0,
+// downloaded after the last), never to a wrong one.
+struct PipelinePlan {
+    const void *map_key = nullptr;
+    fdb_int start = 0, end = 0;
+    int nlay = 0;
+    std::vector<fdb_int> c0, c1;          // column range of each chunk
+    std::vector<long long> upto;          // rows [0, upto[k]) must be resident before chunk k
+    std::vector<long long> final_below;   // rows [0, final_below[k]) are final after chunk k
+};
+static PipelinePlan g_plan;
+static cudaStream_t g_h2d = nullptr, g_d2h = nullptr;
+static std::vector<cudaEvent_t> g_ev_up, g_ev_done;
+
+static int pipelined_host_action(fdb_kernel_s *k, const fdb_call_args *a, int nlay)
+{
+    static const int nchunks_env = getenv("FDB_PIPELINE_CHUNKS") ? atoi(getenv("FDB_PIPELINE_CHUNKS")) : 16;
+    const fdb_int ncols = a->end - a->start;
+    int K = nchunks_env;
+    if (K <= 1 || ncols < 64 * K) return -1;
+    const int arity = k->arity;
+    const size_t nrows = a->arg_bytes[0] / (sizeof(double) * k->desc.cdim);
+    cudaStream_t st = ctx().stream;
+    if (!g_h2d) {
+        FDB_CUDA(cudaStreamCreateWithFlags(&g_h2d, cudaStreamNonBlocking));
+        FDB_CUDA(cudaStreamCreateWithFlags(&g_d2h, cudaStreamNonBlocking));
+    }
+    while ((int)g_ev_up.size() < K) {
+        cudaEvent_t e1, e2;
+        FDB_CUDA(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+        FDB_CUDA(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+        g_ev_up.push_back(e1);
+        g_ev_done.push_back(e2);
+    }
+    PipelinePlan &pl = g_plan;
+    if (pl.map_key != (const void *)a->maps[0] || pl.start != a->start || pl.end != a->end ||
+        pl.nlay != nlay || (int)pl.c0.size() != K) {
+        // host analysis of the map (cached while the same map is passed)
+        const fdb_int *map = a->maps[0];
+        pl = PipelinePlan();
+        pl.map_key = a->maps[0];
+        pl.start = a->start;
+        pl.end = a->end;
+        pl.nlay = nlay;
+        std::vector<long long> lo(K), hi(K);
+        for (int c = 0; c < K; c++) {
+            fdb_int b0 = a->start + (fdb_int)((long long)ncols * c / K);
+            fdb_int b1 = a->start + (fdb_int)((long long)ncols * (c + 1) / K);
+            pl.c0.push_back(b0);
+            pl.c1.push_back(b1);
+            long long l = (long long)nrows, h = 0;
+            for (fdb_int col = b0; col < b1; col++)
+                for (int i = 0; i < arity; i++) {
+                    long long v = map[(size_t)col * arity + i];
+                    long long top = v + (long long)k->h_off0[i] * (nlay - 1);
+                    if (v < l) l = v;
+                    if (top + 1 > h) h = top + 1;
+                }
+            lo[c] = l;
+            hi[c] = h;
+        }
+        pl.upto.resize(K);
+        pl.final_below.resize(K);
+        long long m = 0;
+        for (int c = 0; c < K; c++) {
+            if (hi[c] > m) m = hi[c];
+            pl.upto[c] = m;
+        }
+        long long mn = (long long)nrows;
+        for (int c = K - 1; c >= 0; c--) {
+            pl.final_below[c] = mn;          // min over later chunks of their lowest row
+            if (lo[c] < mn) mn = lo[c];
+        }
+        pl.final_below[K - 1] = (long long)nrows;
+    }
+    void *dy, *dx, *dc, *dm0, *dm1;
+    // static inputs through the mirror cache (uploaded once)
+    if (fdb_mirror_acquire(a->args[1], a->arg_bytes[1], a->arg_versions[1], 1, &dc)) return 1;
+    if (fdb_mirror_acquire(a->maps[0], a->map_bytes[0], 0, 1, &dm0)) return 1;
+    if (fdb_mirror_acquire(a->maps[1], a->map_bytes[1], 0, 1, &dm1)) return 1;
+    if (fdb_mirror_acquire(a->args[0], a->arg_bytes[0], a->arg_versions[0], 0, &dy)) return 1;
+    bool x_current = fdb_mirror_is_current(a->args[2], a->arg_bytes[2], a->arg_versions[2]);
+    if (fdb_mirror_acquire(a->args[2], a->arg_bytes[2], a->arg_versions[2], 0, &dx)) return 1;
+    const size_t rowb = sizeof(double) * k->desc.cdim;
+    // uploads wait for whatever the engine stream was doing with these buffers
+    FDB_CUDA(cudaEventRecord(g_ev_done[0], st));
+    FDB_CUDA(cudaStreamWaitEvent(g_h2d, g_ev_done[0], 0));
+    FDB_CUDA(cudaStreamWaitEvent(g_d2h, g_ev_done[0], 0));
+    // rows above the highest touched one: never gathered, must still read as zero
+    if (pl.upto[K - 1] < (long long)nrows)
+        FDB_CUDA(cudaMemsetAsync((char *)dy + pl.upto[K - 1] * rowb, 0,
+                                 (size_t)((long long)nrows - pl.upto[K - 1]) * rowb, st));
+    long long up_done = 0, down_done = 0;
+    for (int c = 0; c < K; c++) {
+        if (pl.upto[c] > up_done) {
+            if (!x_current)
+                FDB_CUDA(cudaMemcpyAsync((char *)dx + up_done * rowb, (const char *)a->args[2] + up_done * rowb,
+                                         (size_t)(pl.upto[c] - up_done) * rowb, cudaMemcpyHostToDevice, g_h2d));
+            FDB_CUDA(cudaMemsetAsync((char *)dy + up_done * rowb, 0, (size_t)(pl.upto[c] - up_done) * rowb, st));
+            up_done = pl.upto[c];
+        }
+        FDB_CUDA(cudaEventRecord(g_ev_up[c], g_h2d));
+        FDB_CUDA(cudaStreamWaitEvent(st, g_ev_up[c], 0));
+        if (fdb_launch_helmholtz_action(k, pl.c0[c], pl.c1[c], nlay, nullptr, (double *)dy, (const double *)dc,
+                                        (const double *)dx, (const fdb_int *)dm0, (const fdb_int *)dm1))
+            return 1;
+        FDB_CUDA(cudaEventRecord(g_ev_done[c], st));
+        if (pl.final_below[c] > down_done) {
+            FDB_CUDA(cudaStreamWaitEvent(g_d2h, g_ev_done[c], 0));
+            FDB_CUDA(cudaMemcpyAsync((char *)a->args[0] + down_done * rowb, (const char *)dy + down_done * rowb,
+                                     (size_t)(pl.final_below[c] - down_done) * rowb, cudaMemcpyDeviceToHost, g_d2h));
+            down_done = pl.final_below[c];
+        }
+    }
+    FDB_CUDA(cudaStreamSynchronize(g_d2h));
+    FDB_CUDA(cudaStreamSynchronize(st));
+    if (up_done == (long long)nrows) fdb_mirror_set_version(a->args[2], a->arg_versions[2]);
+    fdb_mirror_set_version(a->args[0], a->arg_versions[0] + 1);
     return 0;
 }
 
@@ -309,6 +440,12 @@ int fdb_kernel_call(fdb_kernel_t k, const fdb_call_args *a)
         set_error("fdb_kernel_call: 1-form expects 3 args (y, coords, x) and 2 maps, got %d/%d",
                   a->nargs, a->nmaps);
         return 1;
+    }
+    if (a->location == FDB_LOC_HOST && a->arg_versions && a->arg_bytes && a->map_bytes &&
+        a->writeback && a->output_is_zero && !a->subset && extruded &&
+        k->desc.scatter == FDB_SCATTER_ATOMIC) {
+        int rc = pipelined_host_action(k, a, nlay);
+        if (rc >= 0) return rc;      // -1: not applicable, fall through to the monolithic path
     }
     void *dargs[3];
     const fdb_int *dmaps[2];

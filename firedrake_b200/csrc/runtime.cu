@@ -44,6 +44,13 @@ static std::unordered_map<const void *, Mirror> g_mirrors;
 
 using namespace fdb;
 
+bool fdb_mirror_is_current(const void *host, size_t nbytes, uint64_t version)
+{
+    auto it = fdb::g_mirrors.find(host);
+    return it != fdb::g_mirrors.end() && it->second.valid && it->second.nbytes == nbytes &&
+           it->second.version == version;
+}
+
 extern "C" {
 
 const char *fdb_last_error(void) { return g_err; }

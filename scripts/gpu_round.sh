@@ -1,8 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-python benchmarks/run_configs.py > gpurun_out/configs_r01.jsonl 2> gpurun_out/configs.err
-cat gpurun_out/configs_r01.jsonl | cut -c1-420
-tail -3 gpurun_out/configs.err
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_r01.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > gpurun_out/ncu_launch.log 2>&1
-tail -12 gpurun_out/launches_r01.csv | cut -c1-300
+python bench.py --n 256 --steps 5 --warmup 3 --no-e2e --no-cpu 2>&1 | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['ms_per_step'], d['roofline']['kernel_ms'], d['value'], d['clocks'])"
+ncu --set full --clock-control none --import-source on -k regex:helmholtz -s 3 -c 1 -o gpurun_out/prof_action7 python bench.py --n 128 --steps 1 --warmup 3 --no-e2e --no-cpu > gpurun_out/ncu.log 2>&1
+tail -2 gpurun_out/ncu.log
