@@ -332,8 +332,8 @@ def main():
                 y.zero()                         # assemble() zeroes the tensor (lazy here)
                 hloop()                          # H2D x, device memset y, kernel, D2H y
                 return float(y._data[0])
-            path = ("op2.Parloop(location='host') -> fdb_kernel_call(FDB_LOC_HOST): pinned host Dats, "
-                    "H2D of x and D2H of y inside the timed region")
+            path = ("op2.Parloop(location='host') -> fdb_kernel_call(FDB_LOC_HOST): pinned host Dats; the "
+                    "engine overlaps H2D of x | kernel | D2H of y over 32 column chunks (3 streams)")
         else:
             def hstep():
                 x.data_with_halos[0] += 0.0      # host write -> H2D of the local x

@@ -118,7 +118,7 @@ static std::vector<cudaEvent_t> g_ev_up, g_ev_done;
 
 static int pipelined_host_action(fdb_kernel_s *k, const fdb_call_args *a, int nlay)
 {
-    static const int nchunks_env = getenv("FDB_PIPELINE_CHUNKS") ? atoi(getenv("FDB_PIPELINE_CHUNKS")) : 16;
+    static const int nchunks_env = getenv("FDB_PIPELINE_CHUNKS") ? atoi(getenv("FDB_PIPELINE_CHUNKS")) : 32;
     const fdb_int ncols = a->end - a->start;
     int K = nchunks_env;
     if (K <= 1 || ncols < 64 * K) return -1;
