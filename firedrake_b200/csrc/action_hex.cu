@@ -54,6 +54,8 @@ struct HelmParams {
     double *vals;
     const int *row_lg;       // -1 = row dropped (Dirichlet), NULL = identity
     const int *col_lg;
+    const unsigned short *rank_tab;   // within-row positions per (column, layer class, j, i) or NULL
+    int nvar, nlay_total;
     int chunk;               // items per work chunk
     int *counter;            // device work counter (zeroed before the launch)
     double alpha, beta;
@@ -548,6 +550,12 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
                 // lane's test dofs; negative (BC-masked) indices are dropped
                 int gcol = valid ? si[comp] : -1;
                 if (gcol >= 0 && P.col_lg) gcol = __ldg(P.col_lg + gcol);
+                const unsigned short *rk = nullptr;
+                if (P.rank_tab && valid) {
+                    const int lay = cur.layer;
+                    const int v = P.nlay_total < 3 ? lay : (lay == 0 ? 0 : (lay == P.nlay_total - 1 ? 2 : 1));
+                    rk = P.rank_tab + (((long long)cur.col * P.nvar + v) * ND + comp) * ND;
+                }
                 if (gcol >= 0) {
 #pragma unroll
                     for (int x = 0; x < N; x++)
@@ -556,10 +564,15 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
                             int grow = si[(x * N + yy) * N + t];
                             if (P.row_lg) grow = __ldg(P.row_lg + grow);
                             if (grow < 0) continue;
-                            long long lo = __ldg(P.rowptr + grow), hi = __ldg(P.rowptr + grow + 1);
-                            while (hi - lo > 1) {
-                                long long mid = (lo + hi) >> 1;
-                                if (__ldg(P.colidx + mid) <= gcol) lo = mid; else hi = mid;
+                            long long lo = __ldg(P.rowptr + grow);
+                            if (rk) {
+                                lo += __ldg(rk + (x * N + yy) * N + t);
+                            } else {
+                                long long hi = __ldg(P.rowptr + grow + 1);
+                                while (hi - lo > 1) {
+                                    long long mid = (lo + hi) >> 1;
+                                    if (__ldg(P.colidx + mid) <= gcol) lo = mid; else hi = mid;
+                                }
                             }
                             if (ATOMIC) atomicAdd(P.vals + lo, u[x][yy]);
                             else P.vals[lo] += u[x][yy];
@@ -728,6 +741,9 @@ int launch_matrix_n(fdb_kernel_s *k, fdb_int start, fdb_int end, int nlay, const
         P.xq[i] = k->desc.xq[i];
     }
     fdb_mat_device_view(mat, &P.rowptr, &P.colidx, &P.vals, &P.row_lg, &P.col_lg);
+    fdb_mat_rank_table(mat, &P.rank_tab, &P.nvar);
+    P.nlay_total = nlay;
+    if (subset || k->desc.cell != FDB_CELL_HEX_EXTRUDED) P.rank_tab = nullptr;   // table is per column of the full set
     P.counter = c.work_counter;
     P.collist = subset;
     P.col0 = start;

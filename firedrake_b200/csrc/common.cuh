@@ -74,6 +74,7 @@ bool fdb_mirror_is_current(const void *host, size_t nbytes, uint64_t version);
 typedef struct fdb_mat_s *fdb_mat_t;
 int fdb_mat_device_view(fdb_mat_t m, const long long **rowptr, const fdb_int **colidx, double **vals,
                         const fdb_int **row_lg, const fdb_int **col_lg);
+int fdb_mat_rank_table(fdb_mat_t m, const unsigned short **rank, int *nvar);
 int fdb_launch_helmholtz_matrix(fdb_kernel_s *k, fdb_int start, fdb_int end, int nlay,
                                 const fdb_int *subset, fdb_mat_t mat, const double *coords,
                                 const fdb_int *map0, const fdb_int *map1);

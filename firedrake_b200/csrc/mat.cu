@@ -14,6 +14,8 @@
 // with sorted columns per row.  The element-tensor scatter finds a position by
 // binary search inside the row (the cost model of PETSc's MatSetValues, here
 // in parallel and hitting L2).
+#include <stdlib.h>
+
 #include <thrust/device_ptr.h>
 #include <thrust/execution_policy.h>
 #include <thrust/scan.h>
@@ -31,6 +33,12 @@ struct fdb_mat_s {
     fdb_int *d_colidx = nullptr;
     double *d_vals = nullptr;
     fdb_int *d_row_lgmap = nullptr, *d_col_lgmap = nullptr;   // NULL = identity
+    // within-row position of every (test dof i, trial dof j) pair of a cell,
+    // per column and layer class (bottom / interior / top): extruded numbering
+    // is translation invariant along a column, so interior layers share one
+    // table.  rank[((col*nvar + v)*arity + j)*arity + i].  NULL: binary search.
+    unsigned short *d_rank = nullptr;
+    int nvar = 0, arity = 0, nlay = 0;
 };
 
 namespace {
@@ -67,6 +75,34 @@ __global__ void k_count_rows(const unsigned long long *__restrict__ keys, long l
         unsigned long long r = k / (unsigned long long)nrows;
         colidx[i] = (fdb_int)(k - r * nrows);
         atomicAdd((unsigned long long *)&counts[r], 1ull);
+    }
+}
+
+__global__ void k_build_rank(const fdb_int *__restrict__ map, const fdb_int *__restrict__ off,
+                             fdb_int ncols, int arity, int nlay, int nvar,
+                             const long long *__restrict__ rowptr, const fdb_int *__restrict__ colidx,
+                             unsigned short *__restrict__ rank)
+{
+    const long long per_col = (long long)nvar * arity * arity;
+    const long long total = (long long)ncols * per_col;
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const fdb_int c = (fdb_int)(t / per_col);
+        int e = (int)(t - (long long)c * per_col);
+        const int v = e / (arity * arity);
+        e -= v * arity * arity;
+        const int j = e / arity, i = e - j * arity;
+        // representative layer of the class
+        const int layer = nlay < 3 ? v : (v == 0 ? 0 : (v == 1 ? 1 : nlay - 1));
+        const fdb_int r = map[(long long)c * arity + i] + (off ? off[i] * layer : 0);
+        const fdb_int cc = map[(long long)c * arity + j] + (off ? off[j] * layer : 0);
+        long long lo = rowptr[r], hi = rowptr[r + 1];
+        const long long base = lo;
+        while (hi - lo > 1) {
+            long long mid = (lo + hi) >> 1;
+            if (colidx[mid] <= cc) lo = mid; else hi = mid;
+        }
+        rank[t] = (unsigned short)(lo - base);
     }
 }
 
@@ -113,6 +149,13 @@ int grid1d(long long n)
 }  // namespace
 
 // used by the element-tensor scatter in action_hex.cu / tri_p1.cu
+int fdb_mat_rank_table(fdb_mat_t m, const unsigned short **rank, int *nvar)
+{
+    *rank = m->d_rank;
+    *nvar = m->nvar;
+    return 0;
+}
+
 int fdb_mat_device_view(fdb_mat_t m, const long long **rowptr, const fdb_int **colidx, double **vals,
                         const fdb_int **row_lg, const fdb_int **col_lg)
 {
@@ -188,6 +231,24 @@ int fdb_mat_create(fdb_int nrows, const fdb_int *map_host, fdb_int ncolumns, int
     FDB_CUDA(cudaMemsetAsync(m->d_vals, 0, sizeof(double) * (size_t)nnz, st));
     FDB_CUDA(cudaStreamSynchronize(st));
     cudaFree(keys);
+    keys = nullptr;
+    // position table for the element-tensor scatter (skipped when it would not fit)
+    const int nlay = nlayers;
+    m->arity = arity;
+    m->nlay = nlay;
+    m->nvar = nlay < 3 ? nlay : 3;
+    {
+        const double tab_bytes = (double)ncolumns * m->nvar * arity * arity * 2.0;
+        FDB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        static const bool use_rank = !(getenv("FDB_MAT_NO_RANK") && atoi(getenv("FDB_MAT_NO_RANK")));
+        if (use_rank && tab_bytes < 0.25 * (double)free_b && tab_bytes < 8e9) {
+            FDB_CUDA(cudaMalloc(&m->d_rank, (size_t)tab_bytes));
+            k_build_rank<<<grid1d((long long)(tab_bytes / 2)), 256, 0, st>>>(
+                d_map, d_off, ncolumns, arity, nlay, m->nvar, m->d_rowptr, m->d_colidx, m->d_rank);
+            FDB_LAUNCH_CHECK();
+            FDB_CUDA(cudaStreamSynchronize(st));
+        }
+    }
     cudaFree(d_map);
     if (d_off) cudaFree(d_off);
     *out = m;
@@ -204,6 +265,7 @@ int fdb_mat_destroy(fdb_mat_t m)
         cudaFree(m->d_vals);
         cudaFree(m->d_row_lgmap);
         cudaFree(m->d_col_lgmap);
+        if (m->d_rank) cudaFree(m->d_rank);
     }
     delete m;
     return 0;

@@ -1,7 +1,16 @@
 #!/bin/bash
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-for k in 1 8 16 32; do
-echo "== FDB_PIPELINE_CHUNKS=$k"
-FDB_PIPELINE_CHUNKS=$k python bench.py --n 256 --steps 5 --warmup 3 --no-cpu 2>&1 | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['ms_per_step'], d['value'], d['e2e']['ms_per_step'], d['e2e']['value'])"
-done
+python - <<'PY'
+import sys, json
+sys.path.insert(0, '.')
+sys.argv=['x']
+import benchmarks.run_configs as rc
+from firedrake_b200 import _lib
+_lib.init(0)
+for n,p in [(128,1),(48,2),(32,3),(64,3)]:
+    try:
+        print(json.dumps(rc.matrix_case(f"Poisson CG{p} matrix", n, p)), flush=True)
+    except Exception as e:
+        print("ERR", repr(e)[:300])
+PY
