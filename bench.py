@@ -309,11 +309,15 @@ def main():
     peak_gbs = peaks.get("hbm_gbs", 6650.0)
     abytes = algorithmic_bytes(V, mesh)
     achieved = abytes / (kernel_ms * 1e-3) / 1e9
+    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one launch, from the
+    # `ncu --set full` capture summarised in profiles/r01_action_cg3_n256_summary.txt
+    # (8.28 GB read: x, coordinates and the y lines the atomics fetch; 3.86 GB written: y)
+    NCU_TRAFFIC = {(256, 3, 1): 12.14e9}
     FP64_PEAK = 37.1   # TFLOP/s: tools/microbench_fp64.cu on this pool (DFMA 34.2, DMMA 37.1, shared pipe)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                "frac": achieved / peak_gbs, "traffic": None,
+                "frac": achieved / peak_gbs, "traffic": NCU_TRAFFIC.get((n, p, world)),
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
-                "kernel": f"helmholtz_action_kernel<{p + 1},false,true,2>", "kernel_ms": kernel_ms,
+                "kernel": f"helmholtz_action_kernel<{p + 1},false,true,3>", "kernel_ms": kernel_ms,
                 "algorithmic_bytes_per_launch": abytes,
                 "note": "this kernel is fp64-pipe-bound, not HBM-bound (DESIGN.md section 4): the binding "
                         "fraction is fp64.frac; the HBM fraction is reported because the contract asks for it",

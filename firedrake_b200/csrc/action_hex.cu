@@ -61,6 +61,7 @@ struct HelmParams {
     double alpha, beta;
     double B[N * N];         // B[q][a]
     double Dt[N * N];        // Dt[q][q']
+    double DtR[N * N];       // DtR[q][j] = Dt[q][(j + q) % N]  (rolled zeta loop)
     double wq[N];
     double xq[N];
 };
@@ -116,10 +117,11 @@ struct Tile {
     static constexpr int PAD = (N == 4) ? 0 : ((N * N * N) % 2 == 0 ? 2 : 1);
     static constexpr int STRIDE = N * N * N + PAD;
     double *base;
-    int t, r, k[N];
+    int t, r, k[N], cwrot;
     __device__ __forceinline__ Tile(double *warp_smem, int cw, int t_) : t(t_)
     {
         base = warp_smem + cw * STRIDE;
+        cwrot = cw;
         if (N == 4) {
             r = (t_ + cw) & 3;
 #pragma unroll
@@ -144,6 +146,12 @@ struct Tile {
         for (int x = 0; x < N; x++)
 #pragma unroll
             for (int y = 0; y < N; y++) a[x][y] = base[(x * N + k[y]) * N + r];
+    }
+    // pointer to element (x = 0, lane's y, z) for a RUN-TIME z; (x, y, z) is N*N further per x
+    __device__ __forceinline__ double *row_Y(int z) const
+    {
+        const int kz = (N == 4) ? ((z + cwrot) & 3) : z;
+        return base + r * N + kz;
     }
     __device__ __forceinline__ double get_Y(int x, int z) const { return base[(x * N + r) * N + k[z]]; }
     __device__ __forceinline__ void put_Y(int x, int z, double v) const { base[(x * N + r) * N + k[z]] = v; }
@@ -458,13 +466,23 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
             for (int i = 0; i < N; i++)
 #pragma unroll
                 for (int j = 0; j < N; j++) Vp[i][j] = 0.0;
-#pragma unroll
+            // single-buffered staging: the values / coordinates of `cur` were
+            // consumed (and a __syncwarp passed) before this point
+            stageB_coords(nxt);
+            // The zeta loop is ROLLED (the fully unrolled body did not fit the
+            // 32 KB instruction cache: ~15-20 % no-instruction stalls).  Register
+            // arrays cannot be indexed by a run-time qz, so U and Vp are kept
+            // rotated: column 0 is always the current zeta plane, and both are
+            // rotated by one column at the end of each trip (N trips = identity).
+            // DtR[qz][j] = Dt[qz][(j + qz) % N] is the matching rotation of the
+            // derivative row.
+#pragma unroll 1
             for (int qz = 0; qz < N; qz++) {
-                // single-buffered staging: the values / coordinates of `cur`
-                // were consumed (and a __syncwarp passed) before this point
-                if (qz == 0) stageB_coords(nxt);
                 stageB_part(nxt, ubuf ^ 1, qz);
                 const double zeta = P.xq[qz];
+                double dz[N];
+#pragma unroll
+                for (int j = 0; j < N; j++) dz[j] = P.DtR[qz * N + j];
                 double ca[3], pb[3], qb[3];
 #pragma unroll
                 for (int a = 0; a < 3; a++) {
@@ -474,6 +492,7 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
                 }
                 const double wyz_a = wy_alpha * P.wq[qz];
                 const double wyz_b = wy_beta * P.wq[qz];
+                double *trow = tile.row_Y(qz);
 #pragma unroll
                 for (int qx = 0; qx < N; qx++) {
                     const double xi = P.xq[qx];
@@ -486,10 +505,10 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
                     double gx = 0.0, gz = 0.0;
 #pragma unroll
                     for (int q = 0; q < N; q++) {
-                        gx = fma(P.Dt[qx * N + q], U[q][qz], gx);
-                        gz = fma(P.Dt[qz * N + q], U[qx][q], gz);
+                        gx = fma(P.Dt[qx * N + q], U[q][0], gx);
+                        gz = fma(dz[q], U[qx][q], gz);
                     }
-                    const double gy = tile.get_Y(qx, qz);
+                    const double gy = trow[qx * N * N];
                     // cofactor rows: r0 = b x c, r1 = c x a, r2 = a x b
                     double r0[3], r1[3], r2[3];
                     r0[0] = cb[1] * cc[2] - cb[2] * cc[1];
@@ -510,13 +529,25 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
                     const double fx = s * (r0[0] * h[0] + r0[1] * h[1] + r0[2] * h[2]);
                     const double fy = s * (r1[0] * h[0] + r1[1] * h[1] + r1[2] * h[2]);
                     const double fz = s * (r2[0] * h[0] + r2[1] * h[1] + r2[2] * h[2]);
-                    tile.put_Y(qx, qz, fy);
+                    trow[qx * N * N] = fy;
 #pragma unroll
                     for (int q = 0; q < N; q++) {
-                        Vp[q][qz] = fma(P.Dt[qx * N + q], fx, Vp[q][qz]);
-                        Vp[qx][q] = fma(P.Dt[qz * N + q], fz, Vp[qx][q]);
+                        Vp[q][0] = fma(P.Dt[qx * N + q], fx, Vp[q][0]);
+                        Vp[qx][q] = fma(dz[q], fz, Vp[qx][q]);
                     }
-                    if (MASS) Vp[qx][qz] = fma(wyz_b * P.wq[qx] * adet, U[qx][qz], Vp[qx][qz]);
+                    if (MASS) Vp[qx][0] = fma(wyz_b * P.wq[qx] * adet, U[qx][0], Vp[qx][0]);
+                }
+                // rotate: column j <- column j+1
+#pragma unroll
+                for (int x = 0; x < N; x++) {
+                    const double u0 = U[x][0], v0 = Vp[x][0];
+#pragma unroll
+                    for (int j = 0; j < N - 1; j++) {
+                        U[x][j] = U[x][j + 1];
+                        Vp[x][j] = Vp[x][j + 1];
+                    }
+                    U[x][N - 1] = u0;
+                    Vp[x][N - 1] = v0;
                 }
             }
 
@@ -676,12 +707,14 @@ int launch_n(fdb_kernel_s *k, fdb_int start, fdb_int end, int nlay, const fdb_in
         P.B[i] = k->desc.B[i];
         P.Dt[i] = k->Dt[i];
     }
+    for (int q = 0; q < N; q++)
+        for (int j = 0; j < N; j++) P.DtR[q * N + j] = k->Dt[q * N + (j + q) % N];
     for (int i = 0; i < N; i++) {
         P.wq[i] = k->desc.wq[i];
         P.xq[i] = k->desc.xq[i];
     }
     const bool mass = k->desc.beta != 0.0;
-    static const int minb = getenv("FDB_MINB") ? atoi(getenv("FDB_MINB")) : 2;
+    static const int minb = getenv("FDB_MINB") ? atoi(getenv("FDB_MINB")) : 3;   // N == 4: 3 CTAs x 4 warps, 168 registers, no spills
     static const int cap = getenv("FDB_CTAS_PER_SM") ? atoi(getenv("FDB_CTAS_PER_SM")) : 0;
     P.counter = c.work_counter;
     if (k->desc.scatter == FDB_SCATTER_ATOMIC) {
@@ -736,6 +769,8 @@ int launch_matrix_n(fdb_kernel_s *k, fdb_int start, fdb_int end, int nlay, const
         P.B[i] = k->desc.B[i];
         P.Dt[i] = k->Dt[i];
     }
+    for (int q = 0; q < N; q++)
+        for (int j = 0; j < N; j++) P.DtR[q * N + j] = k->Dt[q * N + (j + q) % N];
     for (int i = 0; i < N; i++) {
         P.wq[i] = k->desc.wq[i];
         P.xq[i] = k->desc.xq[i];
