@@ -176,3 +176,48 @@ def test_pipelined_host_call(engine, oracle, permute):
         loop()
         assert relerr(y.data_ro, yo) < TOL
         x.data[:] *= 1.0            # version bump -> x is uploaded again (pipelined)
+
+
+@pytest.mark.parametrize("p", [1, 3])
+def test_native_hex_mesh_maps(engine, oracle, p):
+    """Non-extruded hexes (``BoxMesh(..., hexahedral=True)``-style maps, reference
+    firedrake/utility_meshes.py:1617-1636): one map row per cell, no offsets.
+    Built here by expanding the extruded map; must equal the extruded result."""
+    mesh = ExtrudedHexMesh(4, 3, 5, warp=0.05, permute_seed=4)
+    V = mesh.function_space(p)
+    full = V.full_cell_node_list()
+    cfull = mesh.coord_space.full_cell_node_list()
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(full.shape[0])             # cells in arbitrary order
+    cells = op2.Set(full.shape[0])
+    nodes = op2.Set(V.node_count)
+    vnodes = op2.Set(mesh.coord_space.node_count)
+    m0 = op2.Map(cells, nodes, V.arity, full[perm])
+    m1 = op2.Map(cells, vnodes, 8, cfull[perm])
+    x = op2.Dat(nodes, rng.standard_normal(V.node_count))
+    y = op2.Dat(nodes)
+    X = op2.Dat(op2.DataSet(vnodes, 3), mesh.coordinates)
+    op2.par_loop(op2.Kernel("helmholtz", degree=p, alpha=1.0, beta=0.7), cells,
+                 y(op2.INC, m0), X(op2.READ, m1), x(op2.READ, m0))
+    yo = oracle_action(oracle, mesh, V, p, x.data_ro, alpha=1.0, beta=0.7)
+    assert relerr(y.data_ro, yo) < TOL
+
+
+def test_edge_cases(engine, oracle):
+    """Empty ranges, a single layer, a single column, ranges not starting at 0."""
+    p = 2
+    mesh = ExtrudedHexMesh(3, 2, 1, warp=0.03)                     # one layer
+    V, cells, m0, m1, x, y, X = build(mesh, p)
+    k = op2.Kernel("helmholtz", degree=p)
+    gk = op2.GlobalKernel(k, [m0, m1], extruded=True)
+    loop = op2.Parloop(gk, cells, [y(op2.INC, m0), X(op2.READ, m1), x(op2.READ, m0)])
+    loop._compute((2, 2))                                          # empty: no launch, no error
+    assert np.abs(y.data_ro).max() == 0.0
+    loop._compute((1, 4))                                          # start > 0
+    yo = oracle_action(oracle, mesh, V, p, x.data_ro, start=1, end=4)
+    assert relerr(y.data_ro, yo) < TOL
+    mesh1 = ExtrudedHexMesh(1, 1, 9, warp=0.0)                     # a single column
+    V1, cells1, a0, a1, x1, y1, X1 = build(mesh1, 3)
+    op2.par_loop(op2.Kernel("helmholtz", degree=3, beta=1.0), cells1, y1(op2.INC, a0), X1(op2.READ, a1),
+                 x1(op2.READ, a0))
+    assert relerr(y1.data_ro, oracle_action(oracle, mesh1, V1, 3, x1.data_ro, beta=1.0)) < TOL
