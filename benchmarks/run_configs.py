@@ -85,6 +85,25 @@ def cg_case(name, n, p, iters=20):
             "residual_reduction": hist[-1] / hist[0]}
 
 
+def dg_case(name, n, steps=10):
+    from firedrake_b200.assemble import DGAdvection
+    from firedrake_b200.utility_meshes import QuadMesh
+    m = QuadMesh(n, n)
+    X = m.coordinates
+    u = np.stack([0.5 - X[:, 1], X[:, 0] - 0.5], axis=1)
+    prob = DGAdvection(m, dt=2 * np.pi / 600 * 40 / n, q_in=1.0)
+    q = prob.function(1.0 + np.random.default_rng(0).random(m.num_cells * 4))
+    uu = prob.velocity(u)
+    out = prob.function()
+    ms = timed(lambda: prob.assemble(q, uu, out), steps)
+    ndof = m.num_cells * 4
+    # algorithmic bytes: read q + write out (16 B/dof), coordinates + velocity (32 B/vertex),
+    # cell maps (32 B/cell) and facet maps (2*(32+32)+8 B per interior facet)
+    nbytes = 16 * ndof + 32 * m.node_count + 32 * m.num_cells + 136 * len(m.int_facet_cells)
+    return {"case": name, "n": n, "cells": m.num_cells, "dofs": ndof, "ms": ms,
+            "dofs_per_s": ndof / ms * 1e3, "algorithmic_GBps": nbytes / ms / 1e6}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
@@ -100,6 +119,7 @@ def main():
         lambda: action_case("config4 vector Helmholtz CG4 action (cdim 3)", 16 if q else 64, 4, cdim=3, beta=1.0),
         lambda: action_case("config5 Poisson CG5 action", 32 if q else 128, 5),
         lambda: cg_case("config5 Poisson CG5 matrix-free CG", 32 if q else 128, 5, iters=10 if q else 20),
+        lambda: dg_case("config3 DG advection DQ1 RHS (cell + ext + int facet kernels)", 256 if q else 2048),
         lambda: matrix_case("Poisson CG1 matrix", 32 if q else 128, 1),
         lambda: matrix_case("Poisson CG2 matrix", 16 if q else 48, 2),
         lambda: matrix_case("Poisson CG3 matrix", 8 if q else 32, 3),

@@ -42,6 +42,7 @@ class KernelDesc(C.Structure):
         ("B", C.c_double * (MAX_1D * MAX_1D)), ("D", C.c_double * (MAX_1D * MAX_1D)),
         ("wq", C.c_double * MAX_1D), ("xq", C.c_double * MAX_1D),
         ("offset0", C.POINTER(C.c_int32)), ("offset1", C.POINTER(C.c_int32)),
+        ("diagonal", C.c_int32),
     ]
 
 

@@ -190,6 +190,18 @@ class ImplicitMatrixContext:
         self._x = V.dat()
         self._assembler = OneFormAssembler(form, self._x, ())
 
+    def getDiagonal(self, D: op2.Dat):
+        """``assemble(a, diagonal=True)`` then 1 on the constrained rows
+        (matrix_free/operators.py:199-205; firedrake/assemble.py:1226-1241)."""
+        V = self.form.V
+        k = op2.Kernel("helmholtz", degree=V.degree, alpha=self.form.alpha, beta=self.form.beta,
+                       diagonal=True)
+        D.zero()
+        op2.par_loop(k, V.cell_set, D(op2.INC, V.cell_node_map), V.coordinates(op2.READ, V.coord_map))
+        for bc in self.bcs:
+            bc.set(D, 1.0)
+        return D
+
     def mult(self, X: op2.Dat, Y: op2.Dat):
         from . import _lib
         L = _lib.lib()

@@ -576,7 +576,16 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
             apply_second<N, true>(P.B, tmp, u);          // q_y -> a_y     R[ax][ay] @ a_z
 
             // ---- scatter-add, layout Z
-            if (MATRIX) {
+            if (MATRIX && P.vals == nullptr) {
+                // diagonal of the bilinear form: only the entry i == j of column j
+                if (valid) {
+#pragma unroll
+                    for (int x = 0; x < N; x++)
+#pragma unroll
+                        for (int yy = 0; yy < N; yy++)
+                            if ((x * N + yy) * N + t == comp) atomicAdd(P.y + si[comp], u[x][yy]);
+                }
+            } else if (MATRIX) {
                 // MatSetValuesLocal(ADD_VALUES): column = trial dof `comp`, rows = this
                 // lane's test dofs; negative (BC-masked) indices are dropped
                 int gcol = valid ? si[comp] : -1;
@@ -752,7 +761,8 @@ int launch_n(fdb_kernel_s *k, fdb_int start, fdb_int end, int nlay, const fdb_in
 
 template <int N>
 int launch_matrix_n(fdb_kernel_s *k, fdb_int start, fdb_int end, int nlay, const fdb_int *subset,
-                    fdb_mat_t mat, const double *coords, const fdb_int *map0, const fdb_int *map1)
+                    fdb_mat_t mat, const double *coords, const fdb_int *map0, const fdb_int *map1,
+                    double *diag_out)
 {
     fdb::Context &c = fdb::ctx();
     HelmParams<N> P;
@@ -775,8 +785,12 @@ int launch_matrix_n(fdb_kernel_s *k, fdb_int start, fdb_int end, int nlay, const
         P.wq[i] = k->desc.wq[i];
         P.xq[i] = k->desc.xq[i];
     }
-    fdb_mat_device_view(mat, &P.rowptr, &P.colidx, &P.vals, &P.row_lg, &P.col_lg);
-    fdb_mat_rank_table(mat, &P.rank_tab, &P.nvar);
+    if (mat) {
+        fdb_mat_device_view(mat, &P.rowptr, &P.colidx, &P.vals, &P.row_lg, &P.col_lg);
+        fdb_mat_rank_table(mat, &P.rank_tab, &P.nvar);
+    } else {
+        P.y = diag_out;          // diagonal mode
+    }
     P.nlay_total = nlay;
     if (subset || k->desc.cell != FDB_CELL_HEX_EXTRUDED) P.rank_tab = nullptr;   // table is per column of the full set
     P.counter = c.work_counter;
@@ -796,12 +810,12 @@ int launch_matrix_n(fdb_kernel_s *k, fdb_int start, fdb_int end, int nlay, const
 
 int fdb_launch_helmholtz_matrix(fdb_kernel_s *k, fdb_int start, fdb_int end, int nlay,
                                 const fdb_int *subset, fdb_mat_t mat, const double *coords,
-                                const fdb_int *map0, const fdb_int *map1)
+                                const fdb_int *map0, const fdb_int *map1, double *diag_out)
 {
     switch (k->n1d) {
-    case 2: return launch_matrix_n<2>(k, start, end, nlay, subset, mat, coords, map0, map1);
-    case 3: return launch_matrix_n<3>(k, start, end, nlay, subset, mat, coords, map0, map1);
-    case 4: return launch_matrix_n<4>(k, start, end, nlay, subset, mat, coords, map0, map1);
+    case 2: return launch_matrix_n<2>(k, start, end, nlay, subset, mat, coords, map0, map1, diag_out);
+    case 3: return launch_matrix_n<3>(k, start, end, nlay, subset, mat, coords, map0, map1, diag_out);
+    case 4: return launch_matrix_n<4>(k, start, end, nlay, subset, mat, coords, map0, map1, diag_out);
     }
     fdb::set_error("helmholtz matrix: degree %d not instantiated (1..3)", k->n1d - 1);
     return 1;

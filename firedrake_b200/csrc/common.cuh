@@ -77,7 +77,7 @@ int fdb_mat_device_view(fdb_mat_t m, const long long **rowptr, const fdb_int **c
 int fdb_mat_rank_table(fdb_mat_t m, const unsigned short **rank, int *nvar);
 int fdb_launch_helmholtz_matrix(fdb_kernel_s *k, fdb_int start, fdb_int end, int nlay,
                                 const fdb_int *subset, fdb_mat_t mat, const double *coords,
-                                const fdb_int *map0, const fdb_int *map1);
+                                const fdb_int *map0, const fdb_int *map1, double *diag_out);
 
 int fdb_launch_tri_p1(fdb_kernel_s *k, fdb_int start, fdb_int end, const fdb_int *subset, double *y,
                       const double *coords, const double *x, const fdb_int *map, fdb_mat_t mat);

@@ -433,7 +433,18 @@ int fdb_kernel_call(fdb_kernel_t k, const fdb_call_args *a)
             dm[1] = a->maps[1];
         }
         return fdb_launch_helmholtz_matrix(k, a->start, a->end, nlay, dsub, (fdb_mat_t)a->args[0],
-                                           dcoords, dm[0], dm[1]);
+                                           dcoords, dm[0], dm[1], nullptr);
+    }
+    if (k->desc.diagonal) {
+        // args = [d (INC), coords]; device-resident only
+        if (a->nargs != 2 || a->nmaps != 2 || a->location != FDB_LOC_DEVICE || k->desc.cdim != 1 ||
+            k->n1d > 4) {
+            set_error("fdb_kernel_call: diagonal assembly expects 2 device args, 2 maps, scalar CG1..3");
+            return 1;
+        }
+        return fdb_launch_helmholtz_matrix(k, a->start, a->end, nlay, a->subset, nullptr,
+                                           (const double *)a->args[1], a->maps[0], a->maps[1],
+                                           (double *)a->args[0]);
     }
     // 1-form: args = [y (INC), coords (READ), x (READ)], maps = [V map, coord map]
     if (a->nargs != 3 || a->nmaps != 2) {

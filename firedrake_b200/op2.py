@@ -543,6 +543,7 @@ class Kernel:
     cdim: int = 1
     integral: str = "cell"          # "cell" | "exterior_facet" | "interior_facet"
     cell: str = "hex"               # "hex" (extruded or native) | "triangle" (affine P1)
+    diagonal: bool = False          # rank 1: diagonal of the bilinear form (args: d, coordinates)
     nq: int = 0                     # 1-D quadrature points (0: the form's default)
     name: str = "form0_cell_integral"
     accesses: tuple = (INC, READ, READ)
@@ -555,6 +556,8 @@ class Kernel:
             acc = (INC, READ, READ, READ, READ) + ((READ,) if self.integral != "cell" else ())
             object.__setattr__(self, "accesses", acc)
             object.__setattr__(self, "name", f"form0_{self.integral}_integral")
+        if self.diagonal:
+            object.__setattr__(self, "accesses", (INC, READ))
         if self.rank == 2 and self.accesses == (INC, READ, READ):
             object.__setattr__(self, "accesses", (INC, READ))
             if self.name == "form0_cell_integral":
@@ -648,6 +651,7 @@ class GlobalKernel:
         d.cdim = lk.cdim
         d.scatter = {"atomic": _lib.SCATTER_ATOMIC, "coloured": _lib.SCATTER_COLOURED}[self.scatter]
         d.alpha, d.beta = lk.alpha, lk.beta
+        d.diagonal = int(lk.diagonal)
         for q in range(el.nq):
             d.wq[q] = el.wq[q]
             d.xq[q] = el.xq[q]

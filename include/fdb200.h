@@ -130,6 +130,11 @@ typedef struct fdb_kernel_desc {
      * non-extruded cells.  Copied at creation. */
     const fdb_int *offset0;
     const fdb_int *offset1;
+    /* rank 1 only: assemble the DIAGONAL of the bilinear form, A[i] += a(phi_i, phi_i)
+     * (assemble(a, diagonal=True), firedrake/assemble.py:1226-1241,
+     * tsfc/kernel_interface/common.py:560-570; ImplicitMatrixContext.getDiagonal).
+     * args = [d (INC), coords], maps as for a 1-form. */
+    int32_t diagonal;
 } fdb_kernel_desc;
 
 typedef struct fdb_kernel_s *fdb_kernel_t;

@@ -66,3 +66,18 @@ def test_cg_matches_scipy(engine):
     xs = spla.spsolve(sp.csr_matrix((va, co, ro), shape=(V.node_count,) * 2).tocsc(), bv)
     assert np.abs(x.data_ro - xs).max() < 1e-8 * np.abs(xs).max()
     assert hist[-1] < 1e-10 * hist[0]
+
+
+def test_get_diagonal(engine):
+    """reference tests/firedrake/regression/test_assemble.py:188-206: the
+    assembled diagonal equals the diagonal of the assembled matrix."""
+    mesh = ExtrudedHexMesh(4, 3, 5, warp=0.05)
+    V = FunctionSpace(mesh, 3)
+    bcs = [DirichletBC(V, 0.0, "bottom")]
+    a = helmholtz(V)
+    A = assemble(a, bcs=bcs)
+    Amf = assemble(a, bcs=bcs, mat_type="matfree")
+    d = Amf.getDiagonal(V.dat())
+    ro, co, va = A.csr()
+    diag = np.array([va[ro[r]:ro[r + 1]][co[ro[r]:ro[r + 1]] == r][0] for r in range(V.node_count)])
+    assert np.abs(d.data_ro - diag).max() < 1e-12 * np.abs(diag).max()
