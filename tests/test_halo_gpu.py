@@ -29,3 +29,17 @@ def test_distributed_device_action(world):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("HALO_OK") == world
+
+
+@pytest.mark.parametrize("world", [2])
+def test_distributed_matrix_free_cg(world):
+    """Config-5 style solve across GPUs: halos in every mult, NCCL all-reduce
+    for the dot products, Dirichlet rows; equals the serial direct solve."""
+    if _ngpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(29530 + world),
+           os.path.join(ROOT, "tests", "_cg_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("CG_OK") == world
