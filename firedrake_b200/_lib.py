@@ -72,6 +72,8 @@ SIGNATURES = {
     "fdb_memcpy_h2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "fdb_memcpy_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "fdb_memcpy_d2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "fdb_zero_background": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "fdb_background_barrier": (C.c_int, []),
     "fdb_host_alloc": (C.c_void_p, [C.c_size_t]),
     "fdb_host_free": (C.c_int, [C.c_void_p]),
     "fdb_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),

@@ -175,7 +175,12 @@ struct Tile {
 #ifndef FDB_WARPS
 #define FDB_WARPS 4
 #endif
-constexpr int WARPS_PER_CTA = FDB_WARPS;
+// warps per CTA: 4 everywhere except degree 5 (N = 6), whose per-warp staging is 38 KB:
+// one CTA of 5 warps fills the 227 KB of shared memory better than one of 4
+template <int N>
+struct WPC {
+    static constexpr int value = (N == 6) ? 5 : FDB_WARPS;
+};
 
 __device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
 {
@@ -216,7 +221,7 @@ struct WarpSmem {
     static constexpr int MAPRAW = CWS * US;                    // ints: bottom-cell map row
     static constexpr int VIDX = 2 * CWS * 8;                   // ints: bottom-cell vertex row
     static constexpr int BYTES = (((TILE + UBUF + COORD) * 8 + (IDX + MAPRAW + VIDX) * 4) + 15) / 16 * 16;
-    static constexpr int CTA_BYTES = WARPS_PER_CTA * BYTES + ND * 4 + 32;
+    static constexpr int CTA_BYTES = WPC<N>::value * BYTES + ND * 4 + 32;
 };
 
 // One pipeline unit = (item, component): the cells a warp works on next.
@@ -231,7 +236,7 @@ struct Unit {
 };
 
 template <int N, bool MASS, bool ATOMIC, int MINB, bool MATRIX = false>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB)
+__global__ void __launch_bounds__(WPC<N>::value * 32, MINB)
 helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
 {
     using WS = WarpSmem<N>;
@@ -249,7 +254,7 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
     int *s_idx = reinterpret_cast<int *>(s_coord + WS::COORD);   // [2][CWS][US]
     int *s_mapraw = s_idx + WS::IDX;                 // [CWS][US]
     int *s_vidx = s_mapraw + WS::MAPRAW;             // [2][CWS][8]
-    int *s_off0 = reinterpret_cast<int *>(smem_raw + (size_t)WARPS_PER_CTA * WS::BYTES);
+    int *s_off0 = reinterpret_cast<int *>(smem_raw + (size_t)WPC<N>::value * WS::BYTES);
     int *s_off1 = s_off0 + ND;
 
     for (int i = threadIdx.x; i < ND; i += blockDim.x) s_off0[i] = P.off0[i];
@@ -641,6 +646,7 @@ template <int N, bool MASS, bool ATOMIC, int MINB, bool MATRIX = false>
 int launch_one(int grid_cap_per_sm, cudaStream_t st, HelmParams<N> &P, int sm_count)
 {
     using WS = WarpSmem<N>;
+    constexpr int WARPS_PER_CTA = WPC<N>::value;
     constexpr int T = WARPS_PER_CTA * 32;
     auto kern = helmholtz_action_kernel<N, MASS, ATOMIC, MINB, MATRIX>;
     static bool configured = false;

@@ -1,6 +1,7 @@
 // Runtime plumbing of libfdb200: context, device memory, the host-pointer
 // mirror cache, timers.  No numerics here.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -43,6 +44,10 @@ static std::unordered_map<const void *, Mirror> g_mirrors;
 }  // namespace fdb
 
 using namespace fdb;
+
+static cudaStream_t g_side = nullptr;
+static cudaEvent_t g_side_ev = nullptr, g_main_ev = nullptr;
+static bool g_side_pending = false;
 
 bool fdb_mirror_is_current(const void *host, size_t nbytes, uint64_t version)
 {
@@ -147,6 +152,7 @@ void *fdb_malloc(size_t nbytes)
 int fdb_free(void *dptr)
 {
     if (require_init()) return 1;
+    if (g_side) FDB_CUDA(cudaStreamSynchronize(g_side));
     FDB_CUDA(cudaStreamSynchronize(ctx().stream));
     FDB_CUDA(cudaFree(dptr));
     return 0;
@@ -179,6 +185,53 @@ int fdb_memcpy_d2d(void *dst, const void *src, size_t nbytes)
 {
     if (require_init()) return 1;
     FDB_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToDevice, ctx().stream));
+    return 0;
+}
+
+// A deliberately narrow zeroing kernel: a full-speed cudaMemset saturates HBM and
+// stalls the (compute-bound, but latency-sensitive) global kernel it overlaps for
+// exactly its own duration; a few CTAs trickle the zeros out over the whole
+// kernel instead.
+__global__ void __launch_bounds__(256) k_zero_trickle(uint4 *p, size_t n16)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (; i < n16; i += stride) p[i] = z;
+}
+
+int fdb_zero_background(void *dptr, size_t nbytes)
+{
+    if (require_init()) return 1;
+    if (!g_side) {
+        FDB_CUDA(cudaStreamCreateWithFlags(&g_side, cudaStreamNonBlocking));
+        FDB_CUDA(cudaEventCreateWithFlags(&g_side_ev, cudaEventDisableTiming));
+        FDB_CUDA(cudaEventCreateWithFlags(&g_main_ev, cudaEventDisableTiming));
+    }
+    FDB_CUDA(cudaEventRecord(g_main_ev, ctx().stream));
+    FDB_CUDA(cudaStreamWaitEvent(g_side, g_main_ev, 0));
+    static const int nblk = getenv("FDB_ZERO_CTAS") ? atoi(getenv("FDB_ZERO_CTAS")) : 0;
+    const size_t n16 = nbytes / 16;
+    if (nblk > 0 && n16 > 0) {
+        k_zero_trickle<<<nblk, 256, 0, g_side>>>((uint4 *)dptr, n16);
+        FDB_LAUNCH_CHECK();
+        if (nbytes % 16)
+            FDB_CUDA(cudaMemsetAsync((char *)dptr + n16 * 16, 0, nbytes % 16, g_side));
+    } else {
+        FDB_CUDA(cudaMemsetAsync(dptr, 0, nbytes, g_side));
+    }
+    FDB_CUDA(cudaEventRecord(g_side_ev, g_side));
+    g_side_pending = true;
+    return 0;
+}
+
+int fdb_background_barrier(void)
+{
+    if (require_init()) return 1;
+    if (g_side_pending) {
+        FDB_CUDA(cudaStreamWaitEvent(ctx().stream, g_side_ev, 0));
+        g_side_pending = false;
+    }
     return 0;
 }
 

@@ -247,6 +247,9 @@ class Dat:
     every write access to ``data`` and by every parloop that writes the Dat.
     """
     _ids = itertools.count()
+    # zero() of a device-resident Dat rotates between two buffers, the idle one being
+    # zeroed on a side stream while the engine stream keeps computing
+    zero_rotation = False   # measured: overlapping the zeroing slows the compute kernel by as much (DESIGN.md)
 
     def __init__(self, dataset, data=None, dtype=ScalarType, name=None, pinned=False):
         self.dataset = _as_dataset(dataset)
@@ -264,6 +267,7 @@ class Dat:
         self.name = name or f"dat_{next(Dat._ids)}"
         self.dat_version = 0
         self._dev = None            # DeviceArray, device-resident mode
+        self._spare = None          # pre-zeroed twin used by zero() (see Dat.zero_rotation)
         self._host_valid = True
         self._dev_valid = False
         self._is_zero = data is None
@@ -361,6 +365,18 @@ class Dat:
         self._dev_valid = False
         self._is_zero = True
         self.increment_dat_version()
+        if self._dev is not None and Dat.zero_rotation:
+            # device-resident tensor: swap in a buffer that was zeroed in the
+            # background (overlapping the previous kernel) and send the old one
+            # to be zeroed for the next call
+            L = _lib.lib()
+            if self._spare is None:
+                self._spare = DeviceArray(self._data.nbytes)
+                _lib.check(L.fdb_zero_background(self._spare.ptr, self._data.nbytes))
+            _lib.check(L.fdb_background_barrier())
+            self._dev, self._spare = self._spare, self._dev
+            _lib.check(L.fdb_zero_background(self._spare.ptr, self._data.nbytes))
+            self._dev_valid = True
 
     def _vec_op(self, other, fn, *scalars):
         L = _lib.lib()

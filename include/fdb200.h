@@ -52,6 +52,14 @@ int fdb_memset(void *dptr, int value, size_t nbytes);
 int fdb_memcpy_h2d(void *dst_dev, const void *src_host, size_t nbytes);
 int fdb_memcpy_d2h(void *dst_host, const void *src_dev, size_t nbytes);
 int fdb_memcpy_d2d(void *dst_dev, const void *src_dev, size_t nbytes);
+/* Zero a buffer on a side stream, ordered after everything already enqueued on
+ * the engine stream (the buffer may still be in use there); the engine stream
+ * is not blocked.  fdb_background_barrier() makes the engine stream wait for
+ * all such zeroing issued so far.  Used to rotate pre-zeroed output buffers so
+ * that the assembler's "zero the tensor" (firedrake/assemble.py:1042-1047)
+ * overlaps the previous global kernel instead of preceding the next one. */
+int fdb_zero_background(void *dptr, size_t nbytes);
+int fdb_background_barrier(void);
 /* pinned host staging (the e2e path copies from/to these) */
 void *fdb_host_alloc(size_t nbytes);
 int fdb_host_free(void *hptr);

@@ -1,6 +1,5 @@
 #!/bin/bash
-mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-python benchmarks/run_configs.py > gpurun_out/configs_r01c.jsonl 2> gpurun_out/configs.err
-grep -E "DG|matrix|CG5" gpurun_out/configs_r01c.jsonl | cut -c1-330
-tail -2 gpurun_out/configs.err
+for z in 0 8 16 24 48; do
+echo "== FDB_ZERO_CTAS=$z"
+FDB_ZERO_CTAS=$z python bench.py --n 256 --steps 10 --warmup 3 --no-e2e --no-cpu 2>&1 | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['ms_per_step'], d['roofline']['kernel_ms'], d['value'], d['gpu_launches'])"
+done
