@@ -85,13 +85,13 @@ def cg_case(name, n, p, iters=20):
             "residual_reduction": hist[-1] / hist[0]}
 
 
-def dg_case(name, n, steps=10):
+def dg_case(name, n, steps=10, fused=False):
     from firedrake_b200.assemble import DGAdvection
     from firedrake_b200.utility_meshes import QuadMesh
     m = QuadMesh(n, n)
     X = m.coordinates
     u = np.stack([0.5 - X[:, 1], X[:, 0] - 0.5], axis=1)
-    prob = DGAdvection(m, dt=2 * np.pi / 600 * 40 / n, q_in=1.0)
+    prob = DGAdvection(m, dt=2 * np.pi / 600 * 40 / n, q_in=1.0, fused=fused)
     q = prob.function(1.0 + np.random.default_rng(0).random(m.num_cells * 4))
     uu = prob.velocity(u)
     out = prob.function()
@@ -120,6 +120,7 @@ def main():
         lambda: action_case("config5 Poisson CG5 action", 32 if q else 128, 5),
         lambda: cg_case("config5 Poisson CG5 matrix-free CG", 32 if q else 128, 5, iters=10 if q else 20),
         lambda: dg_case("config3 DG advection DQ1 RHS (cell + ext + int facet kernels)", 256 if q else 2048),
+        lambda: dg_case("config3 DG advection DQ1 RHS (fused owner-computes kernel)", 256 if q else 2048, fused=True),
         lambda: matrix_case("Poisson CG1 matrix", 32 if q else 128, 1),
         lambda: matrix_case("Poisson CG2 matrix", 16 if q else 48, 2),
         lambda: matrix_case("Poisson CG3 matrix", 8 if q else 32, 3),

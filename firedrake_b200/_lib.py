@@ -23,6 +23,7 @@ CELL_QUAD = 4
 INTEGRAL_CELL = 0
 INTEGRAL_EXTERIOR_FACET = 1
 INTEGRAL_INTERIOR_FACET = 2
+INTEGRAL_FUSED = 3
 SCATTER_ATOMIC = 0
 SCATTER_COLOURED = 1
 LOC_HOST = 0

@@ -263,21 +263,41 @@ def cg(A, b: op2.Dat, x: op2.Dat, rtol=1e-8, atol=0.0, maxit=1000, allreduce=Non
 
 class DGAdvection:
     """Right-hand side ``assemble(L1)`` of the DG advection demo (reference
-    demos/DG_advection/DG_advection.py.rst:182-217) on a :class:`QuadMesh`:
-    three parloops -- cells, exterior facets, interior facets -- exactly the
-    kernels ``OneFormAssembler`` would run (firedrake/assemble.py:1069-1096)."""
+    demos/DG_advection/DG_advection.py.rst:182-217) on a :class:`QuadMesh`.
 
-    def __init__(self, mesh, dt, q_in=1.0, nq=3):
-        self.mesh = mesh
+    ``fused=False``: three parloops -- cells, exterior facets, interior facets --
+    exactly the kernels ``OneFormAssembler`` would run
+    (firedrake/assemble.py:1069-1096), with the reference's facet-kernel ABI.
+    ``fused=True``: ONE owner-computes pass over the cells (each cell adds its
+    cell term and the fluxes through its four facets into its own dofs): no
+    atomics, deterministic, ~3x less traffic; the only off-cell data is the q of
+    neighbouring cells, i.e. a ghost-cell halo when the mesh is a slab of a
+    partitioned run (``halo`` = ``firedrake_b200.halo.Halo`` on the DQ dofs).
+    """
+
+    def __init__(self, mesh, dt, q_in=1.0, nq=3, fused=False, halo=None):
+        self.mesh, self.fused = mesh, fused
         C_ = mesh.num_cells
-        self.cell_set = op2.Set(C_)
-        self.dq_nodes = op2.Set(4 * C_)
+        owned = mesh.num_owned_cells
+        self.cell_set = op2.Set((owned, owned, C_))
+        self.dq_nodes = op2.Set((4 * owned, 4 * owned, 4 * C_))
+        self.dq_dset = op2.DataSet(self.dq_nodes, 1, halo=halo)
         self.vertices = op2.Set(mesh.node_count)
-        self.ext_set = op2.Set(len(mesh.ext_facet_cells))
-        self.int_set = op2.Set(len(mesh.int_facet_cells))
         dg, cg = mesh.dg1_map, mesh.coord_map
         self.cell_dq = op2.Map(self.cell_set, self.dq_nodes, 4, dg)
         self.cell_cg = op2.Map(self.cell_set, self.vertices, 4, cg)
+        self.coordinates = op2.Dat(op2.DataSet(self.vertices, 2), mesh.coordinates)
+        self.consts = op2.Global(2, [dt, q_in])
+        self.nq = nq
+        self._loops = None
+        if fused:
+            self.nbr = op2.Dat(op2.DataSet(self.cell_set, 4), mesh.nbr, dtype=np.int32)
+            self.nbr_facet = op2.Dat(op2.DataSet(self.cell_set, 4), mesh.nbr_facet, dtype=np.uint32)
+            return
+        if halo is not None:
+            raise NotImplementedError("the facet-loop form runs unpartitioned; use fused=True")
+        self.ext_set = op2.Set(len(mesh.ext_facet_cells))
+        self.int_set = op2.Set(len(mesh.int_facet_cells))
         # facet->node maps: the nodes of cell '+' then of cell '-'
         # (firedrake/cython/dmcommon.pyx:1636-1677)
         self.ext_dq = op2.Map(self.ext_set, self.dq_nodes, 4, dg[mesh.ext_facet_cells])
@@ -287,13 +307,9 @@ class DGAdvection:
         self.int_cg = op2.Map(self.int_set, self.vertices, 8, np.concatenate([cg[ic[:, 0]], cg[ic[:, 1]]], axis=1))
         self.ext_facet = op2.Dat(op2.DataSet(self.ext_set, 1), mesh.ext_facet_local, dtype=np.uint32)
         self.int_facet = op2.Dat(op2.DataSet(self.int_set, 2), mesh.int_facet_local, dtype=np.uint32)
-        self.coordinates = op2.Dat(op2.DataSet(self.vertices, 2), mesh.coordinates)
-        self.consts = op2.Global(2, [dt, q_in])
-        self.nq = nq
-        self._loops = None
 
     def function(self, data=None):
-        return op2.Dat(self.dq_nodes, data)
+        return op2.Dat(self.dq_dset, data)
 
     def velocity(self, data):
         return op2.Dat(op2.DataSet(self.vertices, 2), data)
@@ -307,18 +323,48 @@ class DGAdvection:
             mk = lambda integral: op2.Kernel("dg_advection", degree=1, integral=integral, nq=self.nq)
             X, G = self.coordinates, self.consts
             gk = lambda k, maps: op2.GlobalKernel(k, maps, extruded=False)
-            self._loops = [
-                op2.Parloop(gk(mk("cell"), [self.cell_dq, self.cell_cg]), self.cell_set,
-                            [tensor(op2.INC, self.cell_dq), X(op2.READ, self.cell_cg), q(op2.READ, self.cell_dq),
-                             u(op2.READ, self.cell_cg), G(op2.READ)]),
-                op2.Parloop(gk(mk("exterior_facet"), [self.ext_dq, self.ext_cg]), self.ext_set,
-                            [tensor(op2.INC, self.ext_dq), X(op2.READ, self.ext_cg), q(op2.READ, self.ext_dq),
-                             u(op2.READ, self.ext_cg), G(op2.READ), self.ext_facet(op2.READ)]),
-                op2.Parloop(gk(mk("interior_facet"), [self.int_dq, self.int_cg]), self.int_set,
-                            [tensor(op2.INC, self.int_dq), X(op2.READ, self.int_cg), q(op2.READ, self.int_dq),
-                             u(op2.READ, self.int_cg), G(op2.READ), self.int_facet(op2.READ)]),
-            ]
+            if self.fused:
+                self._loops = [
+                    op2.Parloop(gk(mk("fused"), [self.cell_dq, self.cell_cg]), self.cell_set,
+                                [tensor(op2.INC, self.cell_dq), X(op2.READ, self.cell_cg),
+                                 q(op2.READ, self.cell_dq), u(op2.READ, self.cell_cg), G(op2.READ),
+                                 self.nbr_facet(op2.READ), self.nbr(op2.READ)])]
+            else:
+                self._loops = [
+                    op2.Parloop(gk(mk("cell"), [self.cell_dq, self.cell_cg]), self.cell_set,
+                                [tensor(op2.INC, self.cell_dq), X(op2.READ, self.cell_cg), q(op2.READ, self.cell_dq),
+                                 u(op2.READ, self.cell_cg), G(op2.READ)]),
+                    op2.Parloop(gk(mk("exterior_facet"), [self.ext_dq, self.ext_cg]), self.ext_set,
+                                [tensor(op2.INC, self.ext_dq), X(op2.READ, self.ext_cg), q(op2.READ, self.ext_dq),
+                                 u(op2.READ, self.ext_cg), G(op2.READ), self.ext_facet(op2.READ)]),
+                    op2.Parloop(gk(mk("interior_facet"), [self.int_dq, self.int_cg]), self.int_set,
+                                [tensor(op2.INC, self.int_dq), X(op2.READ, self.int_cg), q(op2.READ, self.int_dq),
+                                 u(op2.READ, self.int_cg), G(op2.READ), self.int_facet(op2.READ)]),
+                ]
         tensor.zero()
+        if self.fused and q.dataset.halo is not None and not q.halo_valid:
+            # ghost-cell q must be current before ANY cell runs (every cell may border a ghost)
+            q.dataset.halo.global_to_local_begin(q)
+            q.dataset.halo.global_to_local_end(q)
+        tensor.frozen_halo = True          # owner-computes: nothing to send back
         for loop in self._loops:
             loop()
+        tensor.frozen_halo = False
         return tensor
+
+
+def dg_slab(nx, ny, rank, nranks):
+    """Slab of the nx x ny quad mesh for ``rank`` with ghost-cell columns, and
+    the (rank, send, recv) halo lists of its DQ1 dofs."""
+    from .partition import slab_bounds
+    from .utility_meshes import QuadMesh
+    x0, x1 = slab_bounds(nx, nranks, rank)
+    mesh = QuadMesh(x1 - x0, ny, ix0=x0, nx_global=nx, ghost_left=rank > 0,
+                    ghost_right=rank < nranks - 1)
+    dofs = lambda cells: (np.asarray(cells)[:, None] * 4 + np.arange(4)[None, :]).ravel().astype(np.int32)
+    neigh = []
+    if rank > 0:
+        neigh.append((rank - 1, dofs(mesh.first_owned_column), dofs(mesh.ghost_cells_left)))
+    if rank < nranks - 1:
+        neigh.append((rank + 1, dofs(mesh.last_owned_column), dofs(mesh.ghost_cells_right)))
+    return mesh, neigh

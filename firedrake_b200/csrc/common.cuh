@@ -84,7 +84,7 @@ int fdb_launch_tri_p1(fdb_kernel_s *k, fdb_int start, fdb_int end, const fdb_int
 int fdb_launch_dg_advection(fdb_kernel_s *k, fdb_int start, fdb_int end, const fdb_int *subset,
                             double *out, const double *coords, const double *q, const double *u,
                             const double *consts_host, const unsigned *facet, const fdb_int *dgmap,
-                            const fdb_int *cgmap);
+                            const fdb_int *cgmap, const fdb_int *nbr);
 
 // launchers implemented in the kernel translation units
 int fdb_launch_helmholtz_action(fdb_kernel_s *k, fdb_int start, fdb_int end, int nlay,

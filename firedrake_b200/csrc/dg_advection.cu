@@ -23,6 +23,8 @@ struct DgParams {
     const int *dgmap;      // (n, 4) or (n, 8)
     const int *cgmap;      // (n, 4) or (n, 8)
     const unsigned *facet; // (n, 1) or (n, 2)
+    const int *nbr;        // fused kernel: (ncells, 4) neighbour cell per local facet, -1 = boundary
+    const unsigned *nbr_facet;   // (ncells, 4) the neighbour's local facet number
     int start, end;
     const int *subset;
     int nq;
@@ -249,12 +251,115 @@ __global__ void __launch_bounds__(128) dg_interior_kernel(const __grid_constant_
     }
 }
 
+// Owner-computes fusion of the three integrals: one thread per cell adds the
+// cell term and, for each of its four facets, the flux into ITS OWN test
+// functions -- exterior inflow/outflow, or the upwind interior flux using the
+// neighbour's q (read only).  From the form, for either side of an interior
+// facet:  -phi_me (un_me q_me - un_nb q_nb),  un_me = max(u.n_me, 0),
+// un_nb = max(-u.n_me, 0)  (u continuous, n_nb = -n_me).  Every output dof is
+// written by exactly one thread: no atomics, deterministic, and q of
+// neighbouring cells is the only off-cell data (= the ghost-cell halo of a
+// partitioned run).  Same result as the cell + exterior + interior parloops.
+__global__ void __launch_bounds__(128) dg_fused_kernel(const __grid_constant__ DgParams P)
+{
+    for (int i = P.start + blockIdx.x * blockDim.x + threadIdx.x; i < P.end; i += gridDim.x * blockDim.x) {
+        const int n = P.subset ? P.subset[i] : i;
+        const int4 dg = *reinterpret_cast<const int4 *>(P.dgmap + 4 * (long long)n);
+        const int4 cg = *reinterpret_cast<const int4 *>(P.cgmap + 4 * (long long)n);
+        const int dgi[4] = {dg.x, dg.y, dg.z, dg.w}, cgi[4] = {cg.x, cg.y, cg.z, cg.w};
+        Q1Cell K;
+        load_cell(P, cgi, K);
+        double ql[4], A[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < 4; k++) ql[k] = P.q[dgi[k]];
+        // ---- cell integral
+        for (int qx = 0; qx < P.nq; qx++)
+            for (int qy = 0; qy < P.nq; qy++) {
+                const double x = P.xq[qx], y = P.xq[qy];
+                double J[2][2];
+                jac(K.c, x, y, J);
+                const double det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+                const double id = 1.0 / det;
+                const double Ki[2][2] = {{J[1][1] * id, -J[0][1] * id}, {-J[1][0] * id, J[0][0] * id}};
+                const double w = fabs(det) * P.wq[qx] * P.wq[qy];
+                double uv[2];
+                p1(K.u, x, y, uv);
+                const double bx[2] = {1.0 - x, x}, by[2] = {1.0 - y, y};
+                double divu = 0.0, qv = 0.0;
+#pragma unroll
+                for (int ax = 0; ax < 2; ax++)
+#pragma unroll
+                    for (int ay = 0; ay < 2; ay++) {
+                        const double g0 = (ax ? 1.0 : -1.0) * by[ay], g1 = bx[ax] * (ay ? 1.0 : -1.0);
+                        divu += K.u[(ax * 2 + ay) * 2] * (Ki[0][0] * g0 + Ki[1][0] * g1)
+                              + K.u[(ax * 2 + ay) * 2 + 1] * (Ki[0][1] * g0 + Ki[1][1] * g1);
+                        qv += ql[ax * 2 + ay] * dq(P, ax, x) * dq(P, ay, y);
+                    }
+#pragma unroll
+                for (int ax = 0; ax < 2; ax++)
+#pragma unroll
+                    for (int ay = 0; ay < 2; ay++) {
+                        const double ph = dq(P, ax, x) * dq(P, ay, y);
+                        const double g0 = ddq(P, ax) * dq(P, ay, y), g1 = dq(P, ax, x) * ddq(P, ay);
+                        const double gp0 = Ki[0][0] * g0 + Ki[1][0] * g1, gp1 = Ki[0][1] * g0 + Ki[1][1] * g1;
+                        A[ax * 2 + ay] += P.dt * w * qv * (gp0 * uv[0] + gp1 * uv[1] + ph * divu);
+                    }
+            }
+        // ---- the four facets
+        const int4 nb4 = *reinterpret_cast<const int4 *>(P.nbr + 4 * (long long)n);
+        const uint4 nf4 = *reinterpret_cast<const uint4 *>(P.nbr_facet + 4 * (long long)n);
+        const int nb[4] = {nb4.x, nb4.y, nb4.z, nb4.w};
+        const unsigned nf[4] = {nf4.x, nf4.y, nf4.z, nf4.w};
+#pragma unroll
+        for (int f = 0; f < 4; f++) {
+            double qn[4] = {0, 0, 0, 0};
+            if (nb[f] >= 0) {
+                const int4 dn = *reinterpret_cast<const int4 *>(P.dgmap + 4 * (long long)nb[f]);
+                qn[0] = P.q[dn.x]; qn[1] = P.q[dn.y]; qn[2] = P.q[dn.z]; qn[3] = P.q[dn.w];
+            }
+            for (int k = 0; k < P.nq; k++) {
+                double x, y, nref[2], tref[2], nn[2], ds, uv[2];
+                facet_point(f, P.xq[k], x, y, nref, tref);
+                facet_geometry(K.c, x, y, nref, tref, nn, ds);
+                p1(K.u, x, y, uv);
+                const double udn = uv[0] * nn[0] + uv[1] * nn[1];
+                double qv = 0.0;
+#pragma unroll
+                for (int ax = 0; ax < 2; ax++)
+#pragma unroll
+                    for (int ay = 0; ay < 2; ay++) qv += ql[ax * 2 + ay] * dq(P, ax, x) * dq(P, ay, y);
+                double flux;
+                if (nb[f] < 0) {
+                    flux = (udn < 0.0 ? udn * P.q_in : 0.0) + (udn > 0.0 ? udn * qv : 0.0);
+                } else {
+                    double xn, yn, nr2[2], tr2[2];
+                    facet_point((int)nf[f], P.xq[k], xn, yn, nr2, tr2);
+                    double qnv = 0.0;
+#pragma unroll
+                    for (int ax = 0; ax < 2; ax++)
+#pragma unroll
+                        for (int ay = 0; ay < 2; ay++) qnv += qn[ax * 2 + ay] * dq(P, ax, xn) * dq(P, ay, yn);
+                    const double un_me = 0.5 * (udn + fabs(udn)), un_nb = 0.5 * (-udn + fabs(udn));
+                    flux = un_me * qv - un_nb * qnv;
+                }
+#pragma unroll
+                for (int ax = 0; ax < 2; ax++)
+#pragma unroll
+                    for (int ay = 0; ay < 2; ay++)
+                        A[ax * 2 + ay] -= P.dt * ds * P.wq[k] * dq(P, ax, x) * dq(P, ay, y) * flux;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) P.out[dgi[k]] += A[k];
+    }
+}
+
 }  // namespace
 
 int fdb_launch_dg_advection(fdb_kernel_s *k, fdb_int start, fdb_int end, const fdb_int *subset,
                             double *out, const double *coords, const double *q, const double *u,
                             const double *consts_host, const unsigned *facet, const fdb_int *dgmap,
-                            const fdb_int *cgmap)
+                            const fdb_int *cgmap, const fdb_int *nbr)
 {
     fdb::Context &c = fdb::ctx();
     if (end <= start) return 0;
@@ -266,6 +371,8 @@ int fdb_launch_dg_advection(fdb_kernel_s *k, fdb_int start, fdb_int end, const f
     P.dgmap = dgmap;
     P.cgmap = cgmap;
     P.facet = facet;
+    P.nbr = nbr;
+    P.nbr_facet = facet;   // fused kernel: the "facet" argument is the (ncells, 4) neighbour-facet table
     P.start = start;
     P.end = end;
     P.subset = subset;
@@ -284,6 +391,7 @@ int fdb_launch_dg_advection(fdb_kernel_s *k, fdb_int start, fdb_int end, const f
     case FDB_INTEGRAL_CELL: dg_cell_kernel<<<(int)blocks, 128, 0, c.stream>>>(P); break;
     case FDB_INTEGRAL_EXTERIOR_FACET: dg_exterior_kernel<<<(int)blocks, 128, 0, c.stream>>>(P); break;
     case FDB_INTEGRAL_INTERIOR_FACET: dg_interior_kernel<<<(int)blocks, 128, 0, c.stream>>>(P); break;
+    case FDB_INTEGRAL_FUSED: dg_fused_kernel<<<(int)blocks, 128, 0, c.stream>>>(P); break;
     default: fdb::set_error("dg advection: bad integral type"); return 1;
     }
     FDB_LAUNCH_CHECK();

@@ -236,7 +236,7 @@ int fdb_kernel_create(const fdb_kernel_desc *d, fdb_kernel_t *out)
     }
     if (d->form == FDB_FORM_DG_ADVECTION) {
         if (d->cell != FDB_CELL_QUAD || d->rank != 1 || d->degree != 1 || d->cdim != 1 ||
-            d->nq < 1 || d->nq > FDB_MAX_1D || d->integral < 0 || d->integral > 2) {
+            d->nq < 1 || d->nq > FDB_MAX_1D || d->integral < 0 || d->integral > FDB_INTEGRAL_FUSED) {
             set_error("fdb_kernel_create: DG advection is DQ1 on quads, rank 1, nq <= %d", FDB_MAX_1D);
             return 1;
         }
@@ -347,8 +347,10 @@ int fdb_kernel_call(fdb_kernel_t k, const fdb_call_args *a)
         // args = [out (INC), coords, q, u, consts (HOST double[2] {dtc, q_in}), facet numbers]
         // maps = [DQ1 (facet-)node map, CG1 (facet-)node map]
         const bool facets = k->desc.integral != FDB_INTEGRAL_CELL;
-        if (a->nargs != (facets ? 6 : 5) || a->nmaps != 2) {
-            set_error("fdb_kernel_call: DG advection expects %d args and 2 maps", facets ? 6 : 5);
+        const bool fused = k->desc.integral == FDB_INTEGRAL_FUSED;
+        const int want = fused ? 7 : (facets ? 6 : 5);
+        if (a->nargs != want || a->nmaps != 2) {
+            set_error("fdb_kernel_call: DG advection expects %d args and 2 maps", want);
             return 1;
         }
         if (a->location != FDB_LOC_DEVICE) {
@@ -359,7 +361,7 @@ int fdb_kernel_call(fdb_kernel_t k, const fdb_call_args *a)
                                        (const double *)a->args[1], (const double *)a->args[2],
                                        (const double *)a->args[3], (const double *)a->args[4],
                                        facets ? (const unsigned *)a->args[5] : nullptr, a->maps[0],
-                                       a->maps[1]);
+                                       a->maps[1], fused ? (const fdb_int *)a->args[6] : nullptr);
     }
     if (k->desc.cell == FDB_CELL_TRIANGLE) {
         // rank 1: args = [y, coords, x]; rank 2: args = [mat, coords]; maps[0] = cell->vertex map

@@ -569,7 +569,8 @@ class Kernel:
     def __post_init__(self):
         if self.form == "dg_advection":
             # args: out, coordinates, q, u, constants (dtc, q_in) [, local facet numbers]
-            acc = (INC, READ, READ, READ, READ) + ((READ,) if self.integral != "cell" else ())
+            extra = {"cell": 0, "exterior_facet": 1, "interior_facet": 1, "fused": 2}[self.integral]
+            acc = (INC, READ, READ, READ, READ) + (READ,) * extra
             object.__setattr__(self, "accesses", acc)
             object.__setattr__(self, "name", f"form0_{self.integral}_integral")
         if self.diagonal:
@@ -587,7 +588,7 @@ class Kernel:
 
 _FORMS = {"helmholtz": _lib.FORM_HELMHOLTZ, "dg_advection": _lib.FORM_DG_ADVECTION}
 _INTEGRALS = {"cell": _lib.INTEGRAL_CELL, "exterior_facet": _lib.INTEGRAL_EXTERIOR_FACET,
-              "interior_facet": _lib.INTEGRAL_INTERIOR_FACET}
+              "interior_facet": _lib.INTEGRAL_INTERIOR_FACET, "fused": _lib.INTEGRAL_FUSED}
 
 
 class GlobalKernel:

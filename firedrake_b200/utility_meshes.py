@@ -363,24 +363,65 @@ class QuadMesh:
       Local facet numbering of the reference quad: 0: x==0, 1: x==1, 2: y==0,
       3: y==1 (edges of FInAT dimension (0,1) first; reference
       firedrake/cython/dmcommon.pyx:1496-1499).
+    * ``nbr`` / ``nbr_facet`` (ncell, 4): neighbour cell across each local facet
+      (-1 on the domain boundary) and the neighbour's local facet number -- the
+      cell-centred view used by the fused owner-computes kernel.
+
+    Slab of a larger mesh (``ix0``, ``nx_global``, ``ghost_left/right``): the
+    local mesh holds the owned columns ix0 .. ix0+nx-1 plus one ghost column of
+    cells on each interior side; owned cells are numbered first, ghost cells
+    last (their DQ dofs form the ghost tail of the Dat).  Facet lists are only
+    built for an unpartitioned mesh.
     """
 
-    def __init__(self, nx, ny, Lx=1.0, Ly=1.0):
+    def __init__(self, nx, ny, Lx=1.0, Ly=1.0, ix0=0, nx_global=None, ghost_left=False,
+                 ghost_right=False):
         self.nx, self.ny = nx, ny
-        xs = np.linspace(0.0, Lx, nx + 1)
+        nxg = nx if nx_global is None else nx_global
+        gl, gr = int(ghost_left), int(ghost_right)
+        nxl = nx + gl + gr                                   # local columns incl. ghosts
+        xs = (np.arange(nxl + 1) + ix0 - gl) * (Lx / nxg)
         ys = np.linspace(0.0, Ly, ny + 1)
         X, Y = np.meshgrid(xs, ys, indexing="ij")
         self.coordinates = np.stack([X.ravel(), Y.ravel()], axis=1).astype(ScalarType)
-        i, j = np.meshgrid(np.arange(nx), np.arange(ny), indexing="ij")
-        i, j = i.ravel(), j.ravel()
+        # local cell ids: owned (columns gl .. gl+nx-1) first, then left ghost, right ghost
+        col_order = list(range(gl, gl + nx)) + ([0] if gl else []) + ([nxl - 1] if gr else [])
+        cid_of = -np.ones((nxl, ny), dtype=np.int64)
+        k = 0
+        for c in col_order:
+            cid_of[c, :] = k + np.arange(ny)
+            k += ny
+        ncell = nxl * ny
+        ii = np.empty(ncell, dtype=np.int64)
+        jj = np.empty(ncell, dtype=np.int64)
+        for c in range(nxl):
+            ii[cid_of[c, :]] = c
+            jj[cid_of[c, :]] = np.arange(ny)
         v = lambda a, b: a * (ny + 1) + b
-        self.coord_map = np.stack([v(i, j), v(i, j + 1), v(i + 1, j), v(i + 1, j + 1)],
+        self.coord_map = np.stack([v(ii, jj), v(ii, jj + 1), v(ii + 1, jj), v(ii + 1, jj + 1)],
                                   axis=1).astype(IntType)
-        ncell = nx * ny
         self.num_cells = ncell
+        self.num_owned_cells = nx * ny
         self.node_count = self.coordinates.shape[0]
         self.dg1_map = (np.arange(ncell, dtype=np.int64)[:, None] * 4
                         + np.arange(4)[None, :]).astype(IntType)
+        # neighbour tables (global domain boundary: -1)
+        nbr = -np.ones((ncell, 4), dtype=np.int64)
+        gi = ii + ix0 - gl                                   # global column of each local cell
+        for f, (di, dj) in enumerate([(-1, 0), (1, 0), (0, -1), (0, 1)]):
+            ni, nj = ii + di, jj + dj
+            ok = (ni >= 0) & (ni < nxl) & (nj >= 0) & (nj < ny)
+            nbr[ok, f] = cid_of[ni[ok], nj[ok]]
+        self.nbr = nbr.astype(IntType)
+        self.nbr_facet = np.tile(np.array([1, 0, 3, 2], dtype=np.uint32), (ncell, 1))
+        self.cell_global_column = gi
+        self.ghost_cells_left = cid_of[0, :].copy() if gl else np.zeros(0, dtype=np.int64)
+        self.ghost_cells_right = cid_of[nxl - 1, :].copy() if gr else np.zeros(0, dtype=np.int64)
+        self.first_owned_column = cid_of[gl, :].copy()
+        self.last_owned_column = cid_of[gl + nx - 1, :].copy()
+        if gl or gr:
+            return
+        i, j = ii, jj
         cid = lambda a, b: a * ny + b
         # interior facets normal to x (between (i,j) and (i+1,j)): '+' local 1, '-' local 0
         a, b = np.meshgrid(np.arange(nx - 1), np.arange(ny), indexing="ij")

@@ -106,7 +106,11 @@ enum fdb_cell {
 enum fdb_integral {
     FDB_INTEGRAL_CELL = 0,
     FDB_INTEGRAL_EXTERIOR_FACET = 1,
-    FDB_INTEGRAL_INTERIOR_FACET = 2
+    FDB_INTEGRAL_INTERIOR_FACET = 2,
+    FDB_INTEGRAL_FUSED = 3      /* DG advection only: cell + all facet integrals of a cell in one
+                                   owner-computes pass (no atomics).  args = [out, coords, q, u,
+                                   consts, neighbour facet numbers uint32 (ncells,4),
+                                   neighbour cells int32 (ncells,4), -1 = boundary]          */
 };
 
 enum fdb_scatter {

@@ -43,3 +43,16 @@ def test_distributed_matrix_free_cg(world):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("CG_OK") == world
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_distributed_dg_advection(world):
+    """Config 3 across GPUs: ghost-cell halo of q + fused owner-computes kernel."""
+    if _ngpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(29560 + world),
+           os.path.join(ROOT, "tests", "_dg_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("DG_OK") == world
