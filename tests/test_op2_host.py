@@ -1,0 +1,120 @@
+"""Host-side behaviour of the PyOP2 mirror that needs no GPU: set partitions,
+map validation, Dat versioning / lazy zero, parloop argument checks -- the
+Python-level errors the reference raises before any launch
+(pyop2/parloop.py:175-189, 472-501)."""
+import numpy as np
+import pytest
+
+from firedrake_b200 import op2
+
+
+def test_set_partitions():
+    s = op2.Set((3, 5, 8))
+    assert s.core_part == (0, 3) and s.owned_part == (3, 5) and s.total_size == 8
+    e = op2.ExtrudedSet(s, layers=11)
+    assert e._extruded and e.layers == 11 and e.layers_array.tolist() == [[0, 11]]
+    assert e.sizes == s.sizes
+    with pytest.raises(ValueError):
+        op2.Set((5, 3, 8))
+    with pytest.raises(ValueError):
+        op2.ExtrudedSet(s, layers=1)
+    sub = op2.Subset(s, [7, 1, 4, 1])
+    assert sub.indices.tolist() == [1, 4, 7] and sub.sizes == (1, 2, 3)
+    with pytest.raises(ValueError):
+        op2.Subset(s, [9])
+
+
+def test_map_validation():
+    cells, nodes = op2.Set(2), op2.Set(4)
+    m = op2.Map(cells, nodes, 3, [0, 1, 3, 2, 3, 1])
+    assert m.values.shape == (2, 3)
+    with pytest.raises(op2.MapValueError):
+        op2.Map(cells, nodes, 3, [0, 1, 3, 2, 3, 4])          # out of range
+    with pytest.raises(op2.MapValueError):
+        op2.Map(cells, nodes, 3, [0, 1, 3])                    # wrong number of rows
+    with pytest.raises(op2.MapValueError):
+        op2.Map(cells, nodes, 3, [0, 1, 3, 2, 3, 1], offset=[1, 1])
+
+
+def test_dat_versioning_and_lazy_zero():
+    nodes = op2.Set(5)
+    d = op2.Dat(nodes, np.arange(5.0))
+    v0 = d.dat_version
+    assert d.data_ro.tolist() == [0, 1, 2, 3, 4] and d.dat_version == v0     # read-only: no bump
+    d.data[2] = 7.0
+    assert d.dat_version == v0 + 1 and not d.halo_valid
+    with pytest.raises(ValueError):
+        d.data_ro[0] = 1.0
+    d.zero()
+    assert d._is_zero and not d._host_valid                                   # nothing touched yet
+    assert d.data_ro.tolist() == [0, 0, 0, 0, 0]                              # materialises on read
+    vec = op2.Dat(op2.DataSet(nodes, 3))
+    assert vec.data_ro.shape == (5, 3) and vec.cdim == 3
+    d2 = op2.Dat(op2.Set((3, 3, 5)), np.arange(5.0))
+    assert d2.data_ro.shape == (3,) and d2.data_ro_with_halos.shape == (5,)   # ghosts at the tail
+
+
+def test_kernel_descriptors():
+    k = op2.Kernel("helmholtz", degree=3)
+    assert k.accesses == (op2.INC, op2.READ, op2.READ) and k.name == "form0_cell_integral"
+    k2 = op2.Kernel("helmholtz", degree=2, rank=2)
+    assert k2.accesses == (op2.INC, op2.READ) and k2.name == "form00_cell_integral"
+    kd = op2.Kernel("helmholtz", degree=2, diagonal=True)
+    assert kd.accesses == (op2.INC, op2.READ)
+    kf = op2.Kernel("dg_advection", integral="interior_facet")
+    assert len(kf.accesses) == 6 and kf.name == "form0_interior_facet_integral"
+    assert op2.GlobalKernel(k, []).name == "wrap_form0_cell_integral"        # global_kernel.py:344-346
+
+
+def test_parloop_argument_checks():
+    cells = op2.ExtrudedSet(op2.Set(2), 3)
+    nodes, verts = op2.Set(12), op2.Set(12)
+    m0 = op2.Map(cells, nodes, 8, np.arange(16) % 12, offset=np.ones(8, dtype=np.int32))
+    m1 = op2.Map(cells, verts, 8, np.arange(16) % 12, offset=np.ones(8, dtype=np.int32))
+    x, y = op2.Dat(nodes), op2.Dat(nodes)
+    X = op2.Dat(op2.DataSet(verts, 3))
+    k = op2.Kernel("helmholtz", degree=1)
+    gk = op2.GlobalKernel(k, [m0, m1], extruded=True)
+    op2.Parloop(gk, cells, [y(op2.INC, m0), X(op2.READ, m1), x(op2.READ, m0)])          # fine
+    with pytest.raises(ValueError):                                                     # wrong access
+        op2.Parloop(gk, cells, [y(op2.READ, m0), X(op2.READ, m1), x(op2.READ, m0)])
+    with pytest.raises(ValueError):                                                     # arity
+        op2.Parloop(gk, cells, [y(op2.INC, m0), X(op2.READ, m1)])
+    with pytest.raises(op2.MapValueError):                                              # map/dat mismatch
+        op2.Parloop(gk, cells, [y(op2.INC, m1), X(op2.READ, m1), x(op2.READ, m0)])
+    other = op2.ExtrudedSet(op2.Set(2), 3)
+    with pytest.raises(op2.MapValueError):                                              # map on another set
+        op2.Parloop(gk, other, [y(op2.INC, m0), X(op2.READ, m1), x(op2.READ, m0)])
+    with pytest.raises(NotImplementedError):
+        op2.GlobalKernel(k, [m0, m1], extruded=True, constant_layers=False)
+
+
+def test_sparsity_restrictions():
+    cells, nodes = op2.Set(2), op2.Set(4)
+    m = op2.Map(cells, nodes, 3, [0, 1, 3, 2, 3, 1])
+    s = op2.Sparsity((nodes, nodes), [(m, m, None)])
+    assert s.shape == (4, 4)
+    with pytest.raises(NotImplementedError):
+        op2.Sparsity((op2.DataSet(nodes, 2), op2.DataSet(nodes, 2)), [(m, m, None)])
+    m2 = op2.Map(cells, nodes, 3, [0, 1, 3, 2, 3, 1])
+    with pytest.raises(NotImplementedError):
+        op2.Sparsity((nodes, nodes), [(m, m2, None)])
+
+
+def test_quadmesh_slabs():
+    from firedrake_b200.assemble import dg_slab
+    from firedrake_b200.utility_meshes import QuadMesh
+    g = QuadMesh(9, 4)
+    assert g.nbr.shape == (36, 4) and (g.nbr[0] == [-1, 4, -1, 1]).all()
+    owned = 0
+    for r in range(3):
+        m, neigh = dg_slab(9, 4, r, 3)
+        owned += m.num_owned_cells
+        for _, send, recv in neigh:
+            assert len(send) == len(recv) == 16
+            assert send.max() < 4 * m.num_owned_cells <= recv.min()      # send owned, receive into the tail
+        # owned cells see a neighbour everywhere except on the global boundary
+        gc = m.cell_global_column[:m.num_owned_cells]
+        assert ((m.nbr[:m.num_owned_cells, 0] < 0) == (gc == 0)).all()
+        assert ((m.nbr[:m.num_owned_cells, 1] < 0) == (gc == 8)).all()
+    assert owned == 36
