@@ -3,7 +3,7 @@
 N GPUs (slab partition, NCCL halos in every operator application, NCCL
 all-reduce for the dot products).  Launch with torchrun; rank 0 prints JSON.
 
-    python -m torch.distributed.run --nproc-per-node 4 benchmarks/cg_multi.py --n 128 --degree 5
+    python -m torch.distributed.run --nproc-per-node 4 benchmarks/cg_multi.py --size 128 --degree 5
 """
 import argparse
 import json
@@ -22,7 +22,7 @@ from firedrake_b200.halo import comm_init_from_env                              
 from firedrake_b200.partition import SlabPartition                                   # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--n", type=int, default=128)
+ap.add_argument("--size", dest="n", type=int, default=128)
 ap.add_argument("--degree", type=int, default=5)
 ap.add_argument("--iters", type=int, default=20)
 args = ap.parse_args()
