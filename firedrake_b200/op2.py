@@ -351,10 +351,10 @@ class Dat:
     def zero(self, subset=None):
         if subset is not None:
             if self._dev_valid and not self._host_valid:
-                nodes = DeviceArray.from_host(subset.indices)
-                _lib.check(_lib.lib().fdb_dat_zero_nodes(self._dev.ptr, self.cdim, nodes.ptr,
+                if not hasattr(subset, "_dev_idx"):
+                    subset._dev_idx = DeviceArray.from_host(subset.indices)    # uploaded once
+                _lib.check(_lib.lib().fdb_dat_zero_nodes(self._dev.ptr, self.cdim, subset._dev_idx.ptr,
                                                          len(subset.indices)), "zero_nodes")
-                _lib.check(_lib.lib().fdb_synchronize())
                 self.increment_dat_version()
             else:
                 self.data_with_halos[subset.indices] = 0
