@@ -672,6 +672,8 @@ int launch_one(int grid_cap_per_sm, cudaStream_t st, HelmParams<N> &P, int sm_co
     if (chunk > 64) chunk = 64;
     long long per_warp = nitems / (grid * WARPS_PER_CTA) + 1;
     if (chunk > per_warp / 4 + 1) chunk = (int)(per_warp / 4 + 1);
+    static const int chunk_env = getenv("FDB_CHUNK") ? atoi(getenv("FDB_CHUNK")) : 0;
+    if (chunk_env > 0) chunk = chunk_env;
     P.chunk = chunk;
     P.nlay_rcp = (unsigned)(0x100000000ull / (unsigned long long)P.nlay_items);
     if (P.nlay_items == 1) P.nlay_rcp = 0xffffffffu;
