@@ -177,9 +177,11 @@ struct Tile {
 #endif
 // warps per CTA: 4 everywhere except degree 5 (N = 6), whose per-warp staging is 38 KB:
 // one CTA of 5 warps fills the 227 KB of shared memory better than one of 4
-template <int N>
+template <int N, bool SLIM = false>
 struct WPC {
-    static constexpr int value = (N == 6) ? 5 : FDB_WARPS;
+    // degree 5 (N = 6): 38 KB of staging per warp -> 5 warps; 27.5 KB when SLIM -> 8 warps
+    // (255 registers x 256 threads = the whole register file)
+    static constexpr int value = (N == 6) ? (SLIM ? 8 : 5) : FDB_WARPS;
 };
 
 __device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
@@ -207,7 +209,12 @@ __device__ __forceinline__ void cp_async4(void *smem, const void *gmem)
 
 // per-warp shared-memory footprint.  Cell strides are padded so that the
 // 16 (64-bit) / 32 (32-bit) lanes of an access phase hit distinct banks.
-template <int N>
+// SLIM (used for p >= 4, where the staging buffers limit occupancy): no per-cell
+// index buffer -- gather and scatter indices are recomputed from the staged map
+// row -- and one staged row per distinct COLUMN of the warp (at most two when a
+// column has at least 32/N layers) instead of one per cell, triple-buffered over
+// the three items in flight (compute / value prefetch / row prefetch).
+template <int N, bool SLIM = false>
 struct WarpSmem {
     static constexpr int CW = 32 / N;
     static constexpr int CWS = (32 % N == 0) ? CW : CW + 1;   // idle lanes get a scratch slot
@@ -217,29 +224,31 @@ struct WarpSmem {
     static constexpr int TILE = CWS * Tile<N>::STRIDE;         // doubles
     static constexpr int UBUF = CWS * US;                      // doubles: gathered values (single buffer)
     static constexpr int COORD = CWS * CS;                     // doubles: vertex coordinates (single buffer)
-    static constexpr int IDX = 2 * CWS * US;                   // ints: global dof index per local dof
-    static constexpr int MAPRAW = CWS * US;                    // ints: bottom-cell map row
-    static constexpr int VIDX = 2 * CWS * 8;                   // ints: bottom-cell vertex row
+    static constexpr int IDX = SLIM ? 0 : 2 * CWS * US;        // ints: global dof index per local dof
+    static constexpr int MAPRAW = SLIM ? 3 * 2 * US : CWS * US;   // ints: bottom-cell map row(s)
+    static constexpr int VIDX = SLIM ? 3 * 2 * 8 : 2 * CWS * 8;   // ints: bottom-cell vertex row(s)
     static constexpr int BYTES = (((TILE + UBUF + COORD) * 8 + (IDX + MAPRAW + VIDX) * 4) + 15) / 16 * 16;
-    static constexpr int CTA_BYTES = WPC<N>::value * BYTES + ND * 4 + 32;
+    static constexpr int CTA_BYTES = WPC<N, SLIM>::value * BYTES + ND * 4 + 32;
 };
 
 // One pipeline unit = (item, component): the cells a warp works on next.
 struct Unit {
     int item;     // -1: none
     int comp;
-    int ib;       // item-buffer parity (toggles when the item changes)
+    int ib;       // item-buffer index (advances when the item changes: mod 2, mod 3 if SLIM)
     int cur, end; // chunk bookkeeping (warp uniform)
     bool valid;   // per lane: this lane's cell exists
     int col, layer;
-    int src;      // cell slot holding this column's staged map rows
+    int src;      // slot holding this column's staged map rows (leader cell, or 0/1 if SLIM)
+    bool lead;    // this lane's cell copies the rows of its column
 };
 
-template <int N, bool MASS, bool ATOMIC, int MINB, bool MATRIX = false>
-__global__ void __launch_bounds__(WPC<N>::value * 32, MINB)
+template <int N, bool MASS, bool ATOMIC, int MINB, bool MATRIX = false, bool SLIM = false>
+__global__ void __launch_bounds__(WPC<N, SLIM>::value * 32, MINB)
 helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
 {
-    using WS = WarpSmem<N>;
+    static_assert(!(SLIM && MATRIX), "matrix mode keeps the per-cell index buffer");
+    using WS = WarpSmem<N, SLIM>;
     constexpr int CW = WS::CW;
     constexpr int CWS = WS::CWS;
     constexpr int ND = N * N * N;
@@ -254,7 +263,7 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
     int *s_idx = reinterpret_cast<int *>(s_coord + WS::COORD);   // [2][CWS][US]
     int *s_mapraw = s_idx + WS::IDX;                 // [CWS][US]
     int *s_vidx = s_mapraw + WS::MAPRAW;             // [2][CWS][8]
-    int *s_off0 = reinterpret_cast<int *>(smem_raw + (size_t)WPC<N>::value * WS::BYTES);
+    int *s_off0 = reinterpret_cast<int *>(smem_raw + (size_t)WPC<N, SLIM>::value * WS::BYTES);
     int *s_off1 = s_off0 + ND;
 
     for (int i = threadIdx.x; i < ND; i += blockDim.x) s_off0[i] = P.off0[i];
@@ -280,7 +289,7 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
             return u;
         }
         u.comp = 0;
-        u.ib ^= 1;
+        u.ib = SLIM ? (u.ib == 2 ? 0 : u.ib + 1) : (u.ib ^ 1);
         if (u.item >= 0 && u.cur + 1 < u.end) {
             u.cur++;
             u.item = u.cur;
@@ -314,8 +323,23 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
         // cells of the warp that sit in the same column share one staged copy of
         // the map / vertex rows: the lowest such cell (leader) copies, the
         // others read its slot
-        const unsigned peers = __match_any_sync(0xffffffffu, u.valid ? u.col : -1 - cw);
-        u.src = (__ffs(peers) - 1) / N;
+        if (SLIM) {
+            // at most two distinct columns per warp (launcher guarantees nlay_items >= CW)
+            const int col0 = __shfl_sync(0xffffffffu, u.col, 0);
+            u.src = (u.col != col0) ? 1 : 0;
+            const unsigned peers = __match_any_sync(0xffffffffu, u.valid ? u.src : -1 - cw);
+            u.lead = (__ffs(peers) - 1) / N == cw;
+        } else {
+            const unsigned peers = __match_any_sync(0xffffffffu, u.valid ? u.col : -1 - cw);
+            u.src = (__ffs(peers) - 1) / N;
+            u.lead = u.src == cw;
+        }
+    };
+    auto row_of = [&](const Unit &u) -> int * {
+        return SLIM ? s_mapraw + (u.ib * 2 + u.src) * US : s_mapraw + u.src * US;
+    };
+    auto vrow_of = [&](const Unit &u) -> int * {
+        return SLIM ? s_vidx + (u.ib * 2 + u.src) * 8 : s_vidx + (u.ib * CWS + u.src) * 8;
     };
 
     // Three-stage gather pipeline, all through cp.async (no registers held, no
@@ -330,9 +354,9 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
     // s_coord are shared by the N lanes of a cell and are read after the
     // wait + __syncwarp at the top of the loop.
     auto stageA = [&](const Unit &u) {
-        if (u.valid && u.comp == 0 && u.src == cw) {
+        if (u.valid && u.comp == 0 && u.lead) {
             const int *mrow = P.map0 + (long long)u.col * ND;
-            int *sm = s_mapraw + cw * US;
+            int *sm = row_of(u);
             if ((ND % 4) == 0 && (US % 4) == 0) {
                 // rows are 16-byte aligned: 128-bit copies
                 for (int j = t; j < ND / 4; j += N) cp_async16(sm + 4 * j, mrow + 4 * j);
@@ -340,13 +364,13 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
 #pragma unroll
                 for (int j = 0; j < N * N; j++) cp_async4(sm + j * N + t, mrow + j * N + t);
             }
-            int *sv = s_vidx + (u.ib * CWS + cw) * 8;
+            int *sv = vrow_of(u);
             for (int v = t; v < 8; v += N) cp_async4(sv + v, P.map1 + (long long)u.col * 8 + v);
         }
     };
     auto stageB_coords = [&](const Unit &u) {
         if (u.valid && u.comp == 0) {
-            const int *sv = s_vidx + (u.ib * CWS + u.src) * 8;
+            const int *sv = vrow_of(u);
             double *scd = s_coord + cw * CS;
             for (int i = t; i < 24; i += N) {
                 int v = i / 3, a = i - v * 3;
@@ -359,16 +383,18 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
         if (u.valid) {
             double *su = s_u + cw * US;
             int *si = s_idx + (u.ib * CWS + cw) * US;
-            const int *sm = s_mapraw + u.src * US;
+            const int *sm = row_of(u);
             int g[N];
-            if (u.comp == 0) {
+            if (SLIM || u.comp == 0) {
 #pragma unroll
                 for (int j = 0; j < N; j++) {
                     const int loc = (part * N + j) * N + t;
                     g[j] = sm[loc] + s_off0[loc] * u.layer;
                 }
+                if (!SLIM) {
 #pragma unroll
-                for (int j = 0; j < N; j++) si[(part * N + j) * N + t] = g[j];
+                    for (int j = 0; j < N; j++) si[(part * N + j) * N + t] = g[j];
+                }
             } else {
 #pragma unroll
                 for (int j = 0; j < N; j++) g[j] = si[(part * N + j) * N + t];
@@ -381,7 +407,7 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
         }
     };
 
-    Unit cur{-1, 0, 0, 0, 0, false, 0, 0, 0};
+    Unit cur{-1, 0, 0, 0, 0, false, 0, 0, 0, false};
     cur = advance(cur);
     decode(cur);
     Unit nxt = advance(cur);
@@ -624,11 +650,13 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
                         }
                 }
             } else if (valid) {
+                const int *smc = row_of(cur);
 #pragma unroll
                 for (int x = 0; x < N; x++)
 #pragma unroll
                     for (int yy = 0; yy < N; yy++) {
-                        const int g = si[(x * N + yy) * N + t];
+                        const int loc = (x * N + yy) * N + t;
+                        const int g = SLIM ? smc[loc] + s_off0[loc] * cur.layer : si[loc];
                         double *dst = P.y + (long long)g * P.cdim + comp;
                         if (ATOMIC) atomicAdd(dst, u[x][yy]);
                         else *dst += u[x][yy];
@@ -642,13 +670,13 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
     cp_async_wait<0>();
 }
 
-template <int N, bool MASS, bool ATOMIC, int MINB, bool MATRIX = false>
+template <int N, bool MASS, bool ATOMIC, int MINB, bool MATRIX = false, bool SLIM = false>
 int launch_one(int grid_cap_per_sm, cudaStream_t st, HelmParams<N> &P, int sm_count)
 {
-    using WS = WarpSmem<N>;
-    constexpr int WARPS_PER_CTA = WPC<N>::value;
+    using WS = WarpSmem<N, SLIM>;
+    constexpr int WARPS_PER_CTA = WPC<N, SLIM>::value;
     constexpr int T = WARPS_PER_CTA * 32;
-    auto kern = helmholtz_action_kernel<N, MASS, ATOMIC, MINB, MATRIX>;
+    auto kern = helmholtz_action_kernel<N, MASS, ATOMIC, MINB, MATRIX, SLIM>;
     static bool configured = false;
     static int occ = 1;
     if (!configured) {
@@ -699,6 +727,15 @@ int launch_variant(bool mass, int minb, int cap, cudaStream_t st, HelmParams<N> 
         return launch_one<N, false, ATOMIC, 1>(cap, st, P, sm_count);
     }
     constexpr int DEF = (N >= 5) ? 1 : 2;
+    if (N == 6) {
+        // degree 5: the slim staging lifts occupancy from 5 to 8 warps per SM (12.9 -> 9.0 ms at
+        // 128^3); for degree 4 occupancy is register-bound either way and it measured 6 % slower
+        static const bool slim_on = !(getenv("FDB_NO_SLIM") && atoi(getenv("FDB_NO_SLIM")));
+        if (slim_on && P.nlay_items >= 32 / N) {
+            if (mass) return launch_one<N, true, ATOMIC, DEF, false, (N == 6)>(cap, st, P, sm_count);
+            return launch_one<N, false, ATOMIC, DEF, false, (N == 6)>(cap, st, P, sm_count);
+        }
+    }
     if (mass) return launch_one<N, true, ATOMIC, DEF>(cap, st, P, sm_count);
     return launch_one<N, false, ATOMIC, DEF>(cap, st, P, sm_count);
 }
