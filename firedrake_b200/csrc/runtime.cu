@@ -106,6 +106,14 @@ int fdb_finalize(void)
     for (auto &kv : g_mirrors) cudaFree(kv.second.dev);
     g_mirrors.clear();
     if (c.flush_buf) cudaFree(c.flush_buf);
+    if (g_side) {
+        cudaStreamSynchronize(g_side);
+        cudaStreamDestroy(g_side);
+        cudaEventDestroy(g_side_ev);
+        cudaEventDestroy(g_main_ev);
+        g_side = nullptr;
+        g_side_pending = false;
+    }
     cudaFree(c.reduce_scratch);
     cudaFree(c.work_counter);
     cudaFreeHost(c.reduce_host);
