@@ -58,3 +58,29 @@ def test_p1_matrix_and_action(engine, oracle, alpha, beta):
                           tab, alpha=0.0, beta=1.0)
         yo *= beta
     assert np.abs(y.data_ro - yo).max() < 1e-12 * np.abs(yo).max()
+
+
+def test_pyop2_golden_arrays_on_the_device(engine):
+    """The reference's own value-level pins for this path -- the 2-triangle mass
+    matrix and RHS of tests/pyop2/test_matrices.py:462-503 (fixture
+    tests/golden/pyop2_test_matrices.json) -- checked directly against the CUDA
+    path.  The reference kernels hard-code an 8-digit quadrature table, so its
+    RHS differs from the exact integral by ~5e-8 relative: tolerance 1e-6 for
+    the RHS, the reference's own 1e-5 for the matrix."""
+    import json
+    import os
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "pyop2_test_matrices.json")))
+    cells, nodes = op2.Set(2), op2.Set(4)
+    # the golden kernels order the P1 basis {x, y, 1-x-y}; FIAT order is {1-x-y, x, y}
+    cmap = np.array(g["elem_node_map"], dtype=np.int32)[:, [2, 0, 1]]
+    m = op2.Map(cells, nodes, 3, cmap)
+    X = op2.Dat(op2.DataSet(nodes, 2), np.array(g["coords"]))
+    mat = op2.Mat(op2.Sparsity((nodes, nodes), [(m, m, None)]))
+    op2.par_loop(op2.Kernel("helmholtz", degree=1, alpha=0.0, beta=1.0, rank=2, cell="triangle"), cells,
+                 mat(op2.INC, (m, m)), X(op2.READ, m))
+    np.testing.assert_allclose(mat.values, np.array(g["expected_matrix"]), atol=g["expected_matrix_eps"])
+    f = op2.Dat(nodes, np.array(g["f"]))
+    b = op2.Dat(nodes)
+    op2.par_loop(op2.Kernel("helmholtz", degree=1, alpha=0.0, beta=1.0, cell="triangle"), cells,
+                 b(op2.INC, m), X(op2.READ, m), f(op2.READ, m))
+    np.testing.assert_allclose(b.data_ro, np.array(g["expected_rhs"]), rtol=1e-6)
