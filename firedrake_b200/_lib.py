@@ -103,6 +103,8 @@ SIGNATURES = {
     "fdb_vec_scale": (C.c_int, [C.c_size_t, C.c_double, C.c_void_p]),
     "fdb_vec_dot": (C.c_int, [C.c_size_t, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]),
     "fdb_vec_pointwise_mult": (C.c_int, [C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fdb_interpolate_q1": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_int32, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "fdb_comm_get_unique_id": (C.c_int, [C.c_char_p]),
     "fdb_comm_init": (C.c_int, [C.c_int, C.c_int, C.c_char_p]),
     "fdb_comm_finalize": (C.c_int, []),

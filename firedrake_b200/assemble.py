@@ -59,6 +59,28 @@ class FunctionSpace:
         return self.V.boundary_nodes(sub_domain)
 
 
+def interpolate_q1(V: "FunctionSpace", source: op2.Dat, target: op2.Dat = None):
+    """``Function(V).interpolate(w)`` for a Q1 (x) P1 source ``w`` (scalar or
+    vector, e.g. the mesh coordinates -> the physical position of every node of
+    V): the dual-evaluation parloop of firedrake/interpolation.py:977-1171 with
+    WRITE access on the target.  Returns the target Dat (device resident)."""
+    from . import _lib
+    from .fiat_lite import interval_element
+    cdim = source.cdim
+    if target is None:
+        target = op2.Dat(op2.DataSet(V.node_set, cdim))
+    if not hasattr(V, "_dev_offsets"):
+        V._dev_offsets = (op2.DeviceArray.from_host(np.ascontiguousarray(V.V.offset, dtype=np.int32)),
+                          op2.DeviceArray.from_host(np.ascontiguousarray(V.mesh.coord_offset, dtype=np.int32)))
+    nodes = np.ascontiguousarray(interval_element(V.degree).nodes, dtype=np.float64)
+    _lib.check(_lib.lib().fdb_interpolate_q1(
+        target.device_ptr, source.device_ptr, V.cell_node_map.device_ptr, V.coord_map.device_ptr,
+        V._dev_offsets[0].ptr, V._dev_offsets[1].ptr, V.cell_set.total_size, V.mesh.nz, V.degree + 1,
+        cdim, nodes.ctypes.data), "fdb_interpolate_q1")
+    target._device_written()
+    return target
+
+
 class DirichletBC:
     """``DirichletBC(V, g, sub_domain)``: node subset + value
     (firedrake/bcs.py:260-457)."""

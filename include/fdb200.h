@@ -232,6 +232,16 @@ int fdb_vec_scale(size_t n, double a, double *x);
 int fdb_vec_dot(size_t n, const double *x, const double *y, double *out);
 int fdb_vec_pointwise_mult(size_t n, const double *x, const double *y, double *w);
 
+/* ----------------------------------------------------------- interpolation
+ * Dual-evaluation parloop with WRITE access (firedrake/interpolation.py:977-1171):
+ * interpolate a Q1 (x) P1 field (cdim components, AoS) into the Q_p (x) P_p
+ * space whose 1-D node positions are `nodes_host` (dof numbering, n1d = p+1).
+ * Device pointers for data, maps and the two offset arrays (zeros when not
+ * extruded); `nlay` cells per column. */
+int fdb_interpolate_q1(double *out, const double *src, const fdb_int *map_t, const fdb_int *map_s,
+                       const fdb_int *off_t_dev, const fdb_int *off_s_dev, fdb_int ncols, int nlay,
+                       int n1d, int cdim, const double *nodes_host);
+
 /* ---------------------------------------------------- communicator and halos
  * One process per GPU.  The NCCL communicator replaces the MPI communicator of
  * pyop2/mpi.py; the 128-byte unique id is created on rank 0 and distributed by

@@ -81,3 +81,19 @@ def test_get_diagonal(engine):
     ro, co, va = A.csr()
     diag = np.array([va[ro[r]:ro[r + 1]][co[ro[r]:ro[r + 1]] == r][0] for r in range(V.node_count)])
     assert np.abs(d.data_ro - diag).max() < 1e-12 * np.abs(diag).max()
+
+
+@pytest.mark.parametrize("p", [1, 3, 4])
+def test_interpolate_coordinates(engine, p):
+    """interpolate(SpatialCoordinate) into CG_p^3 ==
+    the trilinear image of the reference node positions (NumPy restatement
+    ``ExtrudedFunctionSpace.dof_coordinates``), and a scalar Q1 field too."""
+    from firedrake_b200.assemble import interpolate_q1
+    mesh = ExtrudedHexMesh(4, 3, 5, warp=0.05, permute_seed=2)
+    V = FunctionSpace(mesh, p)
+    Xp = interpolate_q1(V, V.coordinates)
+    ref = V.V.dof_coordinates()
+    assert np.abs(Xp.data_ro - ref).max() < 1e-14
+    w = op2.Dat(op2.DataSet(V.vertex_set, 1), 2.0 * mesh.coordinates[:, 0] - mesh.coordinates[:, 2])
+    wp = interpolate_q1(V, w)
+    assert np.abs(wp.data_ro - (2.0 * ref[:, 0] - ref[:, 2])).max() < 1e-14
