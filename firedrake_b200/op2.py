@@ -401,6 +401,15 @@ class Dat:
         """Legacy parloop argument ``dat(op2.INC, map)`` (pyop2/parloop.py:709-743)."""
         return LegacyArg(self, access, path)
 
+    def __del__(self):
+        # the engine's host-pointer mirror cache is keyed on the buffer address: drop the
+        # entry so that a later allocation at the same address cannot hit a stale mirror
+        try:
+            if _lib._initialised is not None and self._data is not None:
+                _lib._lib.fdb_mirror_drop(self._data.ctypes.data)
+        except Exception:
+            pass
+
 
 class Sparsity:
     """``op2.Sparsity((row_dset, col_dset), [(rmap, cmap, None)])``
