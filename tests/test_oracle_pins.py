@@ -336,3 +336,37 @@ def test_dg_advection_oracle_invariants(oracle):
     assert abs(oracle.dg_rhs(m, q2, u, dt=0.1).sum() - s0) < 1e-13
     # facet bookkeeping of the synthetic mesh
     assert len(m.int_facet_cells) == 7 * 6 + 8 * 5 and len(m.ext_facet_cells) == 2 * (8 + 6)
+
+
+def test_dg_advection_oracle_analytic_single_cell(oracle):
+    """One unit-square cell, u = (1, 0), q = x, q_in = 0: the weak form of
+    q_t = -div(u q) = -1 gives L1_i = -dt * int phi_i = -dt/4 for each DQ1 basis
+    function (integration by parts of the cell term against the outflow term)."""
+    from firedrake_b200.fiat_lite import interval_element
+    from firedrake_b200.utility_meshes import QuadMesh
+    m = QuadMesh(1, 1)
+    el = interval_element(1, 2, "gl")                 # DQ1 nodes = the two Gauss points
+    xn = el.nodes
+    q = np.array([xn[ax] for ax in range(2) for ay in range(2)])   # q = x at node (ax, ay)
+    u = np.tile(np.array([1.0, 0.0]), (4, 1))
+    for nq in (2, 3, 4):
+        r = oracle.dg_rhs(m, q, u, dt=0.5, q_in=0.0, nq=nq)
+        np.testing.assert_allclose(r, -0.5 / 4 * np.ones(4), rtol=0, atol=1e-15)
+    # and with the inflow value q_in = 2 the x = 0 face adds +dt * int phi_i(0, y) * 2 dy
+    B0, _ = el.tabulate([0.0])
+    r = oracle.dg_rhs(m, q, u, dt=0.5, q_in=2.0)
+    expect = np.array([-0.125 + 0.5 * 2.0 * B0[0, ax] * 0.5 for ax in range(2) for ay in range(2)])
+    np.testing.assert_allclose(r, expect, atol=1e-15)
+
+
+def test_gll_points_known_values():
+    """GLL nodes for p = 2, 3, 4 against their closed forms on [0, 1]."""
+    np.testing.assert_allclose(gll_points(2), [0.0, 0.5, 1.0], atol=1e-16)
+    np.testing.assert_allclose(gll_points(3), [0.0, 0.5 - 0.5 / np.sqrt(5), 0.5 + 0.5 / np.sqrt(5), 1.0], atol=1e-15)
+    np.testing.assert_allclose(gll_points(4), [0.0, 0.5 - 0.5 * np.sqrt(3 / 7), 0.5, 0.5 + 0.5 * np.sqrt(3 / 7), 1.0],
+                               atol=1e-15)
+    # Lagrange property of the tabulation at its own nodes
+    for p in (1, 2, 3, 4, 5):
+        el = interval_element(p)
+        B, _ = el.tabulate(el.nodes)
+        np.testing.assert_allclose(B, np.eye(p + 1), atol=1e-13)
