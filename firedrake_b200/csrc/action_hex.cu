@@ -14,7 +14,17 @@
 //   layout Y: lane t owns index t along y, holds [x][z]   (quadrature points)
 // Contractions along in-slab axes run in registers (N^2 x N FMAs against a
 // constant-bank table); the two orientation changes go through a per-warp
-// shared-memory tile with __syncwarp only -- no block-level barrier anywhere.
+// shared-memory tile with __syncwarp only -- no block-level barrier in the work
+// loop.
+//
+// Data movement: a three-stage cp.async pipeline per warp (map rows -> indices
+// and values -> compute) with chunks of columns handed out by an atomic counter;
+// the quadrature (zeta) loop is rolled, with U / Vp kept column-rotated, so that
+// the loop body fits the instruction cache and 168 registers (12 warps per SM at
+// p = 3).  Template flags: MASS (beta != 0), ATOMIC vs coloured scatter, MATRIX
+// (rank 2: columns of the element tensor as actions on unit vectors, also the
+// diagonal), SLIM (p = 5: one staged map row per column, indices recomputed).
+// DESIGN.md section 4.1 has the measurements behind each of these choices.
 //
 // Arithmetic: the basis is first interpolated to the N Gauss points per axis
 // (B (x) B (x) B), gradients are then taken with the collocated derivative
@@ -258,11 +268,11 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *wbase = reinterpret_cast<double *>(smem_raw + (size_t)warp * WS::BYTES);
     double *s_tile = wbase;
-    double *s_u = s_tile + WS::TILE;                 // [2][CWS][US]
-    double *s_coord = s_u + WS::UBUF;                // [2][CWS][CS]
-    int *s_idx = reinterpret_cast<int *>(s_coord + WS::COORD);   // [2][CWS][US]
-    int *s_mapraw = s_idx + WS::IDX;                 // [CWS][US]
-    int *s_vidx = s_mapraw + WS::MAPRAW;             // [2][CWS][8]
+    double *s_u = s_tile + WS::TILE;                 // [CWS][US]   (single buffer)
+    double *s_coord = s_u + WS::UBUF;                // [CWS][CS]   (single buffer)
+    int *s_idx = reinterpret_cast<int *>(s_coord + WS::COORD);   // [2][CWS][US]  (empty if SLIM)
+    int *s_mapraw = s_idx + WS::IDX;                 // [CWS][US], or [3][2][US] if SLIM
+    int *s_vidx = s_mapraw + WS::MAPRAW;             // [2][CWS][8], or [3][2][8] if SLIM
     int *s_off0 = reinterpret_cast<int *>(smem_raw + (size_t)WPC<N, SLIM>::value * WS::BYTES);
     int *s_off1 = s_off0 + ND;
 
