@@ -118,3 +118,12 @@ def test_quadmesh_slabs():
         assert ((m.nbr[:m.num_owned_cells, 0] < 0) == (gc == 0)).all()
         assert ((m.nbr[:m.num_owned_cells, 1] < 0) == (gc == 8)).all()
     assert owned == 36
+
+
+def test_firedrake_hook_needs_firedrake():
+    """The real-Firedrake hook imports cleanly and fails loudly (ImportError)
+    where PyOP2 is absent -- it can never silently replace anything here."""
+    import firedrake_b200.firedrake_hook as hook
+    with pytest.raises(ImportError):
+        hook.install()
+    hook.uninstall()        # no-op when nothing was installed
