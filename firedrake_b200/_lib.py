@@ -59,6 +59,33 @@ class CallArgs(C.Structure):
     ]
 
 
+# generic wrapper builder (fdb_wrapper_*)
+READ, WRITE, RW, INC, MIN, MAX = 1, 2, 3, 4, 5, 6
+ARG_DAT, ARG_GLOBAL, ARG_MAT = 1, 2, 3
+F64, F32, I32, U32, I64 = 1, 2, 3, 4, 5
+REGION_ALL, REGION_ON_BOTTOM, REGION_ON_TOP, REGION_ON_INTERIOR_FACETS = 0, 1, 2, 3
+WRAP_MAX_ARGS, WRAP_MAX_MAPS, WRAP_MAX_MATS = 16, 8, 4
+
+
+class WrapperArg(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32), ("access", C.c_int32), ("dtype", C.c_int32),
+        ("dim", C.c_int32), ("dim2", C.c_int32), ("map", C.c_int32), ("map2", C.c_int32),
+        ("arity", C.c_int32), ("arity2", C.c_int32),
+        ("offset", C.POINTER(C.c_int32)), ("offset2", C.POINTER(C.c_int32)),
+        ("permutation", C.POINTER(C.c_int32)),
+        ("interior_horizontal", C.c_int32),
+    ]
+
+
+class WrapperDesc(C.Structure):
+    _fields_ = [
+        ("kernel_source", C.c_char_p), ("kernel_name", C.c_char_p),
+        ("nargs", C.c_int32), ("args", C.POINTER(WrapperArg)),
+        ("extruded", C.c_int32), ("subset", C.c_int32), ("iteration_region", C.c_int32),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/fdb200.h declares
 SIGNATURES = {
     "fdb_init": (C.c_int, [C.c_int]),
@@ -86,6 +113,12 @@ SIGNATURES = {
     "fdb_kernel_create": (C.c_int, [C.POINTER(KernelDesc), C.POINTER(C.c_void_p)]),
     "fdb_kernel_destroy": (C.c_int, [C.c_void_p]),
     "fdb_kernel_call": (C.c_int, [C.c_void_p, C.POINTER(CallArgs)]),
+    "fdb_wrapper_source": (C.c_int, [C.POINTER(WrapperDesc), C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "fdb_wrapper_compile": (C.c_int, [C.POINTER(WrapperDesc), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "fdb_wrapper_create": (C.c_int, [C.POINTER(WrapperDesc), C.POINTER(C.c_void_p)]),
+    "fdb_mat_create_blocked": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                         C.POINTER(C.c_void_p)]),
+    "fdb_mat_set_diagonal_blocked": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_int]),
     "fdb_mat_create": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_int, C.c_void_p, C.c_int,
                                  C.POINTER(C.c_void_p)]),
     "fdb_mat_destroy": (C.c_int, [C.c_void_p]),

@@ -1,0 +1,264 @@
+"""Generic parloops: arbitrary C local kernels behind ``op2.par_loop``.
+
+Mirrors the reference's C-string kernel route -- ``op2.Kernel(code, name)`` ->
+``CStringLocalKernel`` (pyop2/local_kernel.py:186-207) -> ``WrapperBuilder``
+(pyop2/codegen/builder.py:702-1008) -> host compiler -- with the engine's
+NVRTC wrapper builder (``fdb_wrapper_*`` in include/fdb200.h,
+csrc/wrapper_jit.cu): the description of the parloop's arguments is turned into
+a ``fdb_wrapper_desc``, the engine generates the sm_100a global kernel around the
+local kernel source and compiles it at run time.
+
+The argument description (access, dtype, dims, map slots, offsets,
+permutations) is exactly what PyOP2 folds into ``GlobalKernel.cache_key``
+(pyop2/global_kernel.py:309-317), so it is also the cache key here.
+
+Status: the generated code is checked on the CPU (tests/test_codegen.py: NVRTC
+compile for sm_100a, and a host re-compilation of the generated wrapper body run
+against the reference's golden arrays); it has not yet run on a GPU (written
+after round 1's GPU budget was spent) -- tests/test_jit_gpu.py is the first
+validation, gated behind FDB_RUN_UNVALIDATED=1 until it has passed once.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+
+_DTYPE_CODE = {
+    np.dtype(np.float64): _lib.F64, np.dtype(np.float32): _lib.F32,
+    np.dtype(np.int32): _lib.I32, np.dtype(np.uint32): _lib.U32, np.dtype(np.int64): _lib.I64,
+}
+_REGIONS = {"ALL": _lib.REGION_ALL, "ON_BOTTOM": _lib.REGION_ON_BOTTOM, "ON_TOP": _lib.REGION_ON_TOP,
+            "ON_INTERIOR_FACETS": _lib.REGION_ON_INTERIOR_FACETS}
+
+
+@dataclass(frozen=True)
+class CStringKernel:
+    """``op2.Kernel(code, name)``: a local kernel given as C source
+    (pyop2/local_kernel.py:33-43, 186-207).  Every argument is a flat pointer to
+    the packed local data of one parloop argument, in parloop argument order."""
+    code: str
+    name: str
+    accesses: tuple = None
+    flop_count: int = 0
+    opts: dict = field(default=None, compare=False, hash=False)
+
+    def __post_init__(self):
+        if not isinstance(self.name, str) or not self.name.isidentifier():
+            raise ValueError("kernel name must be a C identifier")
+
+
+class PermutedMap:
+    """``op2.PermutedMap(map, permutation)``: ``local[i] = global[map[permutation[i]]]``
+    (pyop2/types/map.py:172-230).  Adds no new map argument to the wrapper."""
+
+    def __init__(self, map_, permutation):
+        self.map_ = map_
+        self.permutation = np.ascontiguousarray(permutation, dtype=np.int32)
+        if sorted(self.permutation.tolist()) != list(range(map_.arity)):
+            raise ValueError("permutation must be a permutation of range(arity)")
+        self.iterset, self.toset, self.arity = map_.iterset, map_.toset, map_.arity
+        self.name = f"permuted_{map_.name}"
+
+    @property
+    def offset(self):
+        return None if self.map_.offset is None else np.asarray(self.map_.offset)[self.permutation]
+
+
+def _base(map_):
+    return map_.map_ if isinstance(map_, PermutedMap) else map_
+
+
+def distinct_maps(args):
+    """The parloop's map arguments: distinct by identity, first-use order; a
+    PermutedMap contributes its base map (pyop2/parloop.py:203-212)."""
+    maps = []
+    for a in args:
+        for m in (getattr(a, "map", None), getattr(a, "cmap", None)):
+            if m is not None and not any(_base(m) is b for b in maps):
+                maps.append(_base(m))
+    return maps
+
+
+class WrapperSpec:
+    """The compile-time description of one generic parloop."""
+
+    def __init__(self, kernel: CStringKernel, args, *, extruded=False, subset=False,
+                 iteration_region="ALL"):
+        from . import op2
+        self.kernel = kernel
+        self.maps = distinct_maps(args)
+        if len(args) > _lib.WRAP_MAX_ARGS or len(self.maps) > _lib.WRAP_MAX_MAPS:
+            raise ValueError("too many arguments / maps for the generic wrapper")
+        self._keep = []
+        arr = (_lib.WrapperArg * len(args))()
+        key = [kernel.code, kernel.name, bool(extruded), bool(subset), iteration_region]
+        for i, a in enumerate(args):
+            w = arr[i]
+            w.access = int(a.access)
+            w.map = w.map2 = -1
+            data = a.data
+            if isinstance(data, op2.Mat):
+                rmap, cmap = a.map, a.cmap
+                w.kind, w.dtype = _lib.ARG_MAT, _lib.F64
+                w.dim = w.dim2 = data.bs
+                w.map, w.map2 = self._slot(rmap), self._slot(cmap)
+                w.arity, w.arity2 = rmap.arity, cmap.arity
+                w.offset, w.offset2 = self._ints(rmap.offset), self._ints(cmap.offset)
+                key.append(("mat", w.access, data.bs, w.map, w.map2, w.arity, w.arity2,
+                            self._tup(rmap.offset), self._tup(cmap.offset)))
+            elif isinstance(data, op2.Global):
+                w.kind = _lib.ARG_GLOBAL
+                w.dtype = _DTYPE_CODE[np.dtype(data._data.dtype)]
+                w.dim = int(np.prod(data.dim))
+                key.append(("glob", w.access, w.dtype, w.dim))
+            else:
+                w.kind = _lib.ARG_DAT
+                w.dtype = _DTYPE_CODE[np.dtype(data.dtype)]
+                w.dim = data.cdim
+                m = a.map
+                if m is not None:
+                    w.map, w.arity = self._slot(m), m.arity
+                    w.offset = self._ints(m.offset)
+                    perm = m.permutation if isinstance(m, PermutedMap) else None
+                    w.permutation = self._ints(perm)
+                    key.append(("dat", w.access, w.dtype, w.dim, w.map, w.arity, self._tup(m.offset),
+                                self._tup(perm)))
+                else:
+                    key.append(("dat", w.access, w.dtype, w.dim, -1))
+        self.cache_key = tuple(key)
+        d = _lib.WrapperDesc()
+        d.kernel_source = kernel.code.encode()
+        d.kernel_name = kernel.name.encode()
+        d.nargs, d.args = len(args), arr
+        d.extruded, d.subset = int(bool(extruded)), int(bool(subset))
+        d.iteration_region = _REGIONS[iteration_region]
+        self._keep.append(arr)
+        self.desc = d
+
+    # -- helpers
+    def _slot(self, m):
+        for i, b in enumerate(self.maps):
+            if b is _base(m):
+                return i
+        raise AssertionError("map not registered")
+
+    def _ints(self, v):
+        if v is None:
+            return None
+        a = np.ascontiguousarray(v, dtype=np.int32)
+        self._keep.append(a)
+        return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+    @staticmethod
+    def _tup(v):
+        return None if v is None else tuple(int(x) for x in np.asarray(v).ravel())
+
+    # -- products (no GPU needed for the first two)
+    def source(self) -> str:
+        """The generated CUDA source of ``wrap_<name>``."""
+        L = _lib.load()
+        need = C.c_size_t()
+        _lib.check(L.fdb_wrapper_source(C.byref(self.desc), None, 0, C.byref(need)), "fdb_wrapper_source")
+        buf = C.create_string_buffer(need.value)
+        _lib.check(L.fdb_wrapper_source(C.byref(self.desc), buf, need.value, C.byref(need)), "fdb_wrapper_source")
+        return buf.value.decode()
+
+    def compile(self) -> bytes:
+        """NVRTC-compile for sm_100a; returns the cubin image (ahead-of-time path)."""
+        L = _lib.load()
+        need = C.c_size_t()
+        _lib.check(L.fdb_wrapper_compile(C.byref(self.desc), None, 0, C.byref(need)), "fdb_wrapper_compile")
+        buf = (C.c_char * need.value)()
+        _lib.check(L.fdb_wrapper_compile(C.byref(self.desc), buf, need.value, C.byref(need)), "fdb_wrapper_compile")
+        return bytes(buf)
+
+    def create(self):
+        """Generate, compile and load on the active device -> kernel handle."""
+        h = C.c_void_p()
+        _lib.check(_lib.lib().fdb_wrapper_create(C.byref(self.desc), C.byref(h)), "fdb_wrapper_create")
+        return h
+
+
+_handles = {}     # cache_key -> handle: the reference caches compiled global kernels the same way
+
+
+def _handle(spec: WrapperSpec):
+    h = _handles.get(spec.cache_key)
+    if h is None:
+        h = _handles[spec.cache_key] = spec.create()
+    return h
+
+
+def par_loop(kernel: CStringKernel, iterset, *args, iteration_region="ALL"):
+    """``op2.par_loop(op2.Kernel(code, name), iterset, *args)`` for a C-string
+    kernel: device-resident Dats, one generated wrapper per distinct argument
+    description.  Follows pyop2/parloop.py:243-260 without the halo phases (generic
+    parloops run unpartitioned for now)."""
+    from . import op2
+    base = iterset.superset if isinstance(iterset, op2.Subset) else iterset
+    if kernel.accesses is not None and tuple(a.access for a in args) != tuple(kernel.accesses):
+        raise ValueError("access descriptors do not match the kernel's")
+    for a in args:
+        for m in (a.map, getattr(a, "cmap", None)):
+            if m is None:
+                continue
+            if m.iterset is not base:
+                raise op2.MapValueError(f"map {m.name} is not defined on the iteration set")
+        if a.map is not None and not isinstance(a.data, op2.Mat) and a.map.toset is not a.data.dataset.set:
+            raise op2.MapValueError(f"map {a.map.name} does not target {a.data.name}'s set")
+        if a.map is None and isinstance(a.data, op2.Dat) and a.data.dataset.set is not base:
+            raise op2.MapValueError(f"direct argument {a.data.name} is not defined on the iteration set")
+    spec = WrapperSpec(kernel, args, extruded=base._extruded, subset=isinstance(iterset, op2.Subset),
+                       iteration_region=iteration_region)
+    h = _handle(spec)
+    ca = _lib.CallArgs()
+    lgmat = []
+    ptrs = []
+    for a in args:
+        if isinstance(a.data, op2.Mat):
+            ptrs.append(a.data.handle.value)
+            if a.lgmaps is not None:
+                lgmat.append(a)
+        elif isinstance(a.data, op2.Global):
+            ptrs.append(a.data._data.ctypes.data)
+        else:
+            ptrs.append(a.data.device_ptr)
+    subset = None
+    if isinstance(iterset, op2.Subset):
+        if not hasattr(iterset, "_dev_idx"):
+            iterset._dev_idx = op2.DeviceArray.from_host(iterset.indices)
+        subset = iterset._dev_idx.ptr
+    layers = base.layers_array.ravel() if base._extruded else None
+    L = _lib.lib()
+    for a in lgmat:
+        r, c = (np.ascontiguousarray(v, dtype=np.int32) for v in a.lgmaps)
+        _lib.check(L.fdb_mat_set_lgmaps(a.data.handle, r.ctypes.data, c.ctypes.data))
+    try:
+        for start, end in (iterset.core_part, iterset.owned_part):
+            if end <= start:
+                continue
+            ca.start, ca.end = int(start), int(end)
+            if layers is not None:
+                ca.layers = layers.ctypes.data_as(C.POINTER(C.c_int32))
+            ca.subset = subset
+            ca.nargs, ca.args = len(ptrs), (C.c_void_p * len(ptrs))(*ptrs)
+            mp = [m.device_ptr for m in spec.maps]
+            ca.nmaps, ca.maps = len(mp), (C.c_void_p * max(len(mp), 1))(*mp)
+            ca.location, ca.writeback, ca.output_is_zero = _lib.LOC_DEVICE, 0, 0
+            _lib.check(L.fdb_kernel_call(h, C.byref(ca)), "wrap_" + kernel.name)
+    finally:
+        for a in lgmat:
+            _lib.check(L.fdb_mat_set_lgmaps(a.data.handle, None, None))
+    for a in args:
+        if a.access == op2.READ:
+            continue
+        if isinstance(a.data, op2.Dat):
+            a.data._device_written()
+            a.data.halo_valid = False
+        else:
+            a.data.dat_version += 1
+    return spec

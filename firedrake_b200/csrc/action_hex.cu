@@ -871,8 +871,9 @@ int fdb_launch_helmholtz_matrix(fdb_kernel_s *k, fdb_int start, fdb_int end, int
     case 2: return launch_matrix_n<2>(k, start, end, nlay, subset, mat, coords, map0, map1, diag_out);
     case 3: return launch_matrix_n<3>(k, start, end, nlay, subset, mat, coords, map0, map1, diag_out);
     case 4: return launch_matrix_n<4>(k, start, end, nlay, subset, mat, coords, map0, map1, diag_out);
+    case 5: return launch_matrix_n<5>(k, start, end, nlay, subset, mat, coords, map0, map1, diag_out);
     }
-    fdb::set_error("helmholtz matrix: degree %d not instantiated (1..3)", k->n1d - 1);
+    fdb::set_error("helmholtz matrix: degree %d not instantiated (1..4)", k->n1d - 1);
     return 1;
 }
 

@@ -51,6 +51,8 @@ int require_init();
 
 }  // namespace fdb
 
+struct fdb_jit_s;   // NVRTC-compiled generic wrapper (wrapper_jit.cu)
+
 // kernel object behind fdb_kernel_t
 struct fdb_kernel_s {
     fdb_kernel_desc desc;
@@ -66,7 +68,12 @@ struct fdb_kernel_s {
     fdb_int *d_colour_cols = nullptr;     // columns sorted by colour
     int ncolours = 0;
     fdb_int colour_start[65];
+    // non-NULL: this handle is a generated wrapper around an arbitrary local kernel
+    fdb_jit_s *jit = nullptr;
 };
+
+int fdb_jit_call(fdb_kernel_s *k, const fdb_call_args *a);
+void fdb_jit_destroy(fdb_jit_s *j);
 
 extern "C" int fdb_mirror_set_version(const void *host, uint64_t version);
 bool fdb_mirror_is_current(const void *host, size_t nbytes, uint64_t version);
@@ -75,6 +82,9 @@ typedef struct fdb_mat_s *fdb_mat_t;
 int fdb_mat_device_view(fdb_mat_t m, const long long **rowptr, const fdb_int **colidx, double **vals,
                         const fdb_int **row_lg, const fdb_int **col_lg);
 int fdb_mat_rank_table(fdb_mat_t m, const unsigned short **rank, int *nvar);
+int fdb_mat_block_size(fdb_mat_t m, int *bs);
+int fdb_mat_scalar_view_begin(fdb_mat_t blocked, fdb_mat_t *view);
+int fdb_mat_scalar_view_end(fdb_mat_t blocked, fdb_mat_t view);
 int fdb_launch_helmholtz_matrix(fdb_kernel_s *k, fdb_int start, fdb_int end, int nlay,
                                 const fdb_int *subset, fdb_mat_t mat, const double *coords,
                                 const fdb_int *map0, const fdb_int *map1, double *diag_out);

@@ -326,8 +326,9 @@ int fdb_kernel_create(const fdb_kernel_desc *d, fdb_kernel_t *out)
 int fdb_kernel_destroy(fdb_kernel_t k)
 {
     if (!k) return 0;
+    if (ctx().ready) cudaStreamSynchronize(ctx().stream);
+    if (k->jit) fdb_jit_destroy(k->jit);
     if (ctx().ready) {
-        cudaStreamSynchronize(ctx().stream);
         if (k->d_off0) cudaFree(k->d_off0);
         if (k->d_off1) cudaFree(k->d_off1);
         if (k->d_colour_cols) cudaFree(k->d_colour_cols);
@@ -343,6 +344,7 @@ int fdb_kernel_call(fdb_kernel_t k, const fdb_call_args *a)
         set_error("fdb_kernel_call: NULL argument");
         return 1;
     }
+    if (k->jit) return fdb_jit_call(k, a);      // generated wrapper (wrapper_jit.cu)
     if (k->desc.form == FDB_FORM_DG_ADVECTION) {
         // args = [out (INC), coords, q, u, consts (HOST double[2] {dtc, q_in}), facet numbers]
         // maps = [DQ1 (facet-)node map, CG1 (facet-)node map]
@@ -404,8 +406,12 @@ int fdb_kernel_call(fdb_kernel_t k, const fdb_call_args *a)
             set_error("fdb_kernel_call: 2-form expects 2 args (mat, coords) and 2 maps");
             return 1;
         }
-        if (k->desc.cdim != 1) {
-            set_error("fdb_kernel_call: matrix assembly of vector spaces is not implemented");
+        fdb_mat_t target = (fdb_mat_t)a->args[0];
+        int mat_bs = 1;
+        fdb_mat_block_size(target, &mat_bs);
+        if (mat_bs != k->desc.cdim) {
+            set_error("fdb_kernel_call: Mat block size %d != value size %d of the argument space", mat_bs,
+                      k->desc.cdim);
             return 1;
         }
         if (k->desc.scatter != FDB_SCATTER_ATOMIC) {
@@ -434,8 +440,17 @@ int fdb_kernel_call(fdb_kernel_t k, const fdb_call_args *a)
             dm[0] = a->maps[0];
             dm[1] = a->maps[1];
         }
-        return fdb_launch_helmholtz_matrix(k, a->start, a->end, nlay, dsub, (fdb_mat_t)a->args[0],
-                                           dcoords, dm[0], dm[1], nullptr);
+        if (mat_bs == 1)
+            return fdb_launch_helmholtz_matrix(k, a->start, a->end, nlay, dsub, target, dcoords, dm[0], dm[1],
+                                               nullptr);
+        // vector-valued space: the element tensor of the Helmholtz family is A_scalar (x) I_cdim
+        // (off-diagonal component blocks vanish identically), so the scalar kernel assembles into
+        // a scalar view of the blocked pattern, which is then added to the block diagonals
+        fdb_mat_t view = nullptr;
+        if (fdb_mat_scalar_view_begin(target, &view)) return 1;
+        int rc = fdb_launch_helmholtz_matrix(k, a->start, a->end, nlay, dsub, view, dcoords, dm[0], dm[1], nullptr);
+        int rc2 = fdb_mat_scalar_view_end(target, view);
+        return rc ? rc : rc2;
     }
     if (k->desc.diagonal) {
         // args = [d (INC), coords]; device-resident only

@@ -39,6 +39,10 @@ struct fdb_mat_s {
     // table.  rank[((col*nvar + v)*arity + j)*arity + i].  NULL: binary search.
     unsigned short *d_rank = nullptr;
     int nvar = 0, arity = 0, nlay = 0;
+    // block size (BAIJ-like): rowptr/colidx address NODES, vals holds bs*bs doubles
+    // per stored block, row-major inside the block; lgmaps are dof-level (nrows*bs)
+    int bs = 1;
+    bool shallow = false;      // scalar view sharing the pattern of a blocked matrix
 };
 
 namespace {
@@ -137,6 +141,79 @@ __global__ void k_set_diag(const long long *__restrict__ rowptr, const fdb_int *
     if (colidx[lo] == r) vals[lo] = value;
 }
 
+// blocked SpMV: one warp per node row, bs partial sums per lane
+template <int BS>
+__global__ void k_spmv_blocked(fdb_int nrows, const long long *__restrict__ rowptr,
+                               const fdb_int *__restrict__ colidx, const double *__restrict__ vals,
+                               const double *__restrict__ x, double *__restrict__ y)
+{
+    long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long r = w; r < nrows; r += nw) {
+        double s[BS];
+#pragma unroll
+        for (int a = 0; a < BS; a++) s[a] = 0.0;
+        for (long long k = rowptr[r] + lane; k < rowptr[r + 1]; k += 32) {
+            const double *blk = vals + k * (BS * BS);
+            const double *xc = x + (long long)colidx[k] * BS;
+#pragma unroll
+            for (int a = 0; a < BS; a++)
+#pragma unroll
+                for (int b = 0; b < BS; b++) s[a] = fma(blk[a * BS + b], xc[b], s[a]);
+        }
+#pragma unroll
+        for (int a = 0; a < BS; a++) {
+            for (int o = 16; o > 0; o >>= 1) s[a] += __shfl_xor_sync(0xffffffffu, s[a], o);
+            if (lane == 0) y[r * BS + a] = s[a];
+        }
+    }
+}
+
+// diagonal of constrained node rows: component idx, or every component when idx < 0
+__global__ void k_set_diag_blocked(const long long *__restrict__ rowptr, const fdb_int *__restrict__ colidx,
+                                   double *__restrict__ vals, const fdb_int *__restrict__ rows, fdb_int n,
+                                   double value, int bs, int idx)
+{
+    fdb_int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fdb_int r = rows[i];
+    long long lo = rowptr[r], hi = rowptr[r + 1];
+    while (hi - lo > 1) {
+        long long mid = (lo + hi) >> 1;
+        if (colidx[mid] <= r) lo = mid; else hi = mid;
+    }
+    if (colidx[lo] != r) return;
+    double *blk = vals + lo * bs * bs;
+    for (int a = 0; a < bs; a++)
+        if (idx < 0 || idx == a) blk[a * bs + a] = value;
+}
+
+// node-level lgmap of a dof-level one: a node is masked when ALL its components are;
+// *mixed is raised when only some are (component BC: not expressible per node)
+__global__ void k_node_lgmap(const fdb_int *__restrict__ dof_lg, fdb_int nnodes, int bs,
+                             fdb_int *__restrict__ node_lg, int *__restrict__ mixed)
+{
+    fdb_int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nnodes) return;
+    int masked = 0;
+    for (int a = 0; a < bs; a++) masked += dof_lg[(long long)r * bs + a] < 0;
+    node_lg[r] = masked == bs ? -1 : r;
+    if (masked != 0 && masked != bs) *mixed = 1;
+}
+
+// blocked += scalar (x) I_bs on an identical node pattern
+__global__ void k_add_scalar_blocks(long long nnz, int bs, const double *__restrict__ sv, double *__restrict__ bv)
+{
+    long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; k < nnz; k += (long long)gridDim.x * blockDim.x) {
+        const double v = sv[k];
+        if (v == 0.0) continue;
+        double *blk = bv + k * bs * bs;
+        for (int a = 0; a < bs; a++) blk[a * bs + a] += v;
+    }
+}
+
 int grid1d(long long n)
 {
     long long b = (n + 255) / 256;
@@ -156,6 +233,69 @@ int fdb_mat_rank_table(fdb_mat_t m, const unsigned short **rank, int *nvar)
     return 0;
 }
 
+int fdb_mat_block_size(fdb_mat_t m, int *bs)
+{
+    *bs = m->bs;
+    return 0;
+}
+
+// Scalar view of a blocked matrix for forms whose element tensor is A_scalar (x) I
+// (inner(grad u, grad v) + inner(u, v) on a vector space: the off-diagonal
+// component blocks vanish identically).  The view shares the
+// pattern and the rank table, owns a zeroed value array and node-level lgmaps;
+// ..._end adds it into the diagonal of every block and releases it.
+int fdb_mat_scalar_view_begin(fdb_mat_t mb, fdb_mat_t *view)
+{
+    if (require_init()) return 1;
+    cudaStream_t st = ctx().stream;
+    fdb_mat_s *v = new fdb_mat_s(*mb);
+    v->shallow = true;
+    v->bs = 1;
+    v->d_vals = nullptr;
+    v->d_row_lgmap = v->d_col_lgmap = nullptr;
+    FDB_CUDA(cudaMalloc(&v->d_vals, sizeof(double) * (size_t)mb->nnz));
+    FDB_CUDA(cudaMemsetAsync(v->d_vals, 0, sizeof(double) * (size_t)mb->nnz, st));
+    int *d_mixed = nullptr;
+    FDB_CUDA(cudaMalloc(&d_mixed, sizeof(int)));
+    FDB_CUDA(cudaMemsetAsync(d_mixed, 0, sizeof(int), st));
+    const fdb_int *src[2] = {mb->d_row_lgmap, mb->d_col_lgmap};
+    fdb_int **dst[2] = {&v->d_row_lgmap, &v->d_col_lgmap};
+    for (int i = 0; i < 2; i++) {
+        if (!src[i]) continue;
+        FDB_CUDA(cudaMalloc(dst[i], sizeof(fdb_int) * (size_t)mb->nrows));
+        k_node_lgmap<<<(mb->nrows + 255) / 256, 256, 0, st>>>(src[i], mb->nrows, mb->bs, *dst[i], d_mixed);
+        FDB_LAUNCH_CHECK();
+    }
+    int mixed = 0;
+    FDB_CUDA(cudaMemcpyAsync(&mixed, d_mixed, sizeof(int), cudaMemcpyDeviceToHost, st));
+    FDB_CUDA(cudaStreamSynchronize(st));
+    cudaFree(d_mixed);
+    if (mixed) {
+        set_error("blocked matrix assembly: Dirichlet conditions on single components are not supported "
+                  "by the A (x) I fast path (use the generic wrapper)");
+        cudaFree(v->d_vals);
+        cudaFree(v->d_row_lgmap);
+        cudaFree(v->d_col_lgmap);
+        delete v;
+        return 1;
+    }
+    *view = v;
+    return 0;
+}
+
+int fdb_mat_scalar_view_end(fdb_mat_t mb, fdb_mat_t view)
+{
+    cudaStream_t st = ctx().stream;
+    k_add_scalar_blocks<<<grid1d(mb->nnz), 256, 0, st>>>(mb->nnz, mb->bs, view->d_vals, mb->d_vals);
+    FDB_LAUNCH_CHECK();
+    FDB_CUDA(cudaStreamSynchronize(st));
+    cudaFree(view->d_vals);
+    cudaFree(view->d_row_lgmap);
+    cudaFree(view->d_col_lgmap);
+    delete view;
+    return 0;
+}
+
 int fdb_mat_device_view(fdb_mat_t m, const long long **rowptr, const fdb_int **colidx, double **vals,
                         const fdb_int **row_lg, const fdb_int **col_lg)
 {
@@ -172,7 +312,17 @@ extern "C" {
 int fdb_mat_create(fdb_int nrows, const fdb_int *map_host, fdb_int ncolumns, int arity,
                    const fdb_int *offset_host, int nlayers, fdb_mat_t *out)
 {
+    return fdb_mat_create_blocked(nrows, map_host, ncolumns, arity, offset_host, nlayers, 1, out);
+}
+
+int fdb_mat_create_blocked(fdb_int nrows, const fdb_int *map_host, fdb_int ncolumns, int arity,
+                           const fdb_int *offset_host, int nlayers, int bs, fdb_mat_t *out)
+{
     if (require_init()) return 1;
+    if (bs < 1 || bs > 8) {
+        set_error("fdb_mat_create_blocked: block size %d outside 1..8", bs);
+        return 1;
+    }
     if (nlayers < 1 || arity < 1 || nrows < 1) {
         set_error("fdb_mat_create: bad sizes");
         return 1;
@@ -215,9 +365,21 @@ int fdb_mat_create(fdb_int nrows, const fdb_int *map_host, fdb_int ncolumns, int
     fdb_mat_s *m = new fdb_mat_s;
     m->nrows = nrows;
     m->nnz = nnz;
+    m->bs = bs;
+    const size_t bb = (size_t)bs * bs;
     FDB_CUDA(cudaMalloc(&m->d_rowptr, sizeof(long long) * ((size_t)nrows + 1)));
     FDB_CUDA(cudaMalloc(&m->d_colidx, sizeof(fdb_int) * (size_t)nnz));
-    FDB_CUDA(cudaMalloc(&m->d_vals, sizeof(double) * (size_t)nnz));
+    if (cudaMalloc(&m->d_vals, sizeof(double) * (size_t)nnz * bb) != cudaSuccess) {
+        set_error("fdb_mat_create: %.1f GB of values do not fit (nnz %lld, block size %d)",
+                  (double)nnz * bb * 8.0 / 1e9, nnz, bs);
+        cudaFree(m->d_rowptr);
+        cudaFree(m->d_colidx);
+        cudaFree(keys);
+        cudaFree(d_map);
+        cudaFree(d_off);
+        delete m;
+        return 1;
+    }
     FDB_CUDA(cudaMemsetAsync(m->d_rowptr, 0, sizeof(long long) * ((size_t)nrows + 1), st));
     k_count_rows<<<grid1d(nnz), 256, 0, st>>>(keys, nnz, nrows, m->d_rowptr + 1, m->d_colidx);
     FDB_LAUNCH_CHECK();
@@ -228,7 +390,7 @@ int fdb_mat_create(fdb_int nrows, const fdb_int *map_host, fdb_int ncolumns, int
         set_error("fdb_mat_create: scan failed: %s", e.what());
         return 1;
     }
-    FDB_CUDA(cudaMemsetAsync(m->d_vals, 0, sizeof(double) * (size_t)nnz, st));
+    FDB_CUDA(cudaMemsetAsync(m->d_vals, 0, sizeof(double) * (size_t)nnz * bb, st));
     FDB_CUDA(cudaStreamSynchronize(st));
     cudaFree(keys);
     keys = nullptr;
@@ -281,7 +443,7 @@ int fdb_mat_nnz(fdb_mat_t m, long long *nnz, fdb_int *nrows)
 int fdb_mat_zero(fdb_mat_t m)
 {
     if (require_init()) return 1;
-    FDB_CUDA(cudaMemsetAsync(m->d_vals, 0, sizeof(double) * (size_t)m->nnz, ctx().stream));
+    FDB_CUDA(cudaMemsetAsync(m->d_vals, 0, sizeof(double) * (size_t)m->nnz * m->bs * m->bs, ctx().stream));
     return 0;
 }
 
@@ -296,7 +458,8 @@ int fdb_mat_get_csr(fdb_mat_t m, long long *rowptr, fdb_int *colidx, double *val
         FDB_CUDA(cudaMemcpyAsync(colidx, m->d_colidx, sizeof(fdb_int) * (size_t)m->nnz,
                                  cudaMemcpyDeviceToHost, st));
     if (vals)
-        FDB_CUDA(cudaMemcpyAsync(vals, m->d_vals, sizeof(double) * (size_t)m->nnz, cudaMemcpyDeviceToHost, st));
+        FDB_CUDA(cudaMemcpyAsync(vals, m->d_vals, sizeof(double) * (size_t)m->nnz * m->bs * m->bs,
+                                 cudaMemcpyDeviceToHost, st));
     FDB_CUDA(cudaStreamSynchronize(st));
     return 0;
 }
@@ -316,9 +479,9 @@ int fdb_mat_set_lgmaps(fdb_mat_t m, const fdb_int *row_lgmap_host, const fdb_int
             }
             continue;
         }
-        if (!*dst[i]) FDB_CUDA(cudaMalloc(dst[i], sizeof(fdb_int) * (size_t)m->nrows));
-        FDB_CUDA(cudaMemcpyAsync(*dst[i], src[i], sizeof(fdb_int) * (size_t)m->nrows,
-                                 cudaMemcpyHostToDevice, st));
+        const size_t nlg = (size_t)m->nrows * m->bs;      // dof-level for blocked matrices
+        if (!*dst[i]) FDB_CUDA(cudaMalloc(dst[i], sizeof(fdb_int) * nlg));
+        FDB_CUDA(cudaMemcpyAsync(*dst[i], src[i], sizeof(fdb_int) * nlg, cudaMemcpyHostToDevice, st));
     }
     FDB_CUDA(cudaStreamSynchronize(st));
     return 0;
@@ -326,13 +489,26 @@ int fdb_mat_set_lgmaps(fdb_mat_t m, const fdb_int *row_lgmap_host, const fdb_int
 
 int fdb_mat_set_diagonal(fdb_mat_t m, const fdb_int *rows_host, fdb_int n, double value)
 {
+    return fdb_mat_set_diagonal_blocked(m, rows_host, n, value, -1);
+}
+
+int fdb_mat_set_diagonal_blocked(fdb_mat_t m, const fdb_int *rows_host, fdb_int n, double value, int idx)
+{
     if (require_init()) return 1;
     if (n <= 0) return 0;
+    if (idx >= m->bs) {
+        set_error("fdb_mat_set_diagonal_blocked: component %d >= block size %d", idx, m->bs);
+        return 1;
+    }
     cudaStream_t st = ctx().stream;
     fdb_int *d_rows = nullptr;
     FDB_CUDA(cudaMalloc(&d_rows, sizeof(fdb_int) * (size_t)n));
     FDB_CUDA(cudaMemcpyAsync(d_rows, rows_host, sizeof(fdb_int) * (size_t)n, cudaMemcpyHostToDevice, st));
-    k_set_diag<<<(n + 255) / 256, 256, 0, st>>>(m->d_rowptr, m->d_colidx, m->d_vals, d_rows, n, value);
+    if (m->bs == 1)
+        k_set_diag<<<(n + 255) / 256, 256, 0, st>>>(m->d_rowptr, m->d_colidx, m->d_vals, d_rows, n, value);
+    else
+        k_set_diag_blocked<<<(n + 255) / 256, 256, 0, st>>>(m->d_rowptr, m->d_colidx, m->d_vals, d_rows, n,
+                                                           value, m->bs, idx);
     FDB_LAUNCH_CHECK();
     FDB_CUDA(cudaStreamSynchronize(st));
     cudaFree(d_rows);
@@ -343,7 +519,17 @@ int fdb_mat_mult(fdb_mat_t m, const double *x, double *y)
 {
     if (require_init()) return 1;
     long long threads = (long long)m->nrows * 32;
-    k_spmv<<<grid1d(threads), 256, 0, ctx().stream>>>(m->nrows, m->d_rowptr, m->d_colidx, m->d_vals, x, y);
+    cudaStream_t st = ctx().stream;
+    const int g = grid1d(threads);
+    switch (m->bs) {
+    case 1: k_spmv<<<g, 256, 0, st>>>(m->nrows, m->d_rowptr, m->d_colidx, m->d_vals, x, y); break;
+    case 2: k_spmv_blocked<2><<<g, 256, 0, st>>>(m->nrows, m->d_rowptr, m->d_colidx, m->d_vals, x, y); break;
+    case 3: k_spmv_blocked<3><<<g, 256, 0, st>>>(m->nrows, m->d_rowptr, m->d_colidx, m->d_vals, x, y); break;
+    case 4: k_spmv_blocked<4><<<g, 256, 0, st>>>(m->nrows, m->d_rowptr, m->d_colidx, m->d_vals, x, y); break;
+    default:
+        set_error("fdb_mat_mult: block size %d not instantiated (1..4)", m->bs);
+        return 1;
+    }
     FDB_LAUNCH_CHECK();
     return 0;
 }

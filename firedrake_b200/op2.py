@@ -60,6 +60,7 @@ READ, WRITE, RW, INC, MIN, MAX = (Access.READ, Access.WRITE, Access.RW, Access.I
 ALL = "ALL"
 ON_BOTTOM = "ON_BOTTOM"
 ON_TOP = "ON_TOP"
+ON_INTERIOR_FACETS = "ON_INTERIOR_FACETS"
 
 
 class MapValueError(ValueError):
@@ -422,8 +423,9 @@ class Sparsity:
         self.dsets = tuple(_as_dataset(d) for d in dsets)
         if self.dsets[0].set is not self.dsets[1].set:
             raise NotImplementedError("rectangular sparsities are not supported")
-        if any(d.cdim != 1 for d in self.dsets):
-            raise NotImplementedError("vector-valued matrices are not supported yet")
+        if self.dsets[0].cdim != self.dsets[1].cdim:
+            raise NotImplementedError("row and column block sizes must coincide")
+        self.bs = self.dsets[0].cdim          # BAIJ block size (pyop2/types/mat.py:741-804)
         self.maps = []
         for entry in maps_and_regions:
             rmap, cmap = entry[0], entry[1]
@@ -458,9 +460,16 @@ class Mat:
         off = m.offset
         h = C.c_void_p()
         L = _lib.lib()
-        _lib.check(L.fdb_mat_create(sparsity.shape[0], m.values_with_halo.ctypes.data, it.total_size,
-                                    m.arity, None if off is None else off.ctypes.data, nlay,
-                                    C.byref(h)), "fdb_mat_create")
+        self.bs = sparsity.bs
+        if self.bs == 1:
+            _lib.check(L.fdb_mat_create(sparsity.shape[0], m.values_with_halo.ctypes.data, it.total_size,
+                                        m.arity, None if off is None else off.ctypes.data, nlay,
+                                        C.byref(h)), "fdb_mat_create")
+        else:
+            _lib.check(L.fdb_mat_create_blocked(sparsity.shape[0], m.values_with_halo.ctypes.data,
+                                                it.total_size, m.arity,
+                                                None if off is None else off.ctypes.data, nlay, self.bs,
+                                                C.byref(h)), "fdb_mat_create_blocked")
         self.handle = h
         self.dat_version = 0
         nnz = C.c_longlong()
@@ -472,6 +481,7 @@ class Mat:
     def __call__(self, access, path, lgmaps=None):
         rmap, cmap = path
         a = LegacyArg(self, access, rmap)
+        a.cmap = cmap
         a.lgmaps = lgmaps
         return a
 
@@ -484,16 +494,23 @@ class Mat:
         per GPU, owner-computes across GPUs); just drain the stream."""
         _lib.check(_lib.lib().fdb_synchronize())
 
-    def set_local_diagonal_entries(self, rows, diag_val=1.0):
+    def set_local_diagonal_entries(self, rows, diag_val=1.0, idx=None):
+        """``rows`` are node rows; ``idx`` selects one component of a blocked
+        matrix, default every component (pyop2/types/mat.py:897-937)."""
         rows = np.ascontiguousarray(rows, dtype=IntType)
-        _lib.check(_lib.lib().fdb_mat_set_diagonal(self.handle, rows.ctypes.data, len(rows),
-                                                   float(diag_val)), "fdb_mat_set_diagonal")
+        if self.bs == 1:
+            _lib.check(_lib.lib().fdb_mat_set_diagonal(self.handle, rows.ctypes.data, len(rows),
+                                                       float(diag_val)), "fdb_mat_set_diagonal")
+        else:
+            _lib.check(_lib.lib().fdb_mat_set_diagonal_blocked(
+                self.handle, rows.ctypes.data, len(rows), float(diag_val), -1 if idx is None else int(idx)),
+                "fdb_mat_set_diagonal_blocked")
         self.dat_version += 1
 
     def csr(self):
         rowptr = np.empty(self.nrows + 1, dtype=np.int64)
         colidx = np.empty(self.nnz, dtype=IntType)
-        vals = np.empty(self.nnz, dtype=ScalarType)
+        vals = np.empty(self.nnz * self.bs * self.bs, dtype=ScalarType)
         _lib.check(_lib.lib().fdb_mat_get_csr(self.handle, rowptr.ctypes.data, colidx.ctypes.data,
                                               vals.ctypes.data), "fdb_mat_get_csr")
         return rowptr, colidx, vals
@@ -502,9 +519,18 @@ class Mat:
     def values(self):
         """Dense copy (small matrices / tests), as ``Mat.values`` in PyOP2."""
         rowptr, colidx, vals = self.csr()
-        A = np.zeros((self.nrows, self.nrows))
+        bs = self.bs
+        if bs == 1:
+            A = np.zeros((self.nrows, self.nrows))
+            for r in range(self.nrows):
+                A[r, colidx[rowptr[r]:rowptr[r + 1]]] = vals[rowptr[r]:rowptr[r + 1]]
+            return A
+        A = np.zeros((self.nrows * bs, self.nrows * bs))
+        blocks = vals.reshape(-1, bs, bs)
         for r in range(self.nrows):
-            A[r, colidx[rowptr[r]:rowptr[r + 1]]] = vals[rowptr[r]:rowptr[r + 1]]
+            for k in range(rowptr[r], rowptr[r + 1]):
+                c = colidx[k]
+                A[r * bs:(r + 1) * bs, c * bs:(c + 1) * bs] = blocks[k]
         return A
 
     def mult(self, x: "Dat", y: "Dat"):
@@ -574,6 +600,15 @@ class Kernel:
     accesses: tuple = (INC, READ, READ)
     # tabulation: a fiat_lite.Interval1D, or None for the default GLL/Gauss pair
     element: object = field(default=None, compare=False, hash=False)
+
+    def __new__(cls, *args, **kwargs):
+        # ``op2.Kernel(code, name)`` with C source (pyop2/local_kernel.py:33-43) builds the
+        # generic local kernel; form descriptors name the hand-written fast paths
+        src = args[0] if args else kwargs.get("code")
+        if isinstance(src, str) and ("(" in src or "code" in kwargs):
+            from .codegen import CStringKernel
+            return CStringKernel(*args, **kwargs)
+        return super().__new__(cls)
 
     def __post_init__(self):
         if self.form == "dg_advection":
@@ -867,6 +902,9 @@ class Parloop:
 def par_loop(kernel: Kernel, iterset: Set, *args, location="device", scatter="atomic"):
     """``op2.par_loop(kernel, iterset, dat(op2.INC, map), ...)``
     (pyop2/parloop.py:705-762)."""
+    from . import codegen
+    if isinstance(kernel, codegen.CStringKernel):
+        return codegen.par_loop(kernel, iterset, *args)
     maps = []
     for a in args:
         if a.map is not None and a.map not in maps:
@@ -876,3 +914,11 @@ def par_loop(kernel: Kernel, iterset: Set, *args, location="device", scatter="at
                       scatter=scatter)
     Parloop(gk, iterset, args, location=location)()
     return gk
+
+
+def __getattr__(name):
+    # lazily re-exported from codegen (which imports this module)
+    if name in ("PermutedMap", "CStringKernel"):
+        from . import codegen
+        return getattr(codegen, name)
+    raise AttributeError(name)

@@ -190,6 +190,83 @@ typedef struct fdb_call_args {
  * stream in device mode; host mode returns after the writeback. */
 int fdb_kernel_call(fdb_kernel_t k, const fdb_call_args *a);
 
+/* ------------------------------------------- generic wrapper builder (A3-A6)
+ * Replaces pyop2/codegen/builder.py WrapperBuilder (:702-1008) + rep2loopy + the
+ * host C compiler (pyop2/compilation.py:424-455) for ARBITRARY local kernels:
+ * the local kernel arrives as C source (what CStringLocalKernel carries,
+ * pyop2/local_kernel.py:186-207, and what TSFC/loopy emit), the engine generates
+ * the sm_100a global kernel around it -- one thread per (iteration-set entry,
+ * layer): pack through the maps, call the local kernel, unpack with the access
+ * descriptor's semantics -- and compiles it at run time with NVRTC.  The
+ * hand-written kernels behind fdb_kernel_create stay the fast path for the forms
+ * they cover; this is the general one.  Round-1 status: generated code is
+ * verified on the CPU (NVRTC compile for sm_100a + a host re-compilation of the
+ * same generated body against the reference's golden arrays); its first run on a
+ * GPU is scheduled for round 2.
+ *
+ * Packing semantics (pyop2/codegen/builder.py:322-429, 215-300, 520-625):
+ *   Dat through a Map  t[f][i][c] = dat[(map[n][perm[i]] + offset[i]*(layer-bottom+f))*cdim + c]
+ *                      READ/RW/MIN/MAX packs read the Dat, INC/WRITE packs start at zero;
+ *                      unpack: INC += (atomic), MIN/MAX (atomic), WRITE/RW plain store
+ *   Dat direct         the kernel gets &dat[n*cdim]
+ *   Global             READ: pointer to the values; INC/MIN/MAX: privatised per
+ *                      thread, combined with warp shuffles + one atomic per warp
+ *   Mat                zeroed local tensor (nr*rdim, nc*cdim) row-major, added into
+ *                      the CSR through the (masked) lgmaps, ADD_VALUES / INSERT_VALUES
+ * `f` has extent 2 for interior-horizontal-facet packs (both cells of a facet). */
+enum fdb_access { FDB_READ = 1, FDB_WRITE = 2, FDB_RW = 3, FDB_INC = 4, FDB_MIN = 5, FDB_MAX = 6 };
+enum fdb_arg_kind { FDB_ARG_DAT = 1, FDB_ARG_GLOBAL = 2, FDB_ARG_MAT = 3 };
+enum fdb_dtype { FDB_F64 = 1, FDB_F32 = 2, FDB_I32 = 3, FDB_U32 = 4, FDB_I64 = 5 };
+enum fdb_region {               /* pyop2 iteration regions, builder.py:779-800 */
+    FDB_REGION_ALL = 0, FDB_REGION_ON_BOTTOM = 1, FDB_REGION_ON_TOP = 2,
+    FDB_REGION_ON_INTERIOR_FACETS = 3
+};
+
+#define FDB_WRAP_MAX_ARGS 16
+#define FDB_WRAP_MAX_MAPS 8
+#define FDB_WRAP_MAX_MATS 4
+
+typedef struct fdb_wrapper_arg {
+    int32_t kind;               /* enum fdb_arg_kind                                         */
+    int32_t access;             /* enum fdb_access                                           */
+    int32_t dtype;              /* enum fdb_dtype (Mat: FDB_F64)                             */
+    int32_t dim;                /* Dat: values per node; Global: entries; Mat: row block size */
+    int32_t dim2;               /* Mat: column block size                                    */
+    int32_t map;                /* Dat: slot in the call's map list, -1 = direct; Mat: row map */
+    int32_t map2;               /* Mat: column map slot                                      */
+    int32_t arity, arity2;      /* arity of map / map2                                       */
+    const fdb_int *offset;      /* extruded: `arity` layer offsets of map (copied), else NULL */
+    const fdb_int *offset2;     /* Mat column map                                            */
+    const fdb_int *permutation; /* PermutedMap (pyop2/types/map.py:232-290): `arity` entries or NULL */
+    int32_t interior_horizontal;/* 1: pack layer and layer+1                                  */
+} fdb_wrapper_arg;
+
+typedef struct fdb_wrapper_desc {
+    const char *kernel_source;  /* C source of the local kernel; #include lines are ignored,
+                                   PetscScalar/PetscInt/intN_t/restrict are predefined        */
+    const char *kernel_name;    /* the wrapper is called wrap_<kernel_name>
+                                   (pyop2/global_kernel.py:344-346)                           */
+    int32_t nargs;              /* local-kernel argument order                                */
+    const fdb_wrapper_arg *args;
+    int32_t extruded;           /* iterate layers (constant layers only)                     */
+    int32_t subset;             /* n = subset[n]                                             */
+    int32_t iteration_region;   /* enum fdb_region                                           */
+} fdb_wrapper_desc;
+
+/* The generated CUDA source (no GPU needed).  Writes at most `cap` bytes incl.
+ * the terminator and always reports the full length in *needed. */
+int fdb_wrapper_source(const fdb_wrapper_desc *d, char *buf, size_t cap, size_t *needed);
+/* Generate + NVRTC-compile for sm_100a into a cubin image (no GPU needed: this
+ * is the ahead-of-time / disk-cache path, pyop2/compilation.py:424-455).  The
+ * NVRTC log is available from fdb_last_error() on failure. */
+int fdb_wrapper_compile(const fdb_wrapper_desc *d, void *cubin, size_t cap, size_t *needed);
+/* Generate, compile and load; the handle is called with fdb_kernel_call using
+ * the same arglist convention: args[] = one pointer per local-kernel argument
+ * (Dat: data; Global: HOST pointer to its values, always; Mat: fdb_mat_t),
+ * maps[] = the distinct maps in slot order.  Host mode uploads every Dat
+ * through the mirror cache and writes every non-READ Dat back. */
+int fdb_wrapper_create(const fdb_wrapper_desc *d, fdb_kernel_t *out);
+
 /* --------------------------------------------------------------- matrices
  * Device CSR replacing op2.Sparsity + op2.Mat over PETSc AIJ
  * (pyop2/types/mat.py:27-292, 607-985; pyop2/sparsity.pyx:106-389).
@@ -205,12 +282,22 @@ int fdb_kernel_call(fdb_kernel_t k, const fdb_call_args *a);
 typedef struct fdb_mat_s *fdb_mat_t;
 int fdb_mat_create(fdb_int nrows, const fdb_int *map_host, fdb_int ncolumns, int arity,
                    const fdb_int *offset_host, int nlayers, fdb_mat_t *out);
+/* Blocked variant for vector-valued spaces (op2.Mat over a DataSet with cdim > 1, PETSc
+ * BAIJ: pyop2/types/mat.py:741-804): same NODE pattern, every stored entry is a bs x bs
+ * block (row-major), lgmaps are dof-level (nrows*bs entries, so that a Dirichlet condition
+ * on one component can be expressed), get_csr returns node-level rowptr/colidx and
+ * nnz*bs*bs values.  fdb_mat_create(...) == fdb_mat_create_blocked(..., bs = 1, ...). */
+int fdb_mat_create_blocked(fdb_int nrows, const fdb_int *map_host, fdb_int ncolumns, int arity,
+                           const fdb_int *offset_host, int nlayers, int bs, fdb_mat_t *out);
 int fdb_mat_destroy(fdb_mat_t m);
 int fdb_mat_nnz(fdb_mat_t m, long long *nnz, fdb_int *nrows);
 int fdb_mat_zero(fdb_mat_t m);
 int fdb_mat_set_lgmaps(fdb_mat_t m, const fdb_int *row_lgmap_host, const fdb_int *col_lgmap_host);
 /* Mat.set_local_diagonal_entries (pyop2/types/mat.py:897-937) */
 int fdb_mat_set_diagonal(fdb_mat_t m, const fdb_int *rows_host, fdb_int n, double value);
+/* rows are NODE rows; idx = component to set, -1 = every component (the `idx` argument of
+ * set_local_diagonal_entries, pyop2/types/mat.py:897-937) */
+int fdb_mat_set_diagonal_blocked(fdb_mat_t m, const fdb_int *rows_host, fdb_int n, double value, int idx);
 /* y = A x on device pointers (cross-check of assembled vs matrix-free action) */
 int fdb_mat_mult(fdb_mat_t m, const double *x, double *y);
 /* copy the CSR arrays to the host (any pointer may be NULL); rowptr is int64 */

@@ -94,8 +94,10 @@ def test_sparsity_restrictions():
     m = op2.Map(cells, nodes, 3, [0, 1, 3, 2, 3, 1])
     s = op2.Sparsity((nodes, nodes), [(m, m, None)])
     assert s.shape == (4, 4)
-    with pytest.raises(NotImplementedError):
-        op2.Sparsity((op2.DataSet(nodes, 2), op2.DataSet(nodes, 2)), [(m, m, None)])
+    sb = op2.Sparsity((op2.DataSet(nodes, 2), op2.DataSet(nodes, 2)), [(m, m, None)])
+    assert sb.bs == 2 and sb.shape == (4, 4)                    # node-level pattern, 2x2 blocks
+    with pytest.raises(NotImplementedError):                    # rectangular blocks
+        op2.Sparsity((op2.DataSet(nodes, 2), op2.DataSet(nodes, 3)), [(m, m, None)])
     m2 = op2.Map(cells, nodes, 3, [0, 1, 3, 2, 3, 1])
     with pytest.raises(NotImplementedError):
         op2.Sparsity((nodes, nodes), [(m, m2, None)])
