@@ -81,6 +81,55 @@ def interpolate_q1(V: "FunctionSpace", source: op2.Dat, target: op2.Dat = None):
     return target
 
 
+def interpolation_kernel(degree, expressions, name="interpolate_expr"):
+    """C source of the dual-evaluation kernel of ``Function(V).interpolate(expr(x))`` on
+    Q_p (x) P_p with GLL nodes (point evaluation: firedrake/interpolation.py:977-1171
+    builds it with tsfc.compile_expression_dual_evaluation, tsfc/driver.py:225-386).
+    ``expressions``: one C expression per component in ``x[0], x[1], x[2]`` (the physical
+    position of the node, the trilinear image of its reference position) -- the syntax of
+    the reference's former ``Expression("sin(x[0])")``.  Arguments: out (WRITE), coords."""
+    from .fiat_lite import interval_element
+    from .codegen import CStringKernel
+    exprs = [expressions] if isinstance(expressions, str) else list(expressions)
+    n = degree + 1
+    xi = ", ".join(repr(float(v)) for v in interval_element(degree).nodes)
+    body = "\n".join(f"        out[i * {len(exprs)} + {c}] = {e};" for c, e in enumerate(exprs))
+    code = f"""
+static void {name}(double *out, const double *X)
+{{
+    const double xi[{n}] = {{{xi}}};                 /* 1-D node positions, dof numbering */
+    for (int ax = 0; ax < {n}; ++ax)
+    for (int ay = 0; ay < {n}; ++ay)
+    for (int az = 0; az < {n}; ++az) {{
+        const int i = (ax * {n} + ay) * {n} + az;
+        double x[3] = {{0.0, 0.0, 0.0}};
+        for (int v = 0; v < 8; ++v) {{
+            const double w = ((v & 4) ? xi[ax] : 1.0 - xi[ax]) * ((v & 2) ? xi[ay] : 1.0 - xi[ay])
+                           * ((v & 1) ? xi[az] : 1.0 - xi[az]);
+            for (int c = 0; c < 3; ++c) x[c] += w * X[v * 3 + c];
+        }}
+{body}
+    }}
+}}
+"""
+    return CStringKernel(code, name)
+
+
+def interpolate(V: "FunctionSpace", expressions, target: op2.Dat = None):
+    """``Function(V).interpolate(expr)`` for C expressions of the physical coordinates
+    (SURVEY.md section 8f row f2), run as a WRITE parloop through the engine's generic
+    wrapper builder.  Nodes shared by several cells are written by each of them with the
+    same value, as in the reference's sequential loop."""
+    exprs = [expressions] if isinstance(expressions, str) else list(expressions)
+    if len(exprs) != V.cdim:
+        raise ValueError(f"need {V.cdim} expressions for this space, got {len(exprs)}")
+    if target is None:
+        target = V.dat()
+    k = interpolation_kernel(V.degree, exprs)
+    op2.par_loop(k, V.cell_set, target(op2.WRITE, V.cell_node_map), V.coordinates(op2.READ, V.coord_map))
+    return target
+
+
 class DirichletBC:
     """``DirichletBC(V, g, sub_domain)``: node subset + value
     (firedrake/bcs.py:260-457)."""
@@ -182,14 +231,21 @@ def assemble(form: Form, u=None, tensor=None, bcs=(), mat_type="aij"):
     if mat_type == "matfree":
         return ImplicitMatrixContext(form, bcs)
     if tensor is None:
-        tensor = op2.Mat(op2.Sparsity((V.node_set, V.node_set),
-                                      [(V.cell_node_map, V.cell_node_map, None)]))
+        dsets = (V.node_set, V.node_set) if V.cdim == 1 else (V.dof_dset, V.dof_dset)
+        tensor = op2.Mat(op2.Sparsity(dsets, [(V.cell_node_map, V.cell_node_map, None)]))
     tensor.zero()
     lg = None
-    if bcs:
+    if bcs and V.cdim == 1:
         lgm = np.arange(V.node_count, dtype=np.int32)
         for bc in bcs:
             lgm[bc.nodes] = -1
+        lg = (lgm, lgm)
+    elif bcs:
+        # vector-valued space: dof-level lgmap, every component of a constrained node masked
+        lgm = np.arange(V.node_count * V.cdim, dtype=np.int32).reshape(-1, V.cdim)
+        for bc in bcs:
+            lgm[bc.nodes, :] = -1
+        lgm = np.ascontiguousarray(lgm.ravel())
         lg = (lgm, lgm)
     op2.par_loop(form.kernel(2), V.cell_set,
                  tensor(op2.INC, (V.cell_node_map, V.cell_node_map), lgmaps=lg),
@@ -223,6 +279,12 @@ class ImplicitMatrixContext:
         for bc in self.bcs:
             bc.set(D, 1.0)
         return D
+
+    def multTranspose(self, X: op2.Dat, Y: op2.Dat):
+        """``Y = A^T X`` (matrix_free/operators.py:245-330: the action of ``adjoint(a)`` with the
+        row and column conditions exchanged).  Every form of the supported family is
+        symmetric and row/column DirichletBCs coincide here (no EquationBC), so A^T = A."""
+        return self.mult(X, Y)
 
     def mult(self, X: op2.Dat, Y: op2.Dat):
         from . import _lib

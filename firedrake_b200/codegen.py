@@ -87,19 +87,25 @@ class WrapperSpec:
     """The compile-time description of one generic parloop."""
 
     def __init__(self, kernel: CStringKernel, args, *, extruded=False, subset=False,
-                 iteration_region="ALL"):
+                 iteration_region="ALL", interior_horizontal=None):
         from . import op2
+        if interior_horizontal is None:
+            # every indirect argument of an interior-horizontal-facet loop packs the cells
+            # below and above the facet (pyop2/codegen/builder.py:840-844)
+            interior_horizontal = iteration_region == "ON_INTERIOR_FACETS"
         self.kernel = kernel
         self.maps = distinct_maps(args)
         if len(args) > _lib.WRAP_MAX_ARGS or len(self.maps) > _lib.WRAP_MAX_MAPS:
             raise ValueError("too many arguments / maps for the generic wrapper")
         self._keep = []
         arr = (_lib.WrapperArg * len(args))()
-        key = [kernel.code, kernel.name, bool(extruded), bool(subset), iteration_region]
+        key = [kernel.code, kernel.name, bool(extruded), bool(subset), iteration_region,
+               bool(interior_horizontal)]
         for i, a in enumerate(args):
             w = arr[i]
             w.access = int(a.access)
             w.map = w.map2 = -1
+            w.interior_horizontal = int(bool(interior_horizontal) and getattr(a, "map", None) is not None)
             data = a.data
             if isinstance(data, op2.Mat):
                 rmap, cmap = a.map, a.cmap

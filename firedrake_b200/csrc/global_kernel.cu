@@ -1,8 +1,10 @@
 // "Compile" and call of a global kernel: the replacement for
 // pyop2.global_kernel.compile_global_kernel + GlobalKernel.__call__
-// (reference pyop2/global_kernel.py:327-335, 426-456).  Nothing is JIT-compiled:
-// creation validates the descriptor against the set of hand-written sm_100a
-// kernels and precomputes the tables they need.
+// (reference pyop2/global_kernel.py:327-335, 426-456).  fdb_kernel_create compiles
+// nothing: it validates the descriptor against the set of hand-written sm_100a
+// kernels and precomputes the tables they need.  Handles made by
+// fdb_wrapper_create (wrapper_jit.cu: NVRTC wrapper around an arbitrary local
+// kernel) are dispatched from fdb_kernel_call as well.
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>

@@ -15,13 +15,24 @@ Usage (where Firedrake exists)::
     hook.uninstall()
 
 What it does: replaces ``pyop2.global_kernel.compile_global_kernel``
-(reference pyop2/global_kernel.py:426-456).  For global kernels whose local
-kernel was generated from one of the supported forms it returns a callable with
-the JIT-compiled wrapper's signature ``fn(start, end, *arglist)`` that forwards
-to ``fdb_kernel_call`` in host-pointer mode; everything else falls through to
-the stock C path.  A form is recognised by comparing its UFL signature with
-template forms built on the same function space -- the reference keys its own
-kernel cache on ``form.signature()`` (firedrake/tsfc_interface.py:55-62).
+(reference pyop2/global_kernel.py:426-456) with a three-way choice:
+
+1. FAST PATH -- global kernels whose local kernel was generated from a
+   registered form of the supported set get a callable with the JIT-compiled
+   wrapper's signature ``fn(start, end, *arglist)`` that forwards to the
+   hand-written sm_100a kernels (``fdb_kernel_create`` descriptor).  A form is
+   recognised by its UFL signature -- the reference keys its own kernel cache on
+   ``form.signature()`` (firedrake/tsfc_interface.py:55-62).
+2. GENERIC PATH -- any other global kernel whose arguments are Dats and Globals:
+   the local kernel's C source (a ``CStringLocalKernel``'s string, or
+   ``loopy.generate_code_v2`` of a ``LoopyLocalKernel``, which is what PyOP2
+   itself inlines into its wrapper) is handed to the engine's NVRTC wrapper
+   builder (``fdb_wrapper_create``), described by the same ``*KernelArg``
+   objects PyOP2's ``WrapperBuilder`` consumes (pyop2/global_kernel.py:26-170,
+   pyop2/codegen/builder.py:840-916).
+3. Everything else (PETSc ``Mat`` arguments -- the engine assembles into its own
+   CSR, not into a PETSc handle --, MixedDats, periodic extrusion, variable
+   layers, ``pass_layer_arg``) falls through to the stock C path.
 """
 from __future__ import annotations
 
@@ -87,6 +98,88 @@ def _descriptor_for(global_kernel):
     return d, keep
 
 
+_NP_DTYPES = {"float64": _lib.F64, "float32": _lib.F32, "int32": _lib.I32, "uint32": _lib.U32,
+              "int64": _lib.I64}
+
+
+def _local_kernel_source(lk):
+    """C source of a pyop2 LocalKernel (pyop2/local_kernel.py:186-260)."""
+    if isinstance(lk.code, str):
+        return lk.code
+    import loopy as lp
+    return lp.generate_code_v2(lk.code).device_code()
+
+
+def _generic_for(global_kernel):
+    """(WrapperDesc, keepalive) for a pyop2 GlobalKernel made of Dat / Global arguments,
+    else None.  Mirrors WrapperBuilder.add_argument (pyop2/codegen/builder.py:840-916)."""
+    import pyop2.global_kernel as gk
+    from pyop2.types import IterationRegion
+    g = global_kernel
+    if g._extruded and (not g._constant_layers or g._extruded_periodic):
+        return None
+    if g._pass_layer_arg:
+        return None
+    region = {None: _lib.REGION_ALL, IterationRegion.ALL: _lib.REGION_ALL,
+              IterationRegion.BOTTOM: _lib.REGION_ON_BOTTOM, IterationRegion.TOP: _lib.REGION_ON_TOP,
+              IterationRegion.INTERIOR_FACETS: _lib.REGION_ON_INTERIOR_FACETS}[g._iteration_region]
+    horizontal = region == _lib.REGION_ON_INTERIOR_FACETS
+    lk = g.local_kernel
+    slots, keep = [], []          # distinct MapKernelArgs by identity, first-use order
+
+    def slot(m):
+        base = m.base_map if isinstance(m, gk.PermutedMapKernelArg) else m
+        for i, b in enumerate(slots):
+            if b is base:
+                return i
+        slots.append(base)
+        return len(slots) - 1
+
+    def ints(v):
+        if v is None:
+            return None
+        a = np.ascontiguousarray(v, dtype=np.int32)
+        keep.append(a)
+        return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+    arr = (_lib.WrapperArg * len(g.arguments))()
+    for w, larg, garg in zip(arr, lk.arguments, g.arguments):
+        w.access = int(larg.access.value)
+        w.dtype = _NP_DTYPES.get(np.dtype(larg.dtype).name, 0)
+        w.map = w.map2 = -1
+        if w.dtype == 0:
+            return None
+        if isinstance(garg, gk.GlobalKernelArg) and not garg.double:
+            w.kind, w.dim = _lib.ARG_GLOBAL, int(np.prod(garg.dim, dtype=int))
+        elif isinstance(garg, gk.DatKernelArg) and garg.index is None:
+            w.kind, w.dim = _lib.ARG_DAT, int(np.prod(garg.dim, dtype=int))
+            m = garg.map_
+            if isinstance(m, gk.ComposedMapKernelArg):
+                return None
+            if m is not None:
+                base = m.base_map if isinstance(m, gk.PermutedMapKernelArg) else m
+                if base.offset_quotient is not None:
+                    return None
+                w.map, w.arity = slot(m), base.arity
+                perm = m.permutation if isinstance(m, gk.PermutedMapKernelArg) else None
+                w.permutation = ints(perm)
+                off = base.offset
+                if off is not None and perm is not None:
+                    off = np.asarray(off)[np.asarray(perm)]
+                w.offset = ints(off)
+                w.interior_horizontal = int(horizontal)
+        else:
+            return None               # Mat / MixedDat / passthrough: stock path
+    d = _lib.WrapperDesc()
+    src = _local_kernel_source(lk).encode()
+    name = lk.name.encode()
+    keep += [arr, src, name]
+    d.kernel_source, d.kernel_name = src, name
+    d.nargs, d.args = len(g.arguments), arr
+    d.extruded, d.subset, d.iteration_region = int(g._extruded), int(g._subset), region
+    return d, keep
+
+
 def _make_wrapper(handle, global_kernel):
     L = _lib.lib()
     extruded = global_kernel._extruded
@@ -101,7 +194,7 @@ def _make_wrapper(handle, global_kernel):
             layers, pos = arglist[pos], pos + 1
         if subset:
             subset_ptr, pos = arglist[pos], pos + 1
-        nargs = 3 if global_kernel.local_kernel.num_args == 3 else 2
+        nargs = len(global_kernel.arguments)
         data = arglist[pos:pos + nargs]
         maps = arglist[pos + nargs:]
         ca = _lib.CallArgs()
@@ -133,14 +226,19 @@ def install():
 
     def compile_global_kernel(kernel, comm):
         found = _descriptor_for(kernel)
-        if found is None:
-            return _original(kernel, comm)
-        desc, keep = found
-        L = _lib.init()
         h = C.c_void_p()
-        _lib.check(L.fdb_kernel_create(C.byref(desc), C.byref(h)), "fdb_kernel_create")
-        del keep
-        return _make_wrapper(h, kernel)
+        if found is not None:                      # 1. hand-written fast path
+            desc, keep = found
+            _lib.check(_lib.init().fdb_kernel_create(C.byref(desc), C.byref(h)), "fdb_kernel_create")
+            del keep
+            return _make_wrapper(h, kernel)
+        found = _generic_for(kernel)
+        if found is not None:                      # 2. NVRTC wrapper around the local kernel's C
+            desc, keep = found
+            _lib.check(_lib.init().fdb_wrapper_create(C.byref(desc), C.byref(h)), "fdb_wrapper_create")
+            del keep
+            return _make_wrapper(h, kernel)
+        return _original(kernel, comm)             # 3. stock C path
 
     gk.compile_global_kernel = compile_global_kernel
 

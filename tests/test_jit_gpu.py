@@ -1,0 +1,215 @@
+"""GPU run of the generic wrapper builder and of the blocked matrices.
+
+WRITTEN WITHOUT GPU ACCESS (round 1's GPU budget was spent): the generated code
+behind these tests is verified on the CPU (tests/test_codegen.py) but has not
+run on a device yet, so the module is skipped unless FDB_RUN_UNVALIDATED=1.
+First action of the next round: run it, fix, remove the gate.
+
+Each case mirrors a CPU case of tests/test_codegen.py, now through
+``op2.par_loop(op2.Kernel(code, name), ...)`` -> fdb_wrapper_create (NVRTC) ->
+fdb_kernel_call on device-resident Dats.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from firedrake_b200 import op2
+from firedrake_b200.codegen import CStringKernel, PermutedMap
+from firedrake_b200.fiat_lite import interval_element
+from firedrake_b200.utility_meshes import ExtrudedHexMesh
+
+import test_codegen as tc
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("FDB_RUN_UNVALIDATED") != "1",
+                                 reason="generic wrapper / blocked matrices: CPU-verified only, first GPU "
+                                        "validation pending (set FDB_RUN_UNVALIDATED=1)")]
+
+GOLD = tc.GOLD
+
+
+def test_golden_mass_and_rhs(engine):
+    elems, nodes, m, X, f = tc._golden_mesh()
+    mass, rhs = tc._p1_kernels()
+    A = op2.Mat(op2.Sparsity((nodes, nodes), [(m, m, None)]))
+    A.zero()
+    op2.par_loop(mass, elems, A(op2.INC, (m, m)), X(op2.READ, m))
+    A.assemble()
+    assert np.abs(A.values - np.array(GOLD["expected_matrix"])).max() < GOLD["expected_matrix_eps"]
+    b = op2.Dat(nodes)
+    op2.par_loop(rhs, elems, b(op2.INC, m), X(op2.READ, m), f(op2.READ, m))
+    assert np.abs(b.data_ro - np.array(GOLD["expected_rhs"])).max() < GOLD["expected_rhs_eps"]
+    # the same golden arrays through the hand-written P1 kernels agree with the generated path
+    y = op2.Dat(nodes)
+    A.mult(f, y)
+    assert np.allclose(y.data_ro, b.data_ro, rtol=0, atol=1e-14)
+
+
+def test_blocked_matrix_generic_path(engine):
+    elems, nodes, m, X, _ = tc._golden_mesh()
+    mass2, _ = tc._p1_kernels(cdim=2)
+    d2 = op2.DataSet(nodes, 2)
+    A = op2.Mat(op2.Sparsity((d2, d2), [(m, m, None)]))
+    A.zero()
+    lg = np.arange(8, dtype=np.int32)
+    lg[7] = -1
+    op2.par_loop(mass2, elems, A(op2.INC, (m, m), lgmaps=(lg, lg)), X(op2.READ, m))
+    A.set_local_diagonal_entries([3], 1.0, idx=1)
+    A.assemble()
+    M = np.kron(np.array(GOLD["expected_matrix"]), np.eye(2))
+    D = A.values
+    keep = [i for i in range(8) if i != 7]
+    assert np.abs(D[np.ix_(keep, keep)] - M[np.ix_(keep, keep)]).max() < 1e-5
+    assert D[7, 7] == 1.0 and np.all(D[7, :7] == 0) and np.all(D[:7, 7] == 0)
+    x = op2.Dat(d2, np.random.default_rng(0).standard_normal((4, 2)))
+    y = op2.Dat(d2)
+    A.mult(x, y)
+    assert np.allclose(y.data_ro.ravel(), D @ x.data_ro.ravel(), rtol=0, atol=1e-14)
+
+
+def test_access_modes(engine):
+    n = 100000                                 # many warps: atomics and warp reductions matter
+    it, ind, unit = op2.Set(n), op2.Set(n), op2.Set(1)
+    rng = np.random.default_rng(7)
+    i2i = op2.Map(it, ind, 1, rng.permutation(n))
+    i2u = op2.Map(it, unit, 1, np.zeros(n, dtype=np.int32))
+    x = op2.Dat(ind, np.arange(n), dtype=np.uint32)
+    op2.par_loop(op2.Kernel("static void wo(unsigned int *x) { *x = 42; }", "wo"), it, x(op2.WRITE, i2i))
+    assert (x.data_ro == 42).all()
+    x = op2.Dat(ind, np.arange(n), dtype=np.uint32)
+    op2.par_loop(op2.Kernel("static void rw(unsigned int *x) { (*x) = (*x) + 1; }", "rw"), it, x(op2.RW, i2i))
+    assert int(x.data_ro.sum(dtype=np.uint64)) == n * (n + 1) // 2
+    u = op2.Dat(unit, [0], dtype=np.uint32)
+    op2.par_loop(op2.Kernel("static void inc(unsigned int *x) { (*x) = (*x) + 1; }", "inc"), it, u(op2.INC, i2u))
+    assert u.data_ro[0] == n
+    v = op2.Dat(it, rng.standard_normal(n))
+    for acc, cmp, ref in ((op2.MIN, "<", v.data_ro.min()), (op2.MAX, ">", v.data_ro.max())):
+        t = op2.Dat(unit, [v.data_ro[0]])
+        k = op2.Kernel(f"static void mm(double *t, const double *v) {{ if (*v {cmp} *t) *t = *v; }}", "mm")
+        op2.par_loop(k, it, t(acc, i2u), v(op2.READ))
+        assert t.data_ro[0] == ref
+        g = op2.Global(1, v.data_ro[0])
+        k = op2.Kernel(f"static void gm(const double *v, double *g) {{ if (*v {cmp} *g) *g = *v; }}", "gm")
+        op2.par_loop(k, it, v(op2.READ), g(acc))
+        assert g.data_ro[0] == ref
+    g = op2.Global(1, 0.0)
+    op2.par_loop(op2.Kernel("static void gs(const double *v, double *g) { *g += *v; }", "gs"), it,
+                 v(op2.READ), g(op2.INC))
+    assert abs(g.data_ro[0] - v.data_ro.sum()) < 1e-9
+    gi = op2.Global(1, 0, np.int64)
+    w = op2.Dat(it, np.arange(n), dtype=np.int64)
+    op2.par_loop(op2.Kernel("static void gl(const long long *v, long long *g) { *g += *v; }", "gl"), it,
+                 w(op2.READ), gi(op2.INC))
+    assert gi.data_ro[0] == n * (n - 1) // 2
+
+
+def test_permuted_map_and_subset(engine):
+    fromset, toset = op2.Set(1), op2.Set(4)
+    d1 = op2.Dat(toset, [10, 11, 12, 13], dtype=np.int32)
+    d2 = op2.Dat(toset, dtype=np.int32)
+    m1 = op2.Map(fromset, toset, 4, [0, 2, 1, 3])
+    m2, m3 = PermutedMap(m1, [3, 2, 1, 0]), PermutedMap(m1, [0, 2, 3, 1])
+    k = op2.Kernel("void copy(int *to, const int * restrict from) { for (int i = 0; i < 4; i++) to[i] = from[i]; }",
+                   "copy")
+    op2.par_loop(k, fromset, d2(op2.WRITE, m2), d1(op2.READ, m3))
+    expect = np.empty(4, dtype=np.int32)
+    expect[m1.values_with_halo[0][m2.permutation]] = d1.data_ro[m1.values_with_halo[0][m3.permutation]]
+    assert (d2.data_ro == expect).all()
+    it = op2.Set(5000)
+    x = op2.Dat(it, dtype=np.int32)
+    sub = op2.Subset(it, np.arange(3, 5000, 7))
+    op2.par_loop(op2.Kernel("static void one(int *x) { *x = 1; }", "one"), sub, x(op2.WRITE))
+    assert x.data_ro.sum() == len(sub.indices) and (x.data_ro[sub.indices] == 1).all()
+
+
+def test_generic_extruded_action_equals_fast_path_and_oracle(engine, oracle):
+    mesh = ExtrudedHexMesh(7, 6, 9, warp=0.05, permute_seed=0)
+    V = mesh.function_space(1)
+    cells = op2.ExtrudedSet(op2.Set(mesh.num_base_cells), mesh.layers)
+    nodes, vnodes = op2.Set(V.node_count), op2.Set(mesh.coord_space.node_count)
+    m0 = op2.Map(cells, nodes, V.arity, V.cell_node_map, offset=V.offset)
+    m1 = op2.Map(cells, vnodes, 8, mesh.coord_map, offset=mesh.coord_offset)
+    X = op2.Dat(op2.DataSet(vnodes, 3), mesh.coordinates)
+    x = op2.Dat(nodes, np.random.default_rng(3).standard_normal(V.node_count))
+    yg, yf = op2.Dat(nodes), op2.Dat(nodes)
+    op2.par_loop(op2.Kernel(tc.Q1_POISSON, "q1_poisson"), cells, yg(op2.INC, m0), X(op2.READ, m1), x(op2.READ, m0))
+    op2.par_loop(op2.Kernel("helmholtz", degree=1), cells, yf(op2.INC, m0), X(op2.READ, m1), x(op2.READ, m0))
+    yo = np.zeros(V.node_count)
+    oracle.action_extruded(interval_element(1), 0, mesh.num_base_cells, [0, mesh.layers], yo, mesh.coordinates,
+                           x.data_ro.copy(), V.cell_node_map, V.offset, mesh.coord_map, mesh.coord_offset)
+    scale = np.abs(yo).max()
+    assert np.abs(yg.data_ro - yo).max() < 1e-12 * scale
+    assert np.abs(yf.data_ro - yo).max() < 1e-12 * scale
+
+
+@pytest.mark.parametrize("p,cdim", [(2, 3), (1, 2)])
+def test_vector_space_matrix_fast_path(engine, oracle, p, cdim):
+    """assemble(a) on a VectorFunctionSpace (config 4's explicit matrix): blocked CSR ==
+    kron(scalar oracle matrix, I), with node Dirichlet conditions, and SpMV == matrix-free."""
+    from firedrake_b200.assemble import DirichletBC, FunctionSpace, assemble, helmholtz
+    import test_matrix_gpu as tm
+    mesh = ExtrudedHexMesh(3, 3, 4, warp=0.05, permute_seed=2)
+    V = FunctionSpace(mesh, p, cdim=cdim)
+    bcs = [DirichletBC(V, 0.0, "bottom")]
+    A = assemble(helmholtz(V), bcs=bcs)
+    assert A.bs == cdim
+    lg = np.arange(V.node_count, dtype=np.int32)
+    lg[bcs[0].nodes] = -1
+    rowptr, colidx, vo = tm.oracle_matrix(oracle, mesh, V.V, p, 1.0, 1.0, lg)
+    r2, c2, vals = A.csr()
+    assert np.array_equal(rowptr, r2) and np.array_equal(colidx, c2)
+    blocks = vals.reshape(-1, cdim, cdim)
+    diag_rows = np.isin(np.repeat(np.arange(V.node_count), np.diff(rowptr)), bcs[0].nodes) & \
+        (colidx == np.repeat(np.arange(V.node_count), np.diff(rowptr)))
+    expect = vo[:, None, None] * np.eye(cdim)[None]
+    expect[diag_rows] = np.eye(cdim)
+    assert np.abs(blocks - expect).max() < 1e-12 * np.abs(vo).max()
+    x = V.dat(np.random.default_rng(1).standard_normal((V.node_count, cdim)))
+    y1, y2 = V.dat(), V.dat()
+    A.mult(x, y1)
+    assemble(helmholtz(V), bcs=bcs, mat_type="matfree").mult(x, y2)
+    assert np.abs(y1.data_ro - y2.data_ro).max() < 1e-11 * np.abs(y1.data_ro).max()
+
+
+def test_cg4_matrix_instantiation(engine, oracle):
+    """Degree-4 explicit matrix (new launch_matrix_n<5> instantiation)."""
+    import test_matrix_gpu as tm
+    mesh = ExtrudedHexMesh(2, 2, 3, warp=0.05, permute_seed=2)
+    V, cells, nodes, m0, m1, X = tm.setup(mesh, 4)
+    mat = op2.Mat(op2.Sparsity((nodes, nodes), [(m0, m0, None)]))
+    mat.zero()
+    op2.par_loop(op2.Kernel("helmholtz", degree=4, alpha=1.0, beta=1.0, rank=2), cells,
+                 mat(op2.INC, (m0, m0)), X(op2.READ, m1))
+    mat.assemble()
+    _, _, vals = mat.csr()
+    _, _, vo = tm.oracle_matrix(oracle, mesh, V, 4, 1.0, 1.0)
+    assert np.abs(vals - vo).max() < 1e-12 * np.abs(vo).max()
+
+
+def test_mult_transpose(engine):
+    from firedrake_b200.assemble import DirichletBC, FunctionSpace, assemble, poisson
+    mesh = ExtrudedHexMesh(3, 3, 4, warp=0.05)
+    V = FunctionSpace(mesh, 2)
+    bcs = [DirichletBC(V, 0.0, "top")]
+    ctx = assemble(poisson(V), bcs=bcs, mat_type="matfree")
+    A = assemble(poisson(V), bcs=bcs).values
+    x = V.dat(np.random.default_rng(5).standard_normal(V.node_count))
+    y = V.dat()
+    ctx.multTranspose(x, y)
+    assert np.abs(y.data_ro - A.T @ x.data_ro).max() < 1e-11 * np.abs(y.data_ro).max()
+
+
+def test_expression_interpolation(engine):
+    from firedrake_b200.assemble import FunctionSpace, interpolate
+    mesh = ExtrudedHexMesh(5, 4, 6, warp=0.05, permute_seed=1)
+    V = FunctionSpace(mesh, 3)
+    u = interpolate(V, "sin(M_PI * x[0]) * cos(2 * M_PI * x[1]) * (1 + x[2])")
+    P = V.V.dof_coordinates()
+    ref = np.sin(np.pi * P[:, 0]) * np.cos(2 * np.pi * P[:, 1]) * (1 + P[:, 2])
+    assert np.abs(u.data_ro - ref).max() < 1e-13
+    W = FunctionSpace(mesh, 2, cdim=3)
+    w = interpolate(W, ["x[1] * x[2]", "-x[0]", "exp(x[2])"])
+    P = W.V.dof_coordinates()
+    ref = np.stack([P[:, 1] * P[:, 2], -P[:, 0], np.exp(P[:, 2])], axis=1)
+    assert np.abs(w.data_ro - ref).max() < 1e-13
