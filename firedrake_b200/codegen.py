@@ -199,12 +199,16 @@ def _handle(spec: WrapperSpec):
     return h
 
 
-def par_loop(kernel: CStringKernel, iterset, *args, iteration_region="ALL"):
+def par_loop(kernel: CStringKernel, iterset, *args, iteration_region="ALL", location="device"):
     """``op2.par_loop(op2.Kernel(code, name), iterset, *args)`` for a C-string
-    kernel: device-resident Dats, one generated wrapper per distinct argument
-    description.  Follows pyop2/parloop.py:243-260 without the halo phases (generic
-    parloops run unpartitioned for now)."""
+    kernel, one generated wrapper per distinct argument description.
+    ``location="device"``: Dats stay resident on the GPU; ``"host"``: the drop-in
+    call with NumPy buffers (mirror cache keyed on ``dat_version``, every written
+    Dat copied back).  Follows pyop2/parloop.py:243-260 without the halo phases
+    (generic parloops run unpartitioned for now)."""
     from . import op2
+    if location == "host":
+        return _par_loop_host(kernel, iterset, args, iteration_region)
     base = iterset.superset if isinstance(iterset, op2.Subset) else iterset
     if kernel.accesses is not None and tuple(a.access for a in args) != tuple(kernel.accesses):
         raise ValueError("access descriptors do not match the kernel's")
@@ -264,6 +268,55 @@ def par_loop(kernel: CStringKernel, iterset, *args, iteration_region="ALL"):
             continue
         if isinstance(a.data, op2.Dat):
             a.data._device_written()
+            a.data.halo_valid = False
+        else:
+            a.data.dat_version += 1
+    return spec
+
+
+def _par_loop_host(kernel, iterset, args, iteration_region):
+    """The arglist of pyop2/parloop.py:203-212 with host pointers, sizes and versions."""
+    from . import op2
+    base = iterset.superset if isinstance(iterset, op2.Subset) else iterset
+    if any(isinstance(a.data, op2.Mat) for a in args):
+        raise NotImplementedError("host-pointer mode takes Dats and Globals (Mats live on the device)")
+    spec = WrapperSpec(kernel, args, extruded=base._extruded, subset=isinstance(iterset, op2.Subset),
+                       iteration_region=iteration_region)
+    h = _handle(spec)
+    for a in args:
+        if isinstance(a.data, op2.Dat):
+            a.data._sync_host()
+    ptrs = [a.data._data.ctypes.data for a in args]
+    nbytes = [a.data._data.nbytes for a in args]
+    vers = [a.data.dat_version for a in args]
+    maps = [m.values_with_halo for m in spec.maps]
+    layers = base.layers_array.ravel() if base._extruded else None
+    ca = _lib.CallArgs()
+    for start, end in (iterset.core_part, iterset.owned_part):
+        if end <= start:
+            continue
+        ca.start, ca.end = int(start), int(end)
+        if layers is not None:
+            ca.layers = layers.ctypes.data_as(C.POINTER(C.c_int32))
+        ca.subset = iterset.indices.ctypes.data if isinstance(iterset, op2.Subset) else None
+        ca.nargs, ca.args = len(ptrs), (C.c_void_p * len(ptrs))(*ptrs)
+        ca.arg_bytes = (C.c_size_t * len(ptrs))(*nbytes)
+        ca.arg_versions = (C.c_uint64 * len(ptrs))(*vers)
+        ca.nmaps = len(maps)
+        ca.maps = (C.c_void_p * max(len(maps), 1))(*[m.ctypes.data for m in maps])
+        ca.map_bytes = (C.c_size_t * max(len(maps), 1))(*[m.nbytes for m in maps])
+        ca.location, ca.writeback, ca.output_is_zero = _lib.LOC_HOST, 1, 0
+        _lib.check(_lib.lib().fdb_kernel_call(h, C.byref(ca)), "wrap_" + kernel.name)
+        # the engine recorded version+1 for every written mirror (pyop2/parloop.py:262-272)
+        for i, a in enumerate(args):
+            if a.access != op2.READ and isinstance(a.data, op2.Dat):
+                vers[i] += 1
+    for a in args:
+        if a.access == op2.READ:
+            continue
+        if isinstance(a.data, op2.Dat):
+            a.data.increment_dat_version()
+            a.data._host_valid, a.data._dev_valid, a.data._is_zero = True, False, False
             a.data.halo_valid = False
         else:
             a.data.dat_version += 1

@@ -213,3 +213,17 @@ def test_expression_interpolation(engine):
     P = W.V.dof_coordinates()
     ref = np.stack([P[:, 1] * P[:, 2], -P[:, 0], np.exp(P[:, 2])], axis=1)
     assert np.abs(w.data_ro - ref).max() < 1e-13
+
+
+def test_host_pointer_mode_generic(engine):
+    """fdb_kernel_call(FDB_LOC_HOST) on a generated wrapper: NumPy buffers in, every written
+    Dat copied back, versions tracked (two calls: the second must see the first's result)."""
+    from firedrake_b200 import codegen
+    elems, nodes, m, X, f = tc._golden_mesh()
+    _, rhs = tc._p1_kernels()
+    b = op2.Dat(nodes)
+    b.data[:] = 0.0
+    codegen.par_loop(rhs, elems, b(op2.INC, m), X(op2.READ, m), f(op2.READ, m), location="host")
+    assert np.abs(b._data - np.array(GOLD["expected_rhs"])).max() < GOLD["expected_rhs_eps"]
+    codegen.par_loop(rhs, elems, b(op2.INC, m), X(op2.READ, m), f(op2.READ, m), location="host")
+    assert np.abs(b._data - 2 * np.array(GOLD["expected_rhs"])).max() < 2 * GOLD["expected_rhs_eps"]
