@@ -227,3 +227,53 @@ def test_host_pointer_mode_generic(engine):
     assert np.abs(b._data - np.array(GOLD["expected_rhs"])).max() < GOLD["expected_rhs_eps"]
     codegen.par_loop(rhs, elems, b(op2.INC, m), X(op2.READ, m), f(op2.READ, m), location="host")
     assert np.abs(b._data - 2 * np.array(GOLD["expected_rhs"])).max() < 2 * GOLD["expected_rhs_eps"]
+
+
+def test_mg_transfers_on_device(engine):
+    from firedrake_b200 import mg
+    from firedrake_b200.assemble import FunctionSpace
+    h = mg.MeshHierarchy(2, 3, 2, 1, permute_seed=4)
+    Vc, Vf = FunctionSpace(h[0], 2), FunctionSpace(h[1], 2)
+    T = mg.TransferManager(Vc, Vf)
+    Pc, Pf = Vc.V.dof_coordinates(), Vf.V.dof_coordinates()
+    poly = lambda P: (1 + P[:, 0]) ** 2 * (2 - P[:, 1]) ** 2 * (0.5 + P[:, 2]) ** 2
+    uc, uf = Vc.dat(poly(Pc)), Vf.dat()
+    T.prolong(uc, uf)
+    assert np.abs(uf.data_ro - poly(Pf)).max() < 1e-12 * np.abs(poly(Pf)).max()
+    back = Vc.dat()
+    T.inject(uf, back)
+    assert np.abs(back.data_ro - uc.data_ro).max() < 1e-12 * np.abs(uc.data_ro).max()
+    rng = np.random.default_rng(11)
+    vc, rf = Vc.dat(rng.standard_normal(Vc.node_count)), Vf.dat(rng.standard_normal(Vf.node_count))
+    pv, rc = Vf.dat(), Vc.dat()
+    T.prolong(vc, pv)
+    T.restrict(rf, rc)
+    lhs, rhs = float(pv.data_ro @ rf.data_ro), float(vc.data_ro @ rc.data_ro)
+    assert abs(lhs - rhs) < 1e-11 * max(abs(lhs), 1.0)
+
+
+def test_mg_preconditioned_cg_is_mesh_independent(engine):
+    """demos/multigrid/geometric_multigrid.py.rst: CG preconditioned by a V-cycle converges in a
+    number of iterations that does not grow under refinement (unpreconditioned CG doubles)."""
+    from firedrake_b200 import mg
+    from firedrake_b200.assemble import cg, helmholtz
+    its, plain = [], []
+    for levels in (1, 2):
+        h = mg.MeshHierarchy(4, 4, 4, levels, warp=0.03)
+        vc = mg.VCycle(h, 2, helmholtz, bc_domains=("bottom",))
+        top = len(h) - 1
+        V, A = vc.spaces[top], vc.ops[top]
+        b = V.dat(np.random.default_rng(2).standard_normal(V.node_count))
+        for bc in vc.bcs[top]:
+            bc.zero(b)
+        x = V.dat()
+        x.device_ptr
+        n, hist = mg.pcg(A, b, x, lambda r, z: vc.apply(top, r, z), rtol=1e-8)
+        assert hist[-1] <= 1e-8 * hist[0]
+        its.append(n)
+        x2 = V.dat()
+        x2.device_ptr
+        n2, _ = cg(A, b, x2, rtol=1e-8, maxit=2000)
+        plain.append(n2)
+        assert np.abs(x.data_ro - x2.data_ro).max() < 1e-6 * np.abs(x2.data_ro).max()
+    assert its[1] <= its[0] + 3 and its[1] < plain[1] / 3
