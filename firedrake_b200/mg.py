@@ -19,8 +19,10 @@ kernels are generated C run through the engine's generic wrapper builder
 layer offset is twice the fine space's (one coarse layer = two fine layers).
 
 Status: kernels and maps are CPU-verified (tests/test_mg.py: polynomial
-exactness, restrict == prolong^T, inject o prolong == id); the V-cycle needs the
-GPU and its tests are gated like the rest of the generic path.
+exactness, restrict == prolong^T, inject o prolong == id); the V-cycle logic is
+CPU-verified against a mock engine (tests/test_host_logic_mock.py: level-independent
+contraction ~0.12 for CG1, ~0.19 for CG2, PCG in 6-8 iterations on 4^3..32^3); its
+first run on a GPU is gated like the rest of the generic path.
 """
 from __future__ import annotations
 
@@ -257,7 +259,7 @@ class VCycle:
     assembled diagonal (``ImplicitMatrixContext.getDiagonal``, operators.py:199-205),
     coarsest level solved by CG.  Everything stays on the device."""
 
-    def __init__(self, hierarchy, degree, make_form, bc_domains=(), nu=2, omega=2.0 / 3.0,
+    def __init__(self, hierarchy, degree, make_form, bc_domains=(), nu=2, omega=0.8,
                  coarse_rtol=1e-2, coarse_maxit=200):
         from .assemble import DirichletBC, FunctionSpace, assemble
         self.spaces = [FunctionSpace(m, degree) for m in hierarchy.meshes]
@@ -272,7 +274,10 @@ class VCycle:
             op2.par_loop(CStringKernel("static void recip(double *w) { *w = 1.0 / *w; }", "recip"),
                          V.node_set, d(op2.RW))
             self.invdiag.append(d)
-        self._work = [dict(r=V.dat(), e=V.dat(), t=V.dat(), b=V.dat()) for V in self.spaces]
+        # per level: r residual, t smoother scratch, e prolonged correction; as a COARSE level also
+        # b (restricted residual = its right-hand side) and x (its solution) -- x and e must be
+        # distinct Dats: level l-1's solution is the input of the prolongation into level l's e
+        self._work = [dict(r=V.dat(), e=V.dat(), t=V.dat(), b=V.dat(), x=V.dat()) for V in self.spaces]
 
     def _smooth(self, l, b, x):
         """x += omega D^-1 (b - A x), nu times."""
@@ -310,10 +315,10 @@ class VCycle:
         T.restrict(w["r"], wc["b"])
         for bc in self.bcs[l - 1]:
             bc.zero(wc["b"])
-        wc["e"].zero()
-        wc["e"].device_ptr
-        self.apply(l - 1, wc["b"], wc["e"])
-        T.prolong(wc["e"], w["e"])
+        wc["x"].zero()
+        wc["x"].device_ptr
+        self.apply(l - 1, wc["b"], wc["x"])
+        T.prolong(wc["x"], w["e"])
         for bc in self.bcs[l]:
             bc.zero(w["e"])
         _lib.check(L.fdb_vec_axpy(n, 1.0, w["e"].device_ptr, x.device_ptr))

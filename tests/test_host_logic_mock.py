@@ -1,0 +1,70 @@
+"""Host logic of the Python layers against a MOCK engine (tests/_mock_engine.py).
+
+Runs, on the CPU, test functions that normally need the GPU: the mock replaces the C
+ABI (device memory = host memory, generated wrappers through their host build, the
+hand-written Helmholtz kernels through the oracle), so what is checked here is the
+Python side -- argument marshalling, residency / dat_version bookkeeping, lgmap
+swapping, BC handling, the V-cycle and Krylov loops -- not the device code.
+
+Two groups: (1) tests that already PASS on a real B200 (they calibrate the mock: if
+the mock mis-emulated the ABI these would fail), (2) the tests of the code written
+after the GPU budget was spent (tests/test_jit_gpu.py, gated on the GPU until their
+first device run).
+"""
+import numpy as np
+import pytest
+
+import _mock_engine as me
+import test_assemble_gpu as ta
+import test_jit_gpu as tj
+import test_matrix_gpu as tm
+
+
+@pytest.fixture()
+def mock(oracle):
+    with me.install(oracle) as eng:
+        yield eng
+
+
+# ---- (1) calibration: GPU-validated tests must also pass on the mock
+def test_mock_runs_validated_matrix_tests(mock, oracle):
+    tm.test_sparsity_matches_reference_semantics(mock, oracle, 2)
+    tm.test_matrix_matches_oracle(mock, oracle, 2, 1.0, 1.0)
+    tm.test_bc_lgmaps_diagonal_and_matvec(mock, oracle)
+
+
+def test_mock_runs_validated_assemble_tests(mock, oracle):
+    ta.test_matfree_equals_assembled_with_bcs(mock)
+    ta.test_poisson_solve_strong_bcs_extrusion(mock)
+    ta.test_cg_matches_scipy(mock)
+    ta.test_get_diagonal(mock)
+
+
+# ---- (2) the post-budget code paths
+def test_generic_parloops_host_logic(mock):
+    tj.test_golden_mass_and_rhs(mock)
+    tj.test_blocked_matrix_generic_path(mock)
+    tj.test_permuted_map_and_subset(mock)
+    tj.test_host_pointer_mode_generic(mock)
+
+
+def test_access_modes_host_logic(mock):
+    tj.test_access_modes(mock)
+
+
+def test_generic_vs_fast_path_host_logic(mock, oracle):
+    tj.test_generic_extruded_action_equals_fast_path_and_oracle(mock, oracle)
+    tj.test_expression_interpolation(mock)
+
+
+def test_vector_space_assemble_host_logic(mock, oracle):
+    tj.test_vector_space_matrix_fast_path(mock, oracle, 1, 2)
+    tj.test_mult_transpose(mock)
+
+
+def test_mg_transfers_host_logic(mock):
+    tj.test_mg_transfers_on_device(mock)
+
+
+def test_mg_vcycle_host_logic(mock):
+    tj.test_mg_preconditioned_cg_is_mesh_independent(mock)
