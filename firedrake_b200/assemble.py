@@ -130,6 +130,129 @@ def interpolate(V: "FunctionSpace", expressions, target: op2.Dat = None):
     return target
 
 
+def functional_kernel(degree, measure, facet=None, name=None):
+    """C source of the 0-form kernels ``f*dx`` and ``f*ds`` on Q_p (x) P_p hexes with
+    trilinear geometry (what TSFC emits for a rank-0 form: ``A[0] += w*|J|*f(q)``,
+    tsfc/kernel_interface/common.py:139-239; facet kernels get the local facet number
+    as ``uint facet[1]``, firedrake_loopy.py:317-381).  Gauss-Legendre p+1 points per
+    direction.  ``measure``: "dx" (args: out, coords, f) or "ds" (exterior facet; the
+    local facet 2*direction + side is baked in when ``facet`` is given -- the
+    extruded ds_b / ds_t kernels -- else read from a 4th argument: ds_v)."""
+    from .fiat_lite import interval_element, _lagrange_tab
+    from .codegen import CStringKernel
+    el = interval_element(degree)
+    n = degree + 1
+    Bend, _ = el.tabulate([0.0, 1.0])
+    tab = lambda a: "{" + ", ".join("{" + ", ".join(repr(float(v)) for v in r) + "}" for r in a) + "}"
+    vec = lambda a: "{" + ", ".join(repr(float(v)) for v in a) + "}"
+    head = f"""
+static const double FB[{n}][{n}] = {tab(el.B)};      /* basis a at Gauss point q: FB[q][a] */
+static const double FE[2][{n}] = {tab(Bend)};        /* basis at the interval's ends */
+static const double FX[{n}] = {vec(el.xq)};
+static const double FW[{n}] = {vec(el.wq)};
+/* columns of the Jacobian of the trilinear map at xi: J[c][d] = dx_c / dxi_d */
+static inline void q1_jacobian(const double *X, const double *xi, double J[3][3])
+{{
+    for (int c = 0; c < 3; ++c) for (int d = 0; d < 3; ++d) J[c][d] = 0.0;
+    for (int v = 0; v < 8; ++v) {{
+        const int b[3] = {{(v >> 2) & 1, (v >> 1) & 1, v & 1}};
+        for (int d = 0; d < 3; ++d) {{
+            double g = b[d] ? 1.0 : -1.0;
+            for (int e = 0; e < 3; ++e) if (e != d) g *= b[e] ? xi[e] : 1.0 - xi[e];
+            for (int c = 0; c < 3; ++c) J[c][d] += X[v * 3 + c] * g;
+        }}
+    }}
+}}
+"""
+    if measure == "dx":
+        name = name or "functional_dx"
+        code = head + f"""
+static void {name}(double *out, const double *X, const double *f)
+{{
+    for (int qx = 0; qx < {n}; ++qx) for (int qy = 0; qy < {n}; ++qy) for (int qz = 0; qz < {n}; ++qz) {{
+        const double xi[3] = {{FX[qx], FX[qy], FX[qz]}};
+        double J[3][3], v = 0.0;
+        q1_jacobian(X, xi, J);
+        const double det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1])
+                         - J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0])
+                         + J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+        for (int a = 0; a < {n}; ++a) for (int b = 0; b < {n}; ++b) for (int c = 0; c < {n}; ++c)
+            v += f[(a * {n} + b) * {n} + c] * FB[qx][a] * FB[qy][b] * FB[qz][c];
+        out[0] += FW[qx] * FW[qy] * FW[qz] * fabs(det) * v;
+    }}
+}}
+"""
+        return CStringKernel(code, name)
+    if measure != "ds":
+        raise ValueError(f"unknown measure {measure!r}")
+    name = name or ("functional_ds" if facet is None else f"functional_ds{facet}")
+    sig = "const unsigned int *facet" if facet is None else ""
+    get = "facet[0]" if facet is None else str(int(facet))
+    code = head + f"""
+static void {name}(double *out, const double *X, const double *f{", " + sig if sig else ""})
+{{
+    const int fd = (int)({get}) / 2, fs = (int)({get}) % 2;     /* normal direction, side */
+    const int d1 = (fd + 1) % 3, d2 = (fd + 2) % 3;
+    for (int q1 = 0; q1 < {n}; ++q1) for (int q2 = 0; q2 < {n}; ++q2) {{
+        double xi[3], J[3][3], v = 0.0;
+        const double *T[3];                       /* 1-D basis rows per direction */
+        xi[fd] = (double)fs; xi[d1] = FX[q1]; xi[d2] = FX[q2];
+        T[fd] = FE[fs]; T[d1] = FB[q1]; T[d2] = FB[q2];
+        q1_jacobian(X, xi, J);
+        /* surface element |dx/dxi_d1 x dx/dxi_d2| */
+        const double cx = J[1][d1] * J[2][d2] - J[2][d1] * J[1][d2];
+        const double cy = J[2][d1] * J[0][d2] - J[0][d1] * J[2][d2];
+        const double cz = J[0][d1] * J[1][d2] - J[1][d1] * J[0][d2];
+        for (int a = 0; a < {n}; ++a) for (int b = 0; b < {n}; ++b) for (int c = 0; c < {n}; ++c)
+            v += f[(a * {n} + b) * {n} + c] * T[0][a] * T[1][b] * T[2][c];
+        out[0] += FW[q1] * FW[q2] * sqrt(cx * cx + cy * cy + cz * cz) * v;
+    }}
+}}
+"""
+    return CStringKernel(code, name)
+
+
+def assemble_functional(V: "FunctionSpace", f: op2.Dat, measure="dx"):
+    """``assemble(f*dx)`` / ``assemble(f*ds_b)`` / ``ds_t`` / ``ds_v`` / ``ds`` for a scalar
+    ``f`` in V: rank-0 parloops with a Global INC argument (firedrake/assemble.py
+    ZeroFormAssembler :1170-1194; the reduction of pyop2/parloop.py:411-455), through the
+    generic wrapper builder.  Extruded exterior facets follow the reference's split:
+    bottom / top = iteration regions ON_BOTTOM / ON_TOP over the cells, vertical = the base
+    mesh's exterior facets x all layers (firedrake/assemble.py:1810-1850)."""
+    from . import codegen
+    if V.cdim != 1:
+        raise NotImplementedError("functionals of scalar fields only")
+    if measure == "ds":
+        return sum(assemble_functional(V, f, m) for m in ("ds_b", "ds_t", "ds_v"))
+    g = op2.Global(1, 0.0)
+    p = V.degree
+    if measure == "dx":
+        codegen.par_loop(functional_kernel(p, "dx"), V.cell_set, g(op2.INC),
+                         V.coordinates(op2.READ, V.coord_map), f(op2.READ, V.cell_node_map))
+    elif measure in ("ds_b", "ds_t"):
+        k = functional_kernel(p, "ds", facet=4 if measure == "ds_b" else 5)
+        codegen.par_loop(k, V.cell_set, g(op2.INC), V.coordinates(op2.READ, V.coord_map),
+                         f(op2.READ, V.cell_node_map),
+                         iteration_region="ON_BOTTOM" if measure == "ds_b" else "ON_TOP",
+                         interior_horizontal=False)
+    elif measure == "ds_v":
+        if not hasattr(V, "_ext_facets"):
+            cells, local = V.mesh.exterior_vertical_facets()
+            fset = op2.ExtrudedSet(op2.Set(len(cells)), V.mesh.layers)
+            V._ext_facets = (
+                fset,
+                op2.Map(fset, V.node_set, V.V.arity, V.V.cell_node_map[cells], offset=V.V.offset),
+                op2.Map(fset, V.vertex_set, 8, V.mesh.coord_map[cells], offset=V.mesh.coord_offset),
+                op2.Dat(op2.DataSet(fset, 1), local, dtype=np.uint32))
+        fset, fmap, cmap, local = V._ext_facets
+        if fset.total_size:
+            codegen.par_loop(functional_kernel(p, "ds"), fset, g(op2.INC), V.coordinates(op2.READ, cmap),
+                             f(op2.READ, fmap), local(op2.READ))
+    else:
+        raise ValueError(f"unknown measure {measure!r}")
+    return float(g.data_ro[0])
+
+
 class DirichletBC:
     """``DirichletBC(V, g, sub_domain)``: node subset + value
     (firedrake/bcs.py:260-457)."""

@@ -199,7 +199,8 @@ def _handle(spec: WrapperSpec):
     return h
 
 
-def par_loop(kernel: CStringKernel, iterset, *args, iteration_region="ALL", location="device"):
+def par_loop(kernel: CStringKernel, iterset, *args, iteration_region="ALL", location="device",
+             interior_horizontal=None):
     """``op2.par_loop(op2.Kernel(code, name), iterset, *args)`` for a C-string
     kernel, one generated wrapper per distinct argument description.
     ``location="device"``: Dats stay resident on the GPU; ``"host"``: the drop-in
@@ -208,7 +209,7 @@ def par_loop(kernel: CStringKernel, iterset, *args, iteration_region="ALL", loca
     (generic parloops run unpartitioned for now)."""
     from . import op2
     if location == "host":
-        return _par_loop_host(kernel, iterset, args, iteration_region)
+        return _par_loop_host(kernel, iterset, args, iteration_region, interior_horizontal)
     base = iterset.superset if isinstance(iterset, op2.Subset) else iterset
     if kernel.accesses is not None and tuple(a.access for a in args) != tuple(kernel.accesses):
         raise ValueError("access descriptors do not match the kernel's")
@@ -223,7 +224,7 @@ def par_loop(kernel: CStringKernel, iterset, *args, iteration_region="ALL", loca
         if a.map is None and isinstance(a.data, op2.Dat) and a.data.dataset.set is not base:
             raise op2.MapValueError(f"direct argument {a.data.name} is not defined on the iteration set")
     spec = WrapperSpec(kernel, args, extruded=base._extruded, subset=isinstance(iterset, op2.Subset),
-                       iteration_region=iteration_region)
+                       iteration_region=iteration_region, interior_horizontal=interior_horizontal)
     h = _handle(spec)
     ca = _lib.CallArgs()
     lgmat = []
@@ -274,14 +275,14 @@ def par_loop(kernel: CStringKernel, iterset, *args, iteration_region="ALL", loca
     return spec
 
 
-def _par_loop_host(kernel, iterset, args, iteration_region):
+def _par_loop_host(kernel, iterset, args, iteration_region, interior_horizontal=None):
     """The arglist of pyop2/parloop.py:203-212 with host pointers, sizes and versions."""
     from . import op2
     base = iterset.superset if isinstance(iterset, op2.Subset) else iterset
     if any(isinstance(a.data, op2.Mat) for a in args):
         raise NotImplementedError("host-pointer mode takes Dats and Globals (Mats live on the device)")
     spec = WrapperSpec(kernel, args, extruded=base._extruded, subset=isinstance(iterset, op2.Subset),
-                       iteration_region=iteration_region)
+                       iteration_region=iteration_region, interior_horizontal=interior_horizontal)
     h = _handle(spec)
     for a in args:
         if isinstance(a.data, op2.Dat):

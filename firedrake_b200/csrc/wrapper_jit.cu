@@ -335,12 +335,13 @@ int validate(const fdb_wrapper_desc *d, Plan &pl)
                 pl.nmaps = std::max(pl.nmaps, a.map + 1);
                 ai.idx_r = add_index(a.map, a.arity, F, a.offset, a.permutation);
             } else {
-                if (pl.extruded) {
-                    set_error("fdb_wrapper: arg %d: direct Dats on extruded sets are not supported", i);
+                // a direct Dat on an extruded set is indexed by the column only
+                // (pyop2/codegen/builder.py:386-397): every layer of a column sees the same
+                // entry, which is only race free for READ
+                if (pl.extruded && a.access != FDB_READ) {
+                    set_error("fdb_wrapper: arg %d: direct Dats on extruded sets must be READ "
+                              "(one entry per column, shared by the threads of all its layers)", i);
                     return 1;
-                }
-                if (a.access == FDB_MIN || a.access == FDB_MAX) {
-                    // direct MIN/MAX degenerate to RW (one thread per entry); allowed
                 }
             }
         } else if (a.kind == FDB_ARG_GLOBAL) {

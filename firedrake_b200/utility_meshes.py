@@ -147,6 +147,18 @@ class ExtrudedHexMesh:
         return np.concatenate([self._vertex(i, np.arange(self.ny + 1)),
                                self._yedge(i, np.arange(self.ny))]).astype(np.int64)
 
+    def exterior_vertical_facets(self):
+        """(base cells, local facet numbers) of the base mesh's exterior facets: local facet
+        2*direction + side of the hex (0: x-, 1: x+, 2: y-, 3: y+; 4 / 5 are the bottom / top
+        faces, reached through iteration regions).  In a slab of a partitioned mesh only
+        facets on the GLOBAL boundary count (mesh.exterior_facets, firedrake/mesh.py:1211-1260)."""
+        gx = self.cell_ix + self.ix0
+        sel = [(gx == 0, 0), (gx == self.nx_global - 1, 1), (self.cell_iy == 0, 2),
+               (self.cell_iy == self.ny - 1, 3)]
+        cells = np.concatenate([np.nonzero(m)[0] for m, _ in sel]).astype(IntType)
+        local = np.concatenate([np.full(int(m.sum()), k, dtype=np.uint32) for m, k in sel])
+        return cells, local
+
     def function_space(self, degree: int) -> "ExtrudedFunctionSpace":
         if degree not in self._fs_cache:
             self._fs_cache[degree] = ExtrudedFunctionSpace(self, degree)

@@ -68,3 +68,7 @@ def test_mg_transfers_host_logic(mock):
 
 def test_mg_vcycle_host_logic(mock):
     tj.test_mg_preconditioned_cg_is_mesh_independent(mock)
+
+
+def test_zero_forms_host_logic(mock):
+    tj.test_zero_forms_dx_and_exterior_facets(mock)

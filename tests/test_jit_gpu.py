@@ -277,3 +277,23 @@ def test_mg_preconditioned_cg_is_mesh_independent(engine):
         plain.append(n2)
         assert np.abs(x.data_ro - x2.data_ro).max() < 1e-6 * np.abs(x2.data_ro).max()
     assert its[1] <= its[0] + 3 and its[1] < plain[1] / 3
+
+
+def test_zero_forms_dx_and_exterior_facets(engine):
+    """tests/firedrake/regression/test_integral_hex.py:10-23 (f*ds on the unit cube, exact
+    value 2+4+2+5+2+6) on the extruded hex mesh, the per-face split, and volume / area of a
+    warped mesh whose boundary is unchanged (tests/firedrake/extrusion/test_zero_forms_extrusion.py)."""
+    from firedrake_b200.assemble import FunctionSpace, assemble_functional, interpolate
+    mesh = ExtrudedHexMesh(2, 3, 5, permute_seed=3)
+    V = FunctionSpace(mesh, 3)
+    f = interpolate(V, "2 * x[0] + 3 * x[1] * x[1] + 4 * x[2] * x[2] * x[2]")
+    assert abs(assemble_functional(V, f, "ds_b") - 2.0) < 1e-10
+    assert abs(assemble_functional(V, f, "ds_t") - 6.0) < 1e-10
+    assert abs(assemble_functional(V, f, "ds_v") - (2 + 4 + 2 + 5)) < 1e-10
+    assert abs(assemble_functional(V, f, "ds") - 21.0) < 1e-10
+    assert abs(assemble_functional(V, f, "dx") - (1 + 1 + 1)) < 1e-10
+    wm = ExtrudedHexMesh(3, 3, 4, warp=0.05, permute_seed=1)
+    W = FunctionSpace(wm, 2)
+    one = interpolate(W, "1.0")
+    assert abs(assemble_functional(W, one, "dx") - 1.0) < 1e-12
+    assert abs(assemble_functional(W, one, "ds") - 6.0) < 1e-12
