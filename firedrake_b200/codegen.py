@@ -248,8 +248,33 @@ def par_loop(kernel: CStringKernel, iterset, *args, iteration_region="ALL", loca
     for a in lgmat:
         r, c = (np.ascontiguousarray(v, dtype=np.int32) for v in a.lgmaps)
         _lib.check(L.fdb_mat_set_lgmaps(a.data.handle, r.ctypes.data, c.ctypes.data))
+    # distributed protocol (pyop2/parloop.py:243-260, 354-455): ghost refresh of read Dats
+    # overlapped with the core part, ghost contributions of INC Dats summed into their
+    # owners afterwards, Globals reduced over the ranks
+    nranks = L.fdb_comm_size()
+    reads = [a.data for a in args if a.access in (op2.READ, op2.RW) and isinstance(a.data, op2.Dat)
+             and a.data.dataset.halo is not None and not a.data.halo_valid and a.map is not None]
+    incs = [a.data for a in args if a.access == op2.INC and isinstance(a.data, op2.Dat)
+            and a.data.dataset.halo is not None and not a.data.frozen_halo]
+    gouts = [a for a in args if isinstance(a.data, op2.Global) and a.access != op2.READ]
+    saved = {}
+    if nranks > 1:
+        for a in gouts:
+            if a.data._data.dtype != np.float64:
+                raise NotImplementedError("distributed reductions of non-float64 Globals")
+            if a.access == op2.INC:          # privatise: local sum from zero, added after the all-reduce
+                saved[id(a)] = a.data._data.copy()
+                a.data._data[...] = 0
+    for d in reads:
+        d.dataset.halo.global_to_local_begin(d)
+    first = True
     try:
         for start, end in (iterset.core_part, iterset.owned_part):
+            if not first:
+                for d in reads:
+                    d.dataset.halo.global_to_local_end(d)
+                reads = []
+            first = False
             if end <= start:
                 continue
             ca.start, ca.end = int(start), int(end)
@@ -272,6 +297,17 @@ def par_loop(kernel: CStringKernel, iterset, *args, iteration_region="ALL", loca
             a.data.halo_valid = False
         else:
             a.data.dat_version += 1
+    for d in incs:
+        d.dataset.halo.local_to_global_begin(d)
+        d.dataset.halo.local_to_global_end(d)
+    if nranks > 1:
+        for a in gouts:
+            buf = op2.DeviceArray.from_host(a.data._data)
+            op = {op2.INC: 0, op2.MIN: 1, op2.MAX: 2}[a.access]
+            _lib.check(L.fdb_allreduce(buf.ptr, a.data._data.size, op), "fdb_allreduce")
+            buf.to_host(a.data._data)
+            if a.access == op2.INC:
+                a.data._data[...] += saved[id(a)]
     return spec
 
 

@@ -113,6 +113,64 @@ class MockEngine:
     def fdb_mirror_drop(self, p):
         return 0
 
+    # ------------------------------------------------ communicator / halos over gloo
+    # (set .dist = torch.distributed after init_process_group to emulate N ranks)
+    dist = None
+
+    def fdb_comm_size(self):
+        return self.dist.get_world_size() if self.dist is not None else 1
+
+    def fdb_comm_rank(self):
+        return self.dist.get_rank() if self.dist is not None else 0
+
+    def fdb_allreduce(self, dev, n, op):
+        import torch
+        if self.dist is None:
+            return 0
+        v = _view(dev, n)
+        t = torch.from_numpy(v.copy())
+        self.dist.all_reduce(t, op={0: self.dist.ReduceOp.SUM, 1: self.dist.ReduceOp.MIN,
+                                    2: self.dist.ReduceOp.MAX}[op])
+        v[:] = t.numpy()
+        return 0
+
+    def fdb_halo_create(self, nneigh, ranks, send_counts, send_idx, recv_counts, recv_idx, max_cdim, out):
+        rk = _view(ranks, nneigh, np.int32)
+        sc, rc = _view(send_counts, nneigh, np.int32), _view(recv_counts, nneigh, np.int32)
+        si, ri = _view(send_idx, int(sc.sum()), np.int32).copy(), _view(recv_idx, int(rc.sum()), np.int32).copy()
+        so, ro = np.concatenate([[0], np.cumsum(sc)]), np.concatenate([[0], np.cumsum(rc)])
+        self._next += 1
+        self.kernels[self._next] = [(int(rk[i]), si[so[i]:so[i + 1]], ri[ro[i]:ro[i + 1]]) for i in range(nneigh)]
+        _obj(out).value = self._next
+        return 0
+
+    def fdb_halo_destroy(self, h):
+        self.kernels.pop(_addr(h), None)
+        return 0
+
+    def _halo(self, h, dat, cdim, reverse):
+        from _gloo_halo import exchange
+        neigh = self.kernels[_addr(h)]
+        top = max([int(max(s.max(initial=-1), r.max(initial=-1))) for _, s, r in neigh] + [-1]) + 1
+        data = _view(dat, top * cdim).reshape(top, cdim)
+        for c in range(cdim):                       # the gloo helper moves scalar fields
+            col = np.ascontiguousarray(data[:, c])
+            exchange(neigh, col, reverse)
+            data[:, c] = col
+        return 0
+
+    def fdb_halo_global_to_local_begin(self, h, dat, cdim):
+        return self._halo(h, dat, cdim, False)
+
+    def fdb_halo_global_to_local_end(self, h, dat, cdim):
+        return 0
+
+    def fdb_halo_local_to_global_begin(self, h, dat, cdim):
+        return self._halo(h, dat, cdim, True)
+
+    def fdb_halo_local_to_global_end(self, h, dat, cdim):
+        return 0
+
     # ---------------------------------------------------------------- vector algebra
     def fdb_vec_axpy(self, n, a, x, y):
         _view(y, n)[:] += a * _view(x, n)

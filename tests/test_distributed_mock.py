@@ -1,0 +1,88 @@
+"""World-size-2/3 CPU tests (gloo + the mock engine) of the DISTRIBUTED host logic:
+Parloop's halo protocol for the fast path (passes on 2/4 real GPUs: calibration) and,
+new, the same protocol for generic parloops -- ghost refresh of read Dats, local->global
+sum of INC Dats, all-reduce of Globals (pyop2/parloop.py:243-260, 354-455) -- through
+assemble_functional and a C-string Poisson kernel on a slab-partitioned mesh."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+from test_partition_gloo import ROOT, _free_port
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import _mock_engine as me
+    import test_codegen as tc
+    from firedrake_b200 import op2
+    from firedrake_b200.assemble import (FunctionSpace, OneFormAssembler, assemble_functional, helmholtz,
+                                         interpolate)
+    from firedrake_b200.partition import SlabPartition
+    from firedrake_b200.utility_meshes import ExtrudedHexMesh
+    from oracle import oracle
+    out = {}
+    with me.install(oracle) as eng:
+        eng.dist = dist
+        nx, ny, nz = 5, 3, 4
+        # ---- serial references on the whole mesh (every rank computes them redundantly, no comm)
+        eng.dist = None
+        gm = ExtrudedHexMesh(nx, ny, nz, warp=0.05)
+        G = FunctionSpace(gm, 1)
+        expr = "sin(2.0 * x[0]) + x[1] * x[2]"
+        gu = interpolate(G, expr)
+        gy = OneFormAssembler(helmholtz(G), gu).assemble()
+        gyg = G.dat()
+        op2.par_loop(op2.Kernel(tc.Q1_POISSON, "q1_poisson"), G.cell_set, gyg(op2.INC, G.cell_node_map),
+                     G.coordinates(op2.READ, G.coord_map), gu(op2.READ, G.cell_node_map))
+        ref = dict(dx=assemble_functional(G, gu, "dx"), ds=assemble_functional(G, gu, "ds"))
+        glat = G.V.dof_lattice()
+        key = lambda L: (L[:, 0] * 1000 + L[:, 1]) * 1000 + L[:, 2]
+        look_fast = dict(zip(key(glat).tolist(), gy.data_ro.tolist()))
+        look_gen = dict(zip(key(glat).tolist(), gyg.data_ro.tolist()))
+        # ---- the same on this rank's slab, with halos
+        eng.dist = dist
+        part = SlabPartition(nx, ny, nz, 1, rank, world, warp=0.05)
+        V = FunctionSpace(part.mesh, 1, partition=part)
+        u = interpolate(V, expr)
+        lat = V.V.dof_lattice()
+        no = V.V.owned_node_count
+        y = OneFormAssembler(helmholtz(V), u).assemble()                       # fast path + halos
+        out["fast"] = float(np.abs(y.data_ro[:no] - np.array([look_fast[k] for k in key(lat[:no]).tolist()])).max())
+        u2 = interpolate(V, expr)                                               # ghosts stale again
+        yg = V.dat()
+        yg.device_ptr
+        op2.par_loop(op2.Kernel(tc.Q1_POISSON, "q1_poisson"), V.cell_set, yg(op2.INC, V.cell_node_map),
+                     V.coordinates(op2.READ, V.coord_map), u2(op2.READ, V.cell_node_map))
+        out["generic"] = float(np.abs(yg.data_ro[:no] - np.array([look_gen[k] for k in key(lat[:no]).tolist()])).max())
+        out["dx"] = abs(assemble_functional(V, u2, "dx") - ref["dx"])
+        out["ds"] = abs(assemble_functional(V, u2, "ds") - ref["ds"])
+        out["scale"] = float(np.abs(gy.data_ro).max())
+    q.put((rank, out))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_distributed_generic_parloops(world):
+    from oracle import oracle
+    oracle.build()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    for rank, out in res:
+        assert out["fast"] < 1e-12 * out["scale"], (rank, out)
+        assert out["generic"] < 1e-12 * out["scale"], (rank, out)
+        assert out["dx"] < 1e-12 and out["ds"] < 1e-12, (rank, out)
