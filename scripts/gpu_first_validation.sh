@@ -1,0 +1,17 @@
+#!/bin/bash
+# First GPU call of the next round: run the GPU tests that were written after round 1's GPU
+# budget was spent (generic NVRTC wrapper builder, blocked matrices, interpolation, 0-forms,
+# multigrid), without -x so that one failure does not hide the others,
+# then one case under compute-sanitizer (races in the generated atomics / shuffles show here).
+#   gpurun --timeout 900 -- 'bash scripts/gpu_first_validation.sh'
+mkdir -p gpurun_out
+export FDB_RUN_UNVALIDATED=1
+python -m pytest tests/test_jit_gpu.py -q -m gpu -rA 2>&1 | tee gpurun_out/first_validation.log | tail -40
+timeout 300 compute-sanitizer --tool memcheck python -m pytest tests/test_jit_gpu.py -q -m gpu \
+    -k "access_modes or golden" > gpurun_out/first_validation_memcheck.log 2>&1
+tail -5 gpurun_out/first_validation_memcheck.log
+timeout 300 compute-sanitizer --tool racecheck python -m pytest tests/test_jit_gpu.py -q -m gpu \
+    -k "access_modes" > gpurun_out/first_validation_racecheck.log 2>&1
+tail -5 gpurun_out/first_validation_racecheck.log
+# the validated suite must be unaffected
+python -m pytest tests/ -x -q -m gpu 2>&1 | tail -3
