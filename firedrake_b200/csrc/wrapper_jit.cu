@@ -80,6 +80,7 @@ typedef int PetscInt;
 #endif
 #define FDB_DEVICE __device__ __forceinline__
 #define FDB_CONST __device__ const
+#define FDB_ABORT() __trap()
 
 struct FdbMatView {
     const long long *rowptr;
@@ -207,6 +208,85 @@ FDB_DEVICE void fdb_mat_set(const FdbMatView &m, int rnode, int a, int cnode, in
         BODY(p, (long long)blockIdx.x * blockDim.x + threadIdx.x);                    \
     }
 )PRELUDE";
+
+// Small dense linear algebra callable from local kernels: the `inverse` / `solve`
+// entry points PyOP2 provides to Slate-generated kernels through LAPACK
+// (pyop2/codegen/c/inverse.c:20-47, solve.c:20-51).
+// One matrix per thread = per iteration-set entry ("batched" over the parloop);
+// row-major, partial pivoting.  Emitted only when the local kernel mentions them.
+const char *kDenseLA = R"LA(
+#define FDB_LA_MAX 32
+/* Aout = A^{-1}, N x N row-major; Gauss-Jordan with partial pivoting */
+FDB_DEVICE void inverse(double *Aout, const double *A, int N)
+{
+    if (N > FDB_LA_MAX) FDB_ABORT();
+    int piv[FDB_LA_MAX];
+    for (int i = 0; i < N * N; ++i) Aout[i] = A[i];
+    for (int c = 0; c < N; ++c) {
+        int p = c;
+        double best = fabs(Aout[c * N + c]);
+        for (int r = c + 1; r < N; ++r)
+            if (fabs(Aout[r * N + c]) > best) { best = fabs(Aout[r * N + c]); p = r; }
+        if (best == 0.0) FDB_ABORT();                  /* singular: the reference aborts too */
+        piv[c] = p;
+        if (p != c)
+            for (int j = 0; j < N; ++j) { const double t = Aout[c * N + j]; Aout[c * N + j] = Aout[p * N + j]; Aout[p * N + j] = t; }
+        const double d = 1.0 / Aout[c * N + c];
+        Aout[c * N + c] = 1.0;
+        for (int j = 0; j < N; ++j) Aout[c * N + j] *= d;
+        for (int r = 0; r < N; ++r) {
+            if (r == c) continue;
+            const double f = Aout[r * N + c];
+            Aout[r * N + c] = 0.0;
+            for (int j = 0; j < N; ++j) Aout[r * N + j] -= f * Aout[c * N + j];
+        }
+    }
+    for (int c = N - 1; c >= 0; --c)                   /* undo the row swaps on the columns */
+        if (piv[c] != c)
+            for (int r = 0; r < N; ++r) { const double t = Aout[r * N + c]; Aout[r * N + c] = Aout[r * N + piv[c]]; Aout[r * N + piv[c]] = t; }
+}
+/* out = A^{-1} B for one right-hand side, A row-major; LU with partial pivoting on a copy */
+FDB_DEVICE void solve(double *out, const double *A, const double *B, int N)
+{
+    if (N > FDB_LA_MAX) FDB_ABORT();
+    double W[FDB_LA_MAX * FDB_LA_MAX];
+    for (int i = 0; i < N * N; ++i) W[i] = A[i];
+    for (int i = 0; i < N; ++i) out[i] = B[i];
+    for (int c = 0; c < N; ++c) {
+        int p = c;
+        double best = fabs(W[c * N + c]);
+        for (int r = c + 1; r < N; ++r)
+            if (fabs(W[r * N + c]) > best) { best = fabs(W[r * N + c]); p = r; }
+        if (best == 0.0) FDB_ABORT();
+        if (p != c) {
+            for (int j = 0; j < N; ++j) { const double t = W[c * N + j]; W[c * N + j] = W[p * N + j]; W[p * N + j] = t; }
+            const double t = out[c]; out[c] = out[p]; out[p] = t;
+        }
+        for (int r = c + 1; r < N; ++r) {
+            const double f = W[r * N + c] / W[c * N + c];
+            for (int j = c + 1; j < N; ++j) W[r * N + j] -= f * W[c * N + j];
+            out[r] -= f * out[c];
+        }
+    }
+    for (int r = N - 1; r >= 0; --r) {
+        double v = out[r];
+        for (int j = r + 1; j < N; ++j) v -= W[r * N + j] * out[j];
+        out[r] = v / W[r * N + r];
+    }
+}
+)LA";
+
+bool mentions(const char *src, const char *word)
+{
+    const size_t n = strlen(word);
+    for (const char *p = strstr(src, word); p; p = strstr(p + 1, word)) {
+        const bool left = p == src || !(isalnum((unsigned char)p[-1]) || p[-1] == '_');
+        const char *q = p + n;
+        while (*q == ' ' || *q == '\t') q++;
+        if (left && *q == '(') return true;
+    }
+    return false;
+}
 
 const char *ctype(int dt)
 {
@@ -426,6 +506,7 @@ std::string generate(const fdb_wrapper_desc *d, const Plan &pl)
 {
     std::ostringstream o;
     o << kPrelude << "\n" << kPreludeEnd << "\n";
+    if (mentions(d->kernel_source, "inverse") || mentions(d->kernel_source, "solve")) o << kDenseLA << "\n";
     o << "// ---- local kernel: " << pl.name << "\n";
     o << strip_includes(d->kernel_source) << "\n";
     o << "// ---- wrapper (generated): wrap_" << pl.name << "\n";

@@ -16,6 +16,7 @@ typedef int PetscInt;
 #define restrict __restrict__
 #define FDB_DEVICE static inline
 #define FDB_CONST static const
+#define FDB_ABORT() abort()
 
 struct FdbMatView {
     const long long *rowptr;

@@ -72,3 +72,4 @@ def test_mg_vcycle_host_logic(mock):
 
 def test_zero_forms_host_logic(mock):
     tj.test_zero_forms_dx_and_exterior_facets(mock)
+    tj.test_dense_linear_algebra_callables(mock)

@@ -297,3 +297,22 @@ def test_zero_forms_dx_and_exterior_facets(engine):
     one = interpolate(W, "1.0")
     assert abs(assemble_functional(W, one, "dx") - 1.0) < 1e-12
     assert abs(assemble_functional(W, one, "ds") - 6.0) < 1e-12
+
+
+def test_dense_linear_algebra_callables(engine):
+    n, N = 5000, 5
+    it = op2.Set(n)
+    rng = np.random.default_rng(4)
+    A = rng.standard_normal((n, N, N))
+    A[::3, 0, 0] = 0.0
+    b = rng.standard_normal((n, N))
+    dA, db = op2.Dat(op2.DataSet(it, N * N), A), op2.Dat(op2.DataSet(it, N), b)
+    dinv, dx = op2.Dat(op2.DataSet(it, N * N)), op2.Dat(op2.DataSet(it, N))
+    k = op2.Kernel(f"static void la(double *Ainv, double *x, const double *A, const double *b)"
+                   f"{{ inverse(Ainv, A, {N}); solve(x, A, b, {N}); }}", "la")
+    op2.par_loop(k, it, dinv(op2.WRITE), dx(op2.WRITE), dA(op2.READ), db(op2.READ))
+    ref_inv = np.linalg.inv(A)
+    ref_x = np.linalg.solve(A, b[..., None])[..., 0]
+    scale = np.abs(ref_inv).max(axis=(1, 2))
+    assert (np.abs(dinv.data_ro.reshape(n, N, N) - ref_inv).max(axis=(1, 2)) < 1e-10 * scale).all()
+    assert (np.abs(dx.data_ro - ref_x).max(axis=1) < 1e-10 * np.abs(ref_x).max(axis=1) * np.maximum(scale, 1)).all()
