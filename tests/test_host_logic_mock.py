@@ -73,3 +73,8 @@ def test_mg_vcycle_host_logic(mock):
 def test_zero_forms_host_logic(mock):
     tj.test_zero_forms_dx_and_exterior_facets(mock)
     tj.test_dense_linear_algebra_callables(mock)
+
+
+def test_helmholtz_convergence_host_logic(mock):
+    tj.test_helmholtz_convergence_rates(mock, 2, (2, 4), 2.9)
+    tj.test_helmholtz_convergence_rates(mock, 3, (1, 3), 3.9)

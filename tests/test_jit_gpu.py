@@ -316,3 +316,29 @@ def test_dense_linear_algebra_callables(engine):
     scale = np.abs(ref_inv).max(axis=(1, 2))
     assert (np.abs(dinv.data_ro.reshape(n, N, N) - ref_inv).max(axis=(1, 2)) < 1e-10 * scale).all()
     assert (np.abs(dx.data_ro - ref_x).max(axis=1) < 1e-10 * np.abs(ref_x).max(axis=1) * np.maximum(scale, 1)).all()
+
+
+@pytest.mark.parametrize("p,levels,rate", [(1, (4, 6), 1.9), (2, (2, 4), 2.9), (3, (1, 3), 3.9)])
+def test_helmholtz_convergence_rates(engine, p, levels, rate):
+    """tests/firedrake/extrusion/test_helmholtz_scalar.py:8-36 through the engine: f and the exact
+    solution interpolated (generic path), load vector = mass action, matrix-free CG on the device,
+    L2 error through the mass form."""
+    from firedrake_b200.assemble import FunctionSpace, assemble, cg, helmholtz, interpolate, mass
+    errs = []
+    for ii in range(*levels):
+        n = 2 ** ii
+        V = FunctionSpace(ExtrudedHexMesh(n, n, n, permute_seed=ii), p)
+        u_exact = "cos(2*M_PI*x[0]) * cos(2*M_PI*x[1]) * cos(2*M_PI*x[2])"
+        exact = interpolate(V, u_exact)
+        f = interpolate(V, f"(1 + 12*M_PI*M_PI) * {u_exact}")
+        b = assemble(mass(V), u=f)
+        A = assemble(helmholtz(V), mat_type="matfree")
+        u = V.dat()
+        u.device_ptr
+        it, hist = cg(A, b, u, rtol=1e-12, maxit=5000)
+        assert hist[-1] <= 1e-12 * hist[0]
+        e = V.dat(u.data_ro - exact.data_ro)
+        Me = assemble(mass(V), u=e)
+        errs.append(np.sqrt(e.data_ro @ Me.data_ro))
+    rates = [np.log2(errs[i] / errs[i + 1]) for i in range(len(errs) - 1)]
+    assert min(rates) > rate, (errs, rates)

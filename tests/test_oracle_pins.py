@@ -370,3 +370,31 @@ def test_gll_points_known_values():
         el = interval_element(p)
         B, _ = el.tabulate(el.nodes)
         np.testing.assert_allclose(B, np.eye(p + 1), atol=1e-13)
+
+
+@pytest.mark.parametrize("p,levels,rate", [(1, (4, 6), 1.9), (2, (2, 4), 2.9), (3, (1, 3), 3.9)])
+def test_helmholtz_convergence_rates(oracle, p, levels, rate):
+    """reference tests/firedrake/extrusion/test_helmholtz_scalar.py:8-36 (quadrilateral=True):
+    -lap u + u = f with natural conditions, u = cos(2 pi x) cos(2 pi y) cos(2 pi z), f and the
+    exact solution interpolated into the space, L2 error rate > p + 0.9.  CG1 on the reference's
+    16^3 / 32^3; CG2 and CG3 one level coarser than the reference (their rates are already
+    asymptotic there) to keep the CPU suite short."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    errs = []
+    for ii in range(*levels):
+        n = 2 ** ii
+        mesh = ExtrudedHexMesh(n, n, n, permute_seed=ii)
+        V = mesh.function_space(p)
+        P = V.dof_coordinates()
+        exact = np.cos(2 * np.pi * P[:, 0]) * np.cos(2 * np.pi * P[:, 1]) * np.cos(2 * np.pi * P[:, 2])
+        f = (1 + 12 * np.pi ** 2) * exact
+        rowptr, colidx, vals = assemble_matrix(oracle, mesh, V, p, 1.0, 1.0, None, None)
+        A = sp.csr_matrix((vals, colidx, rowptr), shape=(V.node_count, V.node_count))
+        b = action(oracle, mesh, V, p, f, 0.0, 1.0)                       # inner(f, v)*dx
+        u, info = spla.cg(A, b, rtol=1e-12, maxiter=5000)
+        assert info == 0
+        e = u - exact
+        errs.append(np.sqrt(e @ action(oracle, mesh, V, p, e, 0.0, 1.0)))  # ||e||_L2 through the mass form
+    rates = [np.log2(errs[i] / errs[i + 1]) for i in range(len(errs) - 1)]
+    assert min(rates) > rate, (errs, rates)
