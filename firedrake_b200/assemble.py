@@ -130,14 +130,16 @@ def interpolate(V: "FunctionSpace", expressions, target: op2.Dat = None):
     return target
 
 
-def functional_kernel(degree, measure, facet=None, name=None):
+def functional_kernel(degree, measure, facet=None, name=None, integrand="avg"):
     """C source of the 0-form kernels ``f*dx`` and ``f*ds`` on Q_p (x) P_p hexes with
     trilinear geometry (what TSFC emits for a rank-0 form: ``A[0] += w*|J|*f(q)``,
     tsfc/kernel_interface/common.py:139-239; facet kernels get the local facet number
     as ``uint facet[1]``, firedrake_loopy.py:317-381).  Gauss-Legendre p+1 points per
     direction.  ``measure``: "dx" (args: out, coords, f) or "ds" (exterior facet; the
     local facet 2*direction + side is baked in when ``facet`` is given -- the
-    extruded ds_b / ds_t kernels -- else read from a 4th argument: ds_v)."""
+    extruded ds_b / ds_t kernels -- else read from a 4th argument: ds_v), or "dS" (interior
+    facet; ``integrand`` "avg" = avg(f), "jump2" = (f('+') - f('-'))**2; ``facet`` = the pair of
+    local facet numbers or None to read uint[2])."""
     from .fiat_lite import interval_element, _lagrange_tab
     from .codegen import CStringKernel
     el = interval_element(degree)
@@ -183,6 +185,39 @@ static void {name}(double *out, const double *X, const double *f)
 }}
 """
         return CStringKernel(code, name)
+    if measure == "dS":
+        # interior facets: coefficient and coordinate arrays are doubled, cell '+' then cell '-'
+        # (tsfc/kernel_interface/common.py:518-522); local facet numbers uint[2]
+        # (firedrake_loopy.py:317-381).  The two cells are conforming and equally oriented, so a
+        # quadrature point has the same tangential reference coordinates in both.
+        name = name or ("functional_dS" if facet is None else f"functional_dS{facet[0]}{facet[1]}")
+        sig = ", const unsigned int *facet" if facet is None else ""
+        getp, getm = ("facet[0]", "facet[1]") if facet is None else (str(int(facet[0])), str(int(facet[1])))
+        expr = {"avg": "0.5 * (v[0] + v[1])", "jump2": "(v[0] - v[1]) * (v[0] - v[1])"}[integrand]
+        code = head + f"""
+static void {name}(double *out, const double *X, const double *f{sig})
+{{
+    const int fac[2] = {{(int)({getp}), (int)({getm})}};
+    const int fd = fac[0] / 2, d1 = (fd + 1) % 3, d2 = (fd + 2) % 3;
+    for (int q1 = 0; q1 < {n}; ++q1) for (int q2 = 0; q2 < {n}; ++q2) {{
+        double xi[3], J[3][3], v[2];
+        const double *T[3];
+        for (int s = 0; s < 2; ++s) {{                 /* restriction '+' (s = 0) and '-' (s = 1) */
+            T[fd] = FE[fac[s] % 2]; T[d1] = FB[q1]; T[d2] = FB[q2];
+            v[s] = 0.0;
+            for (int a = 0; a < {n}; ++a) for (int b = 0; b < {n}; ++b) for (int c = 0; c < {n}; ++c)
+                v[s] += f[s * {n ** 3} + (a * {n} + b) * {n} + c] * T[0][a] * T[1][b] * T[2][c];
+        }}
+        xi[fd] = (double)(fac[0] % 2); xi[d1] = FX[q1]; xi[d2] = FX[q2];
+        q1_jacobian(X, xi, J);                          /* geometry from the '+' cell */
+        const double cx = J[1][d1] * J[2][d2] - J[2][d1] * J[1][d2];
+        const double cy = J[2][d1] * J[0][d2] - J[0][d1] * J[2][d2];
+        const double cz = J[0][d1] * J[1][d2] - J[1][d1] * J[0][d2];
+        out[0] += FW[q1] * FW[q2] * sqrt(cx * cx + cy * cy + cz * cz) * ({expr});
+    }}
+}}
+"""
+        return CStringKernel(code, name)
     if measure != "ds":
         raise ValueError(f"unknown measure {measure!r}")
     name = name or ("functional_ds" if facet is None else f"functional_ds{facet}")
@@ -212,7 +247,7 @@ static void {name}(double *out, const double *X, const double *f{", " + sig if s
     return CStringKernel(code, name)
 
 
-def assemble_functional(V: "FunctionSpace", f: op2.Dat, measure="dx"):
+def assemble_functional(V: "FunctionSpace", f: op2.Dat, measure="dx", integrand="avg"):
     """``assemble(f*dx)`` / ``assemble(f*ds_b)`` / ``ds_t`` / ``ds_v`` / ``ds`` for a scalar
     ``f`` in V: rank-0 parloops with a Global INC argument (firedrake/assemble.py
     ZeroFormAssembler :1170-1194; the reduction of pyop2/parloop.py:411-455), through the
@@ -248,6 +283,32 @@ def assemble_functional(V: "FunctionSpace", f: op2.Dat, measure="dx"):
         if fset.total_size:
             codegen.par_loop(functional_kernel(p, "ds"), fset, g(op2.INC), V.coordinates(op2.READ, cmap),
                              f(op2.READ, fmap), local(op2.READ))
+    elif measure == "dS_h":
+        # horizontal interior facets: ON_INTERIOR_FACETS over the cells, every argument packs the
+        # cell below ('+') and the cell above ('-') (pyop2/codegen/builder.py:779-800, 840-844)
+        k = functional_kernel(p, "dS", facet=(5, 4), integrand=integrand)
+        codegen.par_loop(k, V.cell_set, g(op2.INC), V.coordinates(op2.READ, V.coord_map),
+                         f(op2.READ, V.cell_node_map), iteration_region="ON_INTERIOR_FACETS")
+    elif measure == "dS_v":
+        # vertical interior facets: the base mesh's interior facets x all layers; maps list the
+        # nodes of cell '+' then of cell '-' (firedrake/cython/dmcommon.pyx:1636-1677)
+        if V.dof_dset.halo is not None:
+            raise NotImplementedError("dS_v on a partitioned mesh needs an exec halo of cells")
+        if not hasattr(V, "_int_facets"):
+            cp, cm, local = V.mesh.interior_vertical_facets()
+            fset = op2.ExtrudedSet(op2.Set(len(cp)), V.mesh.layers)
+            cat = lambda m: np.concatenate([m[cp], m[cm]], axis=1)
+            V._int_facets = (
+                fset,
+                op2.Map(fset, V.node_set, 2 * V.V.arity, cat(V.V.cell_node_map), offset=np.tile(V.V.offset, 2)),
+                op2.Map(fset, V.vertex_set, 16, cat(V.mesh.coord_map), offset=np.tile(V.mesh.coord_offset, 2)),
+                op2.Dat(op2.DataSet(fset, 2), local, dtype=np.uint32))
+        fset, fmap, cmap, local = V._int_facets
+        if fset.total_size:
+            codegen.par_loop(functional_kernel(p, "dS", integrand=integrand), fset, g(op2.INC),
+                             V.coordinates(op2.READ, cmap), f(op2.READ, fmap), local(op2.READ))
+    elif measure == "dS":
+        return sum(assemble_functional(V, f, m, integrand) for m in ("dS_h", "dS_v"))
     else:
         raise ValueError(f"unknown measure {measure!r}")
     return float(g.data_ro[0])

@@ -159,6 +159,17 @@ class ExtrudedHexMesh:
         local = np.concatenate([np.full(int(m.sum()), k, dtype=np.uint32) for m, k in sel])
         return cells, local
 
+    def interior_vertical_facets(self):
+        """(cells '+', cells '-', local facet pairs (nfacets, 2)) of the base mesh's interior
+        facets within this (unpartitioned) mesh: x-normal facets carry local facets (1, 0),
+        y-normal ones (3, 2) (mesh.interior_facets, firedrake/mesh.py:1262-1300)."""
+        col = np.full((self.nx, self.ny), -1, dtype=np.int64)
+        col[self.cell_ix, self.cell_iy] = np.arange(self.num_base_cells)
+        xp, xm = col[:-1, :].ravel(), col[1:, :].ravel()
+        yp, ym = col[:, :-1].ravel(), col[:, 1:].ravel()
+        local = np.concatenate([np.tile([1, 0], (len(xp), 1)), np.tile([3, 2], (len(yp), 1))]).astype(np.uint32)
+        return (np.concatenate([xp, yp]).astype(IntType), np.concatenate([xm, ym]).astype(IntType), local)
+
     def function_space(self, degree: int) -> "ExtrudedFunctionSpace":
         if degree not in self._fs_cache:
             self._fs_cache[degree] = ExtrudedFunctionSpace(self, degree)

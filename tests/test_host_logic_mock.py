@@ -73,6 +73,7 @@ def test_mg_vcycle_host_logic(mock):
 def test_zero_forms_host_logic(mock):
     tj.test_zero_forms_dx_and_exterior_facets(mock)
     tj.test_dense_linear_algebra_callables(mock)
+    tj.test_interior_facet_functionals(mock)
 
 
 def test_helmholtz_convergence_host_logic(mock):

@@ -342,3 +342,21 @@ def test_helmholtz_convergence_rates(engine, p, levels, rate):
         errs.append(np.sqrt(e.data_ro @ Me.data_ro))
     rates = [np.log2(errs[i] / errs[i + 1]) for i in range(len(errs) - 1)]
     assert min(rates) > rate, (errs, rates)
+
+
+def test_interior_facet_functionals(engine):
+    """tests/firedrake/regression/test_integral_hex.py:26-37: the jump of a continuous function
+    over all interior facets vanishes; avg(1)*dS measures the interior facet area
+    ((nz-1) Lx Ly horizontal + ((nx-1) + (ny-1)) vertical unit faces on the unit cube).
+    Exercises ON_INTERIOR_FACETS two-layer packs and doubled '+'/'-' facet maps."""
+    from firedrake_b200.assemble import FunctionSpace, assemble_functional, interpolate
+    mesh = ExtrudedHexMesh(2, 3, 5, permute_seed=2)
+    V = FunctionSpace(mesh, 3)
+    f = interpolate(V, "2 * x[0] + 3 * x[1] * x[1] + 4 * x[2] * x[2] * x[2]")
+    assert assemble_functional(V, f, "dS", integrand="jump2") ** 0.5 < 1e-13
+    one = interpolate(V, "1.0")
+    assert abs(assemble_functional(V, one, "dS_h") - 4.0) < 1e-12
+    assert abs(assemble_functional(V, one, "dS_v") - 3.0) < 1e-12
+    # avg(f) over the horizontal facets z = k/5: int 2x + 3y^2 + 4z^3 = 2 + 4 z^3
+    ref = sum(2 + 4 * (k / 5) ** 3 for k in range(1, 5))
+    assert abs(assemble_functional(V, f, "dS_h") - ref) < 1e-11
