@@ -202,8 +202,8 @@ def _make_wrapper(handle, global_kernel):
         ca.layers = C.cast(layers, C.POINTER(C.c_int32)) if layers else None
         ca.subset = subset_ptr
         ca.nargs, ca.args = nargs, (C.c_void_p * nargs)(*data)
-        # sizes and dat_versions are not part of the reference arglist: the patched
-        # Parloop passes them through a side channel (Parloop._fdb_sizes / _fdb_versions)
+        # sizes and dat_versions are not part of the reference arglist: _patched_compute
+        # (below) sets them on this callable right before PyOP2 invokes it
         ca.arg_bytes = (C.c_size_t * nargs)(*fn.sizes[:nargs])
         ca.arg_versions = (C.c_uint64 * nargs)(*fn.versions[:nargs])
         ca.nmaps, ca.maps = len(maps), (C.c_void_p * len(maps))(*maps)
@@ -216,13 +216,46 @@ def _make_wrapper(handle, global_kernel):
     return fn
 
 
+_original_compute = None
+
+
+def _patched_compute(self, part):
+    """``Parloop._compute`` (pyop2/parloop.py:224-232) with the side channel the engine's
+    host-pointer mode needs and the reference arglist lacks: byte sizes of the argument and map
+    buffers and ``dat_version`` of every argument (the mirror cache key).  PyOP2 bumps the version
+    of written arguments BEFORE the compute phases (``increment_dat_version``,
+    parloop.py:243-245) while the engine records ``version + 1`` after its write-back, so written
+    arguments are announced with ``dat_version - 1``."""
+    import pyop2.global_kernel as gk
+    fn = gk.compile_global_kernel(self.global_kernel, self.comm)      # memory-cached
+    if hasattr(fn, "sizes"):
+        from pyop2.types import READ
+        sizes, versions = [], []
+        for arg, access in zip(self.arguments, self.accesses):
+            data = arg.data
+            for d in (data if hasattr(data, "__iter__") and not hasattr(data, "_data") else (data,)):
+                buf = getattr(d, "_data", None)
+                sizes.append(0 if buf is None else buf.nbytes)
+                v = getattr(d, "dat_version", 0)
+                versions.append(v if access is READ else max(v - 1, 0))
+        maps = {m: None for d in self.arguments for m in d.map_kernel_args}
+        fn.sizes, fn.versions = tuple(sizes), tuple(versions)
+        fn.map_sizes = tuple(self.iterset.total_size * 4 * getattr(m, "arity", 0) if not hasattr(m, "nbytes")
+                             else m.nbytes for m in maps)
+        fn.output_is_zero = False
+    return _original_compute(self, part)
+
+
 def install():
-    """Swap ``compile_global_kernel``; idempotent."""
-    global _original
+    """Swap ``compile_global_kernel`` and ``Parloop._compute``; idempotent."""
+    global _original, _original_compute
     import pyop2.global_kernel as gk          # noqa: F401  (ImportError here: no Firedrake)
+    import pyop2.parloop as pl
     if _original is not None:
         return
     _original = gk.compile_global_kernel
+    _original_compute = pl.Parloop._compute
+    pl.Parloop._compute = _patched_compute
 
     def compile_global_kernel(kernel, comm):
         found = _descriptor_for(kernel)
@@ -244,8 +277,10 @@ def install():
 
 
 def uninstall():
-    global _original
+    global _original, _original_compute
     if _original is not None:
         import pyop2.global_kernel as gk
+        import pyop2.parloop as pl
         gk.compile_global_kernel = _original
-        _original = None
+        pl.Parloop._compute = _original_compute
+        _original = _original_compute = None
