@@ -83,6 +83,7 @@ class WrapperDesc(C.Structure):
         ("kernel_source", C.c_char_p), ("kernel_name", C.c_char_p),
         ("nargs", C.c_int32), ("args", C.POINTER(WrapperArg)),
         ("extruded", C.c_int32), ("subset", C.c_int32), ("iteration_region", C.c_int32),
+        ("pass_layer_arg", C.c_int32),
     ]
 
 

@@ -87,7 +87,7 @@ class WrapperSpec:
     """The compile-time description of one generic parloop."""
 
     def __init__(self, kernel: CStringKernel, args, *, extruded=False, subset=False,
-                 iteration_region="ALL", interior_horizontal=None):
+                 iteration_region="ALL", interior_horizontal=None, pass_layer_arg=False):
         from . import op2
         if interior_horizontal is None:
             # every indirect argument of an interior-horizontal-facet loop packs the cells
@@ -100,7 +100,7 @@ class WrapperSpec:
         self._keep = []
         arr = (_lib.WrapperArg * len(args))()
         key = [kernel.code, kernel.name, bool(extruded), bool(subset), iteration_region,
-               bool(interior_horizontal)]
+               bool(interior_horizontal), bool(pass_layer_arg)]
         for i, a in enumerate(args):
             w = arr[i]
             w.access = int(a.access)
@@ -142,6 +142,7 @@ class WrapperSpec:
         d.nargs, d.args = len(args), arr
         d.extruded, d.subset = int(bool(extruded)), int(bool(subset))
         d.iteration_region = _REGIONS[iteration_region]
+        d.pass_layer_arg = int(bool(pass_layer_arg))
         self._keep.append(arr)
         self.desc = d
 
@@ -200,7 +201,7 @@ def _handle(spec: WrapperSpec):
 
 
 def par_loop(kernel: CStringKernel, iterset, *args, iteration_region="ALL", location="device",
-             interior_horizontal=None):
+             interior_horizontal=None, pass_layer_arg=False):
     """``op2.par_loop(op2.Kernel(code, name), iterset, *args)`` for a C-string
     kernel, one generated wrapper per distinct argument description.
     ``location="device"``: Dats stay resident on the GPU; ``"host"``: the drop-in
@@ -209,7 +210,7 @@ def par_loop(kernel: CStringKernel, iterset, *args, iteration_region="ALL", loca
     (generic parloops run unpartitioned for now)."""
     from . import op2
     if location == "host":
-        return _par_loop_host(kernel, iterset, args, iteration_region, interior_horizontal)
+        return _par_loop_host(kernel, iterset, args, iteration_region, interior_horizontal, pass_layer_arg)
     base = iterset.superset if isinstance(iterset, op2.Subset) else iterset
     if kernel.accesses is not None and tuple(a.access for a in args) != tuple(kernel.accesses):
         raise ValueError("access descriptors do not match the kernel's")
@@ -224,7 +225,8 @@ def par_loop(kernel: CStringKernel, iterset, *args, iteration_region="ALL", loca
         if a.map is None and isinstance(a.data, op2.Dat) and a.data.dataset.set is not base:
             raise op2.MapValueError(f"direct argument {a.data.name} is not defined on the iteration set")
     spec = WrapperSpec(kernel, args, extruded=base._extruded, subset=isinstance(iterset, op2.Subset),
-                       iteration_region=iteration_region, interior_horizontal=interior_horizontal)
+                       iteration_region=iteration_region, interior_horizontal=interior_horizontal,
+                       pass_layer_arg=pass_layer_arg)
     h = _handle(spec)
     ca = _lib.CallArgs()
     lgmat = []
@@ -311,14 +313,15 @@ def par_loop(kernel: CStringKernel, iterset, *args, iteration_region="ALL", loca
     return spec
 
 
-def _par_loop_host(kernel, iterset, args, iteration_region, interior_horizontal=None):
+def _par_loop_host(kernel, iterset, args, iteration_region, interior_horizontal=None, pass_layer_arg=False):
     """The arglist of pyop2/parloop.py:203-212 with host pointers, sizes and versions."""
     from . import op2
     base = iterset.superset if isinstance(iterset, op2.Subset) else iterset
     if any(isinstance(a.data, op2.Mat) for a in args):
         raise NotImplementedError("host-pointer mode takes Dats and Globals (Mats live on the device)")
     spec = WrapperSpec(kernel, args, extruded=base._extruded, subset=isinstance(iterset, op2.Subset),
-                       iteration_region=iteration_region, interior_horizontal=interior_horizontal)
+                       iteration_region=iteration_region, interior_horizontal=interior_horizontal,
+                       pass_layer_arg=pass_layer_arg)
     h = _handle(spec)
     for a in args:
         if isinstance(a.data, op2.Dat):

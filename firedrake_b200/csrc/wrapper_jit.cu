@@ -338,7 +338,12 @@ struct Plan {
     std::string name;
     std::vector<ArgInfo> args;
     std::vector<IndexSet> idx;
-    int extruded = 0, subset = 0, region = 0, nmaps = 0, nmats = 0;
+    int extruded = 0, subset = 0, region = 0, nmaps = 0, nmats = 0, pass_layer = 0;
+    // a direct Dat that is written from an extruded loop goes through a private copy
+    bool private_direct(const fdb_wrapper_arg &a) const
+    {
+        return extruded && a.kind == FDB_ARG_DAT && a.map < 0 && a.access != FDB_READ;
+    }
 };
 
 int validate(const fdb_wrapper_desc *d, Plan &pl)
@@ -367,6 +372,11 @@ int validate(const fdb_wrapper_desc *d, Plan &pl)
     pl.extruded = d->extruded ? 1 : 0;
     pl.subset = d->subset ? 1 : 0;
     pl.region = d->iteration_region;
+    pl.pass_layer = d->pass_layer_arg ? 1 : 0;
+    if (pl.pass_layer && !pl.extruded) {
+        set_error("fdb_wrapper: pass_layer_arg needs an extruded set (pyop2/global_kernel.py:299-302)");
+        return 1;
+    }
     auto add_index = [&](int map, int arity, int F, const fdb_int *off, const fdb_int *perm) -> int {
         IndexSet s;
         s.map = map;
@@ -418,9 +428,10 @@ int validate(const fdb_wrapper_desc *d, Plan &pl)
                 // a direct Dat on an extruded set is indexed by the column only
                 // (pyop2/codegen/builder.py:386-397): every layer of a column sees the same
                 // entry, which is only race free for READ
-                if (pl.extruded && a.access != FDB_READ) {
-                    set_error("fdb_wrapper: arg %d: direct Dats on extruded sets must be READ "
-                              "(one entry per column, shared by the threads of all its layers)", i);
+                if (pl.extruded && a.access != FDB_READ && a.access != FDB_INC && a.access != FDB_WRITE) {
+                    set_error("fdb_wrapper: arg %d: direct Dats on extruded sets are READ, INC or WRITE "
+                              "(one entry per column, shared by the threads of all its layers: RW / MIN / "
+                              "MAX would depend on the layer order)", i);
                     return 1;
                 }
             }
@@ -537,6 +548,8 @@ std::string generate(const fdb_wrapper_desc *d, const Plan &pl)
         const int F = a.interior_horizontal ? 2 : 1;
         if (a.kind == FDB_ARG_DAT && a.map >= 0)
             o << "    " << ctype(a.dtype) << " t" << i << "[" << F * a.arity * a.dim << "];\n";
+        else if (pl.private_direct(a))
+            o << "    " << ctype(a.dtype) << " t" << i << "[" << a.dim << "];\n";
         else if (a.kind == FDB_ARG_GLOBAL && a.access != FDB_READ)
             o << "    " << ctype(a.dtype) << " t" << i << "[" << a.dim << "];\n";
         else if (a.kind == FDB_ARG_MAT)
@@ -586,6 +599,8 @@ std::string generate(const fdb_wrapper_desc *d, const Plan &pl)
         } else if (a.kind == FDB_ARG_MAT) {
             o << "        for (int k = 0; k < " << F * a.arity * a.dim * F * a.arity2 * a.dim2 << "; ++k) t" << i
               << "[k] = 0.0;\n";
+        } else if (pl.private_direct(a)) {
+            o << "        for (int c = 0; c < " << a.dim << "; ++c) t" << i << "[c] = (" << ctype(a.dtype) << ")0;\n";
         }
     }
     // the local kernel
@@ -593,13 +608,14 @@ std::string generate(const fdb_wrapper_desc *d, const Plan &pl)
     for (size_t i = 0; i < pl.args.size(); i++) {
         const fdb_wrapper_arg &a = pl.args[i].a;
         if (i) o << ", ";
-        if (a.kind == FDB_ARG_DAT && a.map < 0)
+        if (a.kind == FDB_ARG_DAT && a.map < 0 && !pl.private_direct(a))
             o << "((" << ctype(a.dtype) << " *)p.arg[" << i << "]) + (long long)n * " << a.dim;
         else if (a.kind == FDB_ARG_GLOBAL && a.access == FDB_READ)
             o << "(" << ctype(a.dtype) << " *)p.arg[" << i << "]";
         else
             o << "t" << i;
     }
+    if (pl.pass_layer) o << ", layer";
     o << ");\n";
     // unpacks
     for (size_t i = 0; i < pl.args.size(); i++) {
@@ -619,6 +635,13 @@ std::string generate(const fdb_wrapper_desc *d, const Plan &pl)
             default: o << "                *dst = v;\n"; break;
             }
             o << "            }\n";
+        } else if (pl.private_direct(a)) {
+            o << "        for (int c = 0; c < " << a.dim << "; ++c) {\n"
+              << "            " << ctype(a.dtype) << " *dst = ((" << ctype(a.dtype) << " *)p.arg[" << i
+              << "]) + (long long)n * " << a.dim << " + c;\n";
+            if (a.access == FDB_INC) o << "            fdb_atomic_add(dst, t" << i << "[c]);\n";
+            else o << "            *dst = t" << i << "[c];\n";
+            o << "        }\n";
         } else if (a.kind == FDB_ARG_MAT) {
             const int nr = F * a.arity, nc = F * a.arity2;
             o << "        for (int r = 0; r < " << nr << "; ++r)\n"

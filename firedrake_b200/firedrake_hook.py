@@ -32,7 +32,7 @@ What it does: replaces ``pyop2.global_kernel.compile_global_kernel``
    pyop2/codegen/builder.py:840-916).
 3. Everything else (PETSc ``Mat`` arguments -- the engine assembles into its own
    CSR, not into a PETSc handle --, MixedDats, periodic extrusion, variable
-   layers, ``pass_layer_arg``) falls through to the stock C path.
+   layers) falls through to the stock C path.
 """
 from __future__ import annotations
 
@@ -118,8 +118,6 @@ def _generic_for(global_kernel):
     g = global_kernel
     if g._extruded and (not g._constant_layers or g._extruded_periodic):
         return None
-    if g._pass_layer_arg:
-        return None
     region = {None: _lib.REGION_ALL, IterationRegion.ALL: _lib.REGION_ALL,
               IterationRegion.BOTTOM: _lib.REGION_ON_BOTTOM, IterationRegion.TOP: _lib.REGION_ON_TOP,
               IterationRegion.INTERIOR_FACETS: _lib.REGION_ON_INTERIOR_FACETS}[g._iteration_region]
@@ -177,6 +175,7 @@ def _generic_for(global_kernel):
     d.kernel_source, d.kernel_name = src, name
     d.nargs, d.args = len(g.arguments), arr
     d.extruded, d.subset, d.iteration_region = int(g._extruded), int(g._subset), region
+    d.pass_layer_arg = int(bool(g._pass_layer_arg))
     return d, keep
 
 

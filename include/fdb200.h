@@ -208,7 +208,9 @@ int fdb_kernel_call(fdb_kernel_t k, const fdb_call_args *a);
  *   Dat through a Map  t[f][i][c] = dat[(map[n][perm[i]] + offset[i]*(layer-bottom+f))*cdim + c]
  *                      READ/RW/MIN/MAX packs read the Dat, INC/WRITE packs start at zero;
  *                      unpack: INC += (atomic), MIN/MAX (atomic), WRITE/RW plain store
- *   Dat direct         the kernel gets &dat[n*cdim]
+ *   Dat direct         the kernel gets &dat[n*cdim]; on an extruded set the entry belongs to the
+ *                      COLUMN (every layer sees the same one): READ passes the pointer, INC and
+ *                      WRITE go through a private copy (atomic add / plain store), RW is refused
  *   Global             READ: pointer to the values; INC/MIN/MAX: privatised per
  *                      thread, combined with warp shuffles + one atomic per warp
  *   Mat                zeroed local tensor (nr*rdim, nc*cdim) row-major, added into
@@ -251,6 +253,8 @@ typedef struct fdb_wrapper_desc {
     int32_t extruded;           /* iterate layers (constant layers only)                     */
     int32_t subset;             /* n = subset[n]                                             */
     int32_t iteration_region;   /* enum fdb_region                                           */
+    int32_t pass_layer_arg;     /* extruded: append the current layer (int, by value) to the
+                                   local kernel's arguments (pyop2/global_kernel.py:277-279)  */
 } fdb_wrapper_desc;
 
 /* The generated CUDA source (no GPU needed).  Writes at most `cap` bytes incl.
