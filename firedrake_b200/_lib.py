@@ -43,7 +43,7 @@ class KernelDesc(C.Structure):
         ("B", C.c_double * (MAX_1D * MAX_1D)), ("D", C.c_double * (MAX_1D * MAX_1D)),
         ("wq", C.c_double * MAX_1D), ("xq", C.c_double * MAX_1D),
         ("offset0", C.POINTER(C.c_int32)), ("offset1", C.POINTER(C.c_int32)),
-        ("diagonal", C.c_int32),
+        ("diagonal", C.c_int32), ("affine_cells", C.c_int32),
     ]
 
 
@@ -113,6 +113,8 @@ SIGNATURES = {
     "fdb_mirror_drop_all": (C.c_int, []),
     "fdb_kernel_create": (C.c_int, [C.POINTER(KernelDesc), C.POINTER(C.c_void_p)]),
     "fdb_kernel_destroy": (C.c_int, [C.c_void_p]),
+    "fdb_cells_are_affine": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int,
+                                       C.POINTER(C.c_int)]),
     "fdb_kernel_call": (C.c_int, [C.c_void_p, C.POINTER(CallArgs)]),
     "fdb_wrapper_source": (C.c_int, [C.POINTER(WrapperDesc), C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "fdb_wrapper_compile": (C.c_int, [C.POINTER(WrapperDesc), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),

@@ -51,6 +51,21 @@ class FunctionSpace:
     def dat(self, data=None, pinned=False):
         return op2.Dat(self.dof_dset, data, pinned=pinned)
 
+    def cells_are_affine(self):
+        """True iff every cell is a parallelepiped (checked on the device, cached per version of
+        the coordinate Dat): lets the assembler pick the per-cell-metric kernel variant."""
+        import ctypes as C
+        from . import _lib
+        key = self.coordinates.dat_version
+        if getattr(self, "_affine", (None, None))[0] != key:
+            off = np.ascontiguousarray(self.mesh.coord_offset, dtype=np.int32)
+            res = C.c_int()
+            _lib.check(_lib.lib().fdb_cells_are_affine(
+                self.coordinates.device_ptr, self.coord_map.device_ptr, off.ctypes.data, 0,
+                self.cell_set.total_size, self.mesh.nz, C.byref(res)), "fdb_cells_are_affine")
+            self._affine = (key, bool(res.value))
+        return self._affine[1]
+
     @property
     def node_count(self):
         return self.V.node_count
@@ -360,8 +375,12 @@ class Form:
     beta: float = 0.0
 
     def kernel(self, rank):
+        import os
+        # opt-in until its first GPU validation (DESIGN.md sections 7b, 8b): per-cell metric on
+        # meshes whose cells are all parallelepipeds
+        affine = rank == 1 and os.environ.get("FDB_AFFINE") == "1" and self.V.cells_are_affine()
         return op2.Kernel("helmholtz", degree=self.V.degree, alpha=self.alpha, beta=self.beta,
-                          rank=rank, cdim=self.V.cdim)
+                          rank=rank, cdim=self.V.cdim, affine=affine)
 
 
 def poisson(V):

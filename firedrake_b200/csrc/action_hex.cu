@@ -253,11 +253,16 @@ struct Unit {
     bool lead;    // this lane's cell copies the rows of its column
 };
 
-template <int N, bool MASS, bool ATOMIC, int MINB, bool MATRIX = false, bool SLIM = false>
+// AFFINE: the caller promises that every cell is a parallelepiped (fdb_kernel_desc.affine_cells):
+// the trilinear terms of the coordinate field vanish, the Jacobian is constant per cell and the
+// metric G = (alpha / |det|) K K^T (K = cofactor rows) is formed once per cell instead of at
+// each of the N^3 quadrature points.
+template <int N, bool MASS, bool ATOMIC, int MINB, bool MATRIX = false, bool SLIM = false, bool AFFINE = false>
 __global__ void __launch_bounds__(WPC<N, SLIM>::value * 32, MINB)
 helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
 {
     static_assert(!(SLIM && MATRIX), "matrix mode keeps the per-cell index buffer");
+    static_assert(!(AFFINE && MATRIX), "the affine variant exists for 1-forms only");
     using WS = WarpSmem<N, SLIM>;
     constexpr int CW = WS::CW;
     constexpr int CWS = WS::CWS;
@@ -433,6 +438,9 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
     stageA(nxt);
     cp_async_commit();
     double A1[3], A3[3], A6[3], c2[3], c4[3], c5[3], c7[3];
+    double Gm[6], adet_c = 1.0;       // AFFINE: metric (xx, xy, xz, yy, yz, zz) and |det J| of the cell
+#pragma unroll
+    for (int i = 0; i < 6; i++) Gm[i] = 0.0;
 
     while (cur.item >= 0) {
         cp_async_wait<0>();      // values of `cur`, rows of `nxt` have landed
@@ -464,6 +472,28 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
                 A1[a] = fma(c4[a], eta, c1);
                 A3[a] = fma(c5[a], eta, c3);
                 A6[a] = fma(c7[a], eta, c6);
+            }
+            if (AFFINE) {
+                // constant Jacobian: columns a = A1 (dx/dxi), b = c2 (dx/deta), c = A3 (dx/dzeta)
+                double r0[3], r1[3], r2[3];
+                r0[0] = c2[1] * A3[2] - c2[2] * A3[1];
+                r0[1] = c2[2] * A3[0] - c2[0] * A3[2];
+                r0[2] = c2[0] * A3[1] - c2[1] * A3[0];
+                r1[0] = A3[1] * A1[2] - A3[2] * A1[1];
+                r1[1] = A3[2] * A1[0] - A3[0] * A1[2];
+                r1[2] = A3[0] * A1[1] - A3[1] * A1[0];
+                r2[0] = A1[1] * c2[2] - A1[2] * c2[1];
+                r2[1] = A1[2] * c2[0] - A1[0] * c2[2];
+                r2[2] = A1[0] * c2[1] - A1[1] * c2[0];
+                const double det = A1[0] * r0[0] + A1[1] * r0[1] + A1[2] * r0[2];
+                adet_c = fabs(det);
+                const double rd = fast_rcp(adet_c);
+                Gm[0] = rd * (r0[0] * r0[0] + r0[1] * r0[1] + r0[2] * r0[2]);
+                Gm[1] = rd * (r0[0] * r1[0] + r0[1] * r1[1] + r0[2] * r1[2]);
+                Gm[2] = rd * (r0[0] * r2[0] + r0[1] * r2[1] + r0[2] * r2[2]);
+                Gm[3] = rd * (r1[0] * r1[0] + r1[1] * r1[1] + r1[2] * r1[2]);
+                Gm[4] = rd * (r1[0] * r2[0] + r1[1] * r2[1] + r1[2] * r2[2]);
+                Gm[5] = rd * (r2[0] * r2[0] + r2[1] * r2[1] + r2[2] * r2[2]);
             }
         }
         const int comp = cur.comp;
@@ -525,11 +555,13 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
 #pragma unroll
                 for (int j = 0; j < N; j++) dz[j] = P.DtR[qz * N + j];
                 double ca[3], pb[3], qb[3];
+                if (!AFFINE) {
 #pragma unroll
-                for (int a = 0; a < 3; a++) {
-                    ca[a] = fma(A6[a], zeta, A1[a]);       // dx/dxi
-                    pb[a] = fma(c5[a], zeta, c2[a]);
-                    qb[a] = fma(c7[a], zeta, c4[a]);
+                    for (int a = 0; a < 3; a++) {
+                        ca[a] = fma(A6[a], zeta, A1[a]);       // dx/dxi
+                        pb[a] = fma(c5[a], zeta, c2[a]);
+                        qb[a] = fma(c7[a], zeta, c4[a]);
+                    }
                 }
                 const double wyz_a = wy_alpha * P.wq[qz];
                 const double wyz_b = wy_beta * P.wq[qz];
@@ -538,10 +570,12 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
                 for (int qx = 0; qx < N; qx++) {
                     const double xi = P.xq[qx];
                     double cb[3], cc[3];
+                    if (!AFFINE) {
 #pragma unroll
-                    for (int a = 0; a < 3; a++) {
-                        cb[a] = fma(qb[a], xi, pb[a]);     // dx/deta
-                        cc[a] = fma(A6[a], xi, A3[a]);     // dx/dzeta
+                        for (int a = 0; a < 3; a++) {
+                            cb[a] = fma(qb[a], xi, pb[a]);     // dx/deta
+                            cc[a] = fma(A6[a], xi, A3[a]);     // dx/dzeta
+                        }
                     }
                     double gx = 0.0, gz = 0.0;
 #pragma unroll
@@ -550,6 +584,20 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
                         gz = fma(dz[q], U[qx][q], gz);
                     }
                     const double gy = trow[qx * N * N];
+                    if (AFFINE) {
+                        const double wq3 = wyz_a * P.wq[qx];
+                        const double fx = wq3 * (Gm[0] * gx + Gm[1] * gy + Gm[2] * gz);
+                        const double fy = wq3 * (Gm[1] * gx + Gm[3] * gy + Gm[4] * gz);
+                        const double fz = wq3 * (Gm[2] * gx + Gm[4] * gy + Gm[5] * gz);
+                        trow[qx * N * N] = fy;
+#pragma unroll
+                        for (int q = 0; q < N; q++) {
+                            Vp[q][0] = fma(P.Dt[qx * N + q], fx, Vp[q][0]);
+                            Vp[qx][q] = fma(dz[q], fz, Vp[qx][q]);
+                        }
+                        if (MASS) Vp[qx][0] = fma(wyz_b * P.wq[qx] * adet_c, U[qx][0], Vp[qx][0]);
+                        continue;
+                    }
                     // cofactor rows: r0 = b x c, r1 = c x a, r2 = a x b
                     double r0[3], r1[3], r2[3];
                     r0[0] = cb[1] * cc[2] - cb[2] * cc[1];
@@ -680,13 +728,13 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
     cp_async_wait<0>();
 }
 
-template <int N, bool MASS, bool ATOMIC, int MINB, bool MATRIX = false, bool SLIM = false>
+template <int N, bool MASS, bool ATOMIC, int MINB, bool MATRIX = false, bool SLIM = false, bool AFFINE = false>
 int launch_one(int grid_cap_per_sm, cudaStream_t st, HelmParams<N> &P, int sm_count)
 {
     using WS = WarpSmem<N, SLIM>;
     constexpr int WARPS_PER_CTA = WPC<N, SLIM>::value;
     constexpr int T = WARPS_PER_CTA * 32;
-    auto kern = helmholtz_action_kernel<N, MASS, ATOMIC, MINB, MATRIX, SLIM>;
+    auto kern = helmholtz_action_kernel<N, MASS, ATOMIC, MINB, MATRIX, SLIM, AFFINE>;
     static bool configured = false;
     static int occ = 1;
     if (!configured) {
@@ -722,8 +770,18 @@ int launch_one(int grid_cap_per_sm, cudaStream_t st, HelmParams<N> &P, int sm_co
 }
 
 template <int N, bool ATOMIC>
-int launch_variant(bool mass, int minb, int cap, cudaStream_t st, HelmParams<N> &P, int sm_count)
+int launch_variant(bool mass, int minb, int cap, cudaStream_t st, HelmParams<N> &P, int sm_count,
+                   bool affine = false)
 {
+    if (affine && ATOMIC) {
+        // affine cells (caller's promise): per-cell metric; same staging / occupancy choices
+        constexpr int AB = (N == 4) ? 3 : ((N >= 5) ? 1 : 2);
+        constexpr bool ASL = (N == 6);
+        if (!ASL || P.nlay_items >= 32 / N) {
+            if (mass) return launch_one<N, true, true, AB, false, ASL, true>(cap, st, P, sm_count);
+            return launch_one<N, false, true, AB, false, ASL, true>(cap, st, P, sm_count);
+        }
+    }
     if (N == 4 && minb == 3) {
         if (mass) return launch_one<N, true, ATOMIC, (N == 4 ? 3 : 2)>(cap, st, P, sm_count);
         return launch_one<N, false, ATOMIC, (N == 4 ? 3 : 2)>(cap, st, P, sm_count);
@@ -789,7 +847,7 @@ int launch_n(fdb_kernel_s *k, fdb_int start, fdb_int end, int nlay, const fdb_in
         P.lay_first = 0;
         P.lay_step = 1;
         if (P.ncols <= 0 || nlay <= 0) return 0;
-        return launch_variant<N, true>(mass, minb, cap, c.stream, P, c.sm_count);
+        return launch_variant<N, true>(mass, minb, cap, c.stream, P, c.sm_count, k->desc.affine_cells != 0);
     }
     // deterministic: one launch per (colour, layer parity); within a launch no
     // two cells share a dof, so plain read-modify-write is race free and the

@@ -595,6 +595,7 @@ class Kernel:
     integral: str = "cell"          # "cell" | "exterior_facet" | "interior_facet"
     cell: str = "hex"               # "hex" (extruded or native) | "triangle" (affine P1)
     diagonal: bool = False          # rank 1: diagonal of the bilinear form (args: d, coordinates)
+    affine: bool = False            # rank 1 hex: promise that all cells are parallelepipeds (fdb_kernel_desc.affine_cells)
     nq: int = 0                     # 1-D quadrature points (0: the form's default)
     name: str = "form0_cell_integral"
     accesses: tuple = (INC, READ, READ)
@@ -713,6 +714,7 @@ class GlobalKernel:
         d.scatter = {"atomic": _lib.SCATTER_ATOMIC, "coloured": _lib.SCATTER_COLOURED}[self.scatter]
         d.alpha, d.beta = lk.alpha, lk.beta
         d.diagonal = int(lk.diagonal)
+        d.affine_cells = int(lk.affine and lk.rank == 1 and not lk.diagonal)
         for q in range(el.nq):
             d.wq[q] = el.wq[q]
             d.xq[q] = el.xq[q]

@@ -15,3 +15,15 @@ timeout 300 compute-sanitizer --tool racecheck python -m pytest tests/test_jit_g
 tail -5 gpurun_out/first_validation_racecheck.log
 # the validated suite must be unaffected
 python -m pytest tests/ -x -q -m gpu 2>&1 | tail -3
+# affine-cell kernel variant (opt-in): un-warped 256^3 CG3 with and without it
+python bench.py --warp 0 --steps 5 --warmup 3 --no-cpu 2>/dev/null | tail -1 > gpurun_out/bench_unwarped_general.json
+FDB_AFFINE=1 python bench.py --warp 0 --steps 5 --warmup 3 --no-cpu 2>/dev/null | tail -1 > gpurun_out/bench_unwarped_affine.json
+python - <<'PY'
+import json
+for f in ("general", "affine"):
+    try:
+        d = json.loads(open(f"gpurun_out/bench_unwarped_{f}.json").read())
+        print(f, d["ms_per_step"], d["config"].get("kernel_variant"))
+    except Exception as e:
+        print(f, "failed", e)
+PY

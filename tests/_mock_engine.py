@@ -277,6 +277,17 @@ class MockEngine:
         np.add.at(yv, rows, np.einsum("kab,kb->ka", blocks, xv[m.colidx]))
         return 0
 
+    def fdb_cells_are_affine(self, coords, map1, off1, start, end, nlay, result):
+        off = _view(off1, 8, np.int32) if _addr(off1) else np.zeros(8, dtype=np.int32)
+        m = _view(map1, end * 8, np.int32).reshape(end, 8)[start:end]
+        idx = m[:, None, :] + off[None, None, :] * np.arange(nlay)[None, :, None]
+        X = _view(coords, (int(idx.max()) + 1) * 3).reshape(-1, 3)[idx]          # (cols, layers, 8, 3)
+        v = lambda b: X[:, :, b, :]
+        bad = ((v(6) - v(4) - v(2) + v(0)) != 0) | ((v(3) - v(2) - v(1) + v(0)) != 0) | \
+              ((v(5) - v(4) - v(1) + v(0)) != 0) | ((v(7) - v(6) - v(5) - v(3) + v(4) + v(2) + v(1) - v(0)) != 0)
+        _obj(result).value = 0 if bad.any() else 1
+        return 0
+
     # ------------------------------------------------------------------------ kernels
     def fdb_kernel_create(self, desc, out):
         d = _obj(desc)

@@ -79,3 +79,7 @@ def test_zero_forms_host_logic(mock):
 def test_helmholtz_convergence_host_logic(mock):
     tj.test_helmholtz_convergence_rates(mock, 2, (2, 4), 2.9)
     tj.test_helmholtz_convergence_rates(mock, 3, (1, 3), 3.9)
+
+
+def test_affine_variant_host_logic(mock, oracle, monkeypatch):
+    tj.test_affine_cell_variant(mock, oracle, 2, monkeypatch)

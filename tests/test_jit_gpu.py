@@ -360,3 +360,25 @@ def test_interior_facet_functionals(engine):
     # avg(f) over the horizontal facets z = k/5: int 2x + 3y^2 + 4z^3 = 2 + 4 z^3
     ref = sum(2 + 4 * (k / 5) ** 3 for k in range(1, 5))
     assert abs(assemble_functional(V, f, "dS_h") - ref) < 1e-11
+
+
+@pytest.mark.parametrize("p", [1, 2, 3, 4, 5])
+def test_affine_cell_variant(engine, oracle, p, monkeypatch):
+    """The per-cell-metric kernel variant (fdb_kernel_desc.affine_cells) on a mesh of
+    parallelepipeds == the oracle (which evaluates the geometry at every quadrature point),
+    Poisson and Helmholtz; the geometry check refuses a warped mesh."""
+    from firedrake_b200.assemble import FunctionSpace, OneFormAssembler, helmholtz, poisson
+    monkeypatch.setenv("FDB_AFFINE", "1")
+    mesh = ExtrudedHexMesh(4, 3, 8, Lx=2.0, Ly=0.75, Lz=1.0, permute_seed=1)
+    V = FunctionSpace(mesh, p)
+    assert V.cells_are_affine()
+    assert not FunctionSpace(ExtrudedHexMesh(4, 3, 8, warp=0.05), p).cells_are_affine()
+    x = V.dat(np.random.default_rng(9).standard_normal(V.node_count))
+    for form, (alpha, beta) in ((poisson(V), (1.0, 0.0)), (helmholtz(V), (1.0, 1.0))):
+        assert form.kernel(1).affine
+        y = OneFormAssembler(form, x).assemble()
+        yo = np.zeros(V.node_count)
+        oracle.action_extruded(interval_element(p), 0, mesh.num_base_cells, [0, mesh.layers], yo, mesh.coordinates,
+                               x.data_ro.copy(), V.V.cell_node_map, V.V.offset, mesh.coord_map, mesh.coord_offset,
+                               1, alpha, beta)
+        assert np.abs(y.data_ro - yo).max() < 1e-12 * np.abs(yo).max()
