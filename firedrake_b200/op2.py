@@ -398,6 +398,44 @@ class Dat:
     def norm(self):
         return float(np.sqrt(self.inner(self)))
 
+    # in-place algebra on the device (pyop2/types/dat.py:312-352 copy, :354-540 _iop / maxpy)
+    def copy(self, other, subset=None):
+        """``other <- self`` (note the direction: pyop2/types/dat.py:312-330)."""
+        if subset is not None:
+            raise NotImplementedError("copy on a subset")
+        if other.nbytes != self.nbytes:
+            raise ValueError("copy between Dats of different sizes")
+        _lib.check(_lib.lib().fdb_memcpy_d2d(other.device_ptr, self.device_ptr, self.nbytes), "d2d")
+        other._device_written()
+        other.halo_valid = self.halo_valid
+
+    def __iadd__(self, other):
+        if not isinstance(other, Dat):
+            return NotImplemented
+        self.axpy(1.0, other)
+        return self
+
+    def __isub__(self, other):
+        if not isinstance(other, Dat):
+            return NotImplemented
+        self.axpy(-1.0, other)
+        return self
+
+    def __imul__(self, other):
+        L = _lib.lib()
+        if isinstance(other, Dat):
+            _lib.check(L.fdb_vec_pointwise_mult(self._data.size, self.device_ptr, other.device_ptr,
+                                                self.device_ptr), "pointwise_mult")
+        else:
+            _lib.check(L.fdb_vec_scale(self._data.size, float(other), self.device_ptr), "scale")
+        self._device_written()
+        return self
+
+    def maxpy(self, scalars, dats):
+        """``self += sum_i scalars[i] * dats[i]`` (pyop2/types/dat.py:509-540)."""
+        for a, d in zip(scalars, dats):
+            self.axpy(a, d)
+
     def __call__(self, access, path=None):
         """Legacy parloop argument ``dat(op2.INC, map)`` (pyop2/parloop.py:709-743)."""
         return LegacyArg(self, access, path)

@@ -83,3 +83,27 @@ def test_helmholtz_convergence_host_logic(mock):
 
 def test_affine_variant_host_logic(mock, oracle, monkeypatch):
     tj.test_affine_cell_variant(mock, oracle, 2, monkeypatch)
+
+
+def test_dat_algebra_host_logic(mock):
+    """Dat.copy / += / -= / *= / maxpy (pyop2/types/dat.py:312-540) keep host and device copies and
+    dat_version consistent."""
+    from firedrake_b200 import op2
+    s = op2.Set(50)
+    rng = np.random.default_rng(0)
+    a0, b0 = rng.standard_normal(50), rng.standard_normal(50)
+    a, b, c = op2.Dat(s, a0.copy()), op2.Dat(s, b0.copy()), op2.Dat(s)     # Dat wraps the array it is given
+    v = a.dat_version
+    a += b
+    assert a.dat_version > v and np.allclose(a.data_ro, a0 + b0)
+    a -= b
+    a *= 3.0
+    a *= b
+    assert np.allclose(a.data_ro, 3 * a0 * b0)
+    a.copy(c)
+    assert np.allclose(c.data_ro, a.data_ro)
+    c.maxpy([2.0, -1.0], [a, b])
+    assert np.allclose(c.data_ro, 3 * (3 * a0 * b0) - b0)
+    c.data[:] = 1.0                                   # host write, then device op must see it
+    c += b
+    assert np.allclose(c.data_ro, 1 + b0)
