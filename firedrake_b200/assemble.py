@@ -425,8 +425,8 @@ class OneFormAssembler:
 
 def assemble(form: Form, u=None, tensor=None, bcs=(), mat_type="aij"):
     """``assemble(action(a, u))`` when ``u`` is given (-> Dat), else the
-    bilinear form: ``mat_type="aij"`` -> :class:`op2.Mat`, ``"matfree"`` ->
-    :class:`ImplicitMatrixContext`."""
+    bilinear form: ``mat_type="aij"`` -> :class:`op2.Mat`, ``"is"`` -> :class:`ISMat` (distributed,
+    unassembled), ``"matfree"`` -> :class:`ImplicitMatrixContext`."""
     V = form.V
     bcs = tuple(bcs)
     if u is not None:
@@ -453,10 +453,41 @@ def assemble(form: Form, u=None, tensor=None, bcs=(), mat_type="aij"):
     op2.par_loop(form.kernel(2), V.cell_set,
                  tensor(op2.INC, (V.cell_node_map, V.cell_node_map), lgmaps=lg),
                  V.coordinates(op2.READ, V.coord_map))
+    owned = V.node_set.size
     for bc in bcs:
-        tensor.set_local_diagonal_entries(bc.nodes, 1.0)
+        # on a partitioned space a constrained node gets its unit diagonal from its OWNER only:
+        # the ghost copies' rows stay empty and add nothing in the local->global sum of ISMat.mult
+        rows = bc.nodes[bc.nodes < owned] if mat_type == "is" else bc.nodes
+        tensor.set_local_diagonal_entries(rows, 1.0)
     tensor.assemble()
+    if mat_type == "is":
+        return ISMat(V, tensor)
+    if V.dof_dset.halo is not None:
+        raise NotImplementedError("assembled matrices on a partitioned space are mat_type='is' "
+                                  "(unassembled, one block per GPU) or 'matfree'")
     return tensor
+
+
+class ISMat:
+    """``mat_type="is"``: the distributed matrix kept UNASSEMBLED, A = sum_r R_r^T A_r R_r with A_r the
+    matrix of rank r's owned cells over its owned + ghost dofs (PETSc MATIS, which the reference supports:
+    firedrake/assemble.py:1330-1345, pyop2/types/mat.py:930-933).  No matrix entries ever cross GPUs (the
+    reference's MatAssembly stash exchange, SURVEY.md section 2.3 C4, disappears); ``mult`` is a local
+    SpMV followed by the local->global halo sum that vectors use anyway."""
+
+    def __init__(self, V: FunctionSpace, local: op2.Mat):
+        self.V, self.local = V, local
+
+    def mult(self, X: op2.Dat, Y: op2.Dat):
+        halo = self.V.dof_dset.halo
+        if halo is not None and not X.halo_valid:
+            halo.global_to_local_begin(X)
+            halo.global_to_local_end(X)
+        self.local.mult(X, Y)
+        if halo is not None:
+            halo.local_to_global_begin(Y)
+            halo.local_to_global_end(Y)
+        return Y
 
 
 class ImplicitMatrixContext:

@@ -61,6 +61,21 @@ def _worker(rank, world, port, q):
         op2.par_loop(op2.Kernel(tc.Q1_POISSON, "q1_poisson"), V.cell_set, yg(op2.INC, V.cell_node_map),
                      V.coordinates(op2.READ, V.coord_map), u2(op2.READ, V.cell_node_map))
         out["generic"] = float(np.abs(yg.data_ro[:no] - np.array([look_gen[k] for k in key(lat[:no]).tolist()])).max())
+        # explicit distributed matrix, kept unassembled (mat_type="is"): SpMV == serial assembled SpMV,
+        # with Dirichlet conditions on the top face (constrained nodes on the slab interfaces included)
+        from firedrake_b200.assemble import DirichletBC, assemble
+        eng.dist = None
+        gA = assemble(helmholtz(G), bcs=[DirichletBC(G, 0.0, "top")])
+        gz = G.dat()
+        gA.mult(gu, gz)
+        look_mat = dict(zip(key(glat).tolist(), gz.data_ro.tolist()))
+        eng.dist = dist
+        A = assemble(helmholtz(V), bcs=[DirichletBC(V, 0.0, "top")], mat_type="is")
+        u3 = interpolate(V, expr)
+        z = V.dat()
+        z.device_ptr
+        A.mult(u3, z)
+        out["ismat"] = float(np.abs(z.data_ro[:no] - np.array([look_mat[k] for k in key(lat[:no]).tolist()])).max())
         out["dx"] = abs(assemble_functional(V, u2, "dx") - ref["dx"])
         out["ds"] = abs(assemble_functional(V, u2, "ds") - ref["ds"])
         out["scale"] = float(np.abs(gy.data_ro).max())
@@ -85,4 +100,5 @@ def test_distributed_generic_parloops(world):
     for rank, out in res:
         assert out["fast"] < 1e-12 * out["scale"], (rank, out)
         assert out["generic"] < 1e-12 * out["scale"], (rank, out)
+        assert out["ismat"] < 1e-12 * out["scale"], (rank, out)
         assert out["dx"] < 1e-12 and out["ds"] < 1e-12, (rank, out)
