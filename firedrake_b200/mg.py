@@ -195,7 +195,9 @@ class TransferManager:
     def weight(self):
         """1 / multiplicity of every fine node in the coarse-cell lattices (scalar Dat)."""
         if self._weight is None:
-            w = op2.Dat(self.Vf.node_set)
+            # scalar field on the fine nodes, sharing the fine space's halo: the counts of nodes on
+            # a slab interface are summed into their owner and sent back to the ghost copies
+            w = op2.Dat(op2.DataSet(self.Vf.node_set, 1, halo=self.Vf.dof_dset.halo))
             m3 = (2 * self.Vc.degree + 1) ** 3
             count = CStringKernel(f"static void count(double *w) {{ for (int i = 0; i < {m3}; ++i) w[i] += 1.0; }}",
                                   "count")
@@ -235,15 +237,46 @@ def inject(fine, coarse, manager):
     return manager.inject(fine, coarse)
 
 
+def _touched(*dats):
+    """Vector algebra ran over the local entries: owned rows are right, ghost rows are not
+    (pyop2/types/dat.py:622-678: any write invalidates the halo)."""
+    for d in dats:
+        d._device_written()
+        d.halo_valid = False
+
+
 # --------------------------------------------------------------------- V-cycle
 class MeshHierarchy:
     """``ExtrudedMeshHierarchy`` of uniformly refined extruded hex meshes
     (firedrake/mg/mesh.py:190-260): level l has 2^l times the coarse resolution in
     every direction."""
 
-    def __init__(self, nx, ny, nz, levels, **mesh_kwargs):
+    def __init__(self, nx, ny, nz, levels, rank=0, nranks=1, **mesh_kwargs):
+        """``rank`` / ``nranks``: this process's slab of every level (firedrake_b200.partition); the
+        coarse slab bounds must refine exactly (``nx`` divisible by ``nranks``) so that every
+        coarse cell's children live on the same rank, as in a refined DMPlex distribution."""
         from .utility_meshes import ExtrudedHexMesh
+        self.partitions = None
+        if nranks > 1:
+            if nx % nranks:
+                raise ValueError("coarse nx must be divisible by the number of ranks")
+            self.nranks, self.rank = nranks, rank
+            self._sizes = [(nx << l, ny << l, nz << l) for l in range(levels + 1)]
+            self._kwargs = mesh_kwargs
+            self.partitions = {}
+            self.meshes = [None] * (levels + 1)
+            return
         self.meshes = [ExtrudedHexMesh(nx << l, ny << l, nz << l, **mesh_kwargs) for l in range(levels + 1)]
+
+    def partition(self, level, degree):
+        """SlabPartition of ``level`` for function spaces of ``degree`` (built on demand)."""
+        from .partition import SlabPartition
+        key = (level, degree)
+        if key not in self.partitions:
+            nx, ny, nz = self._sizes[level]
+            self.partitions[key] = SlabPartition(nx, ny, nz, degree, self.rank, self.nranks, **self._kwargs)
+            self.meshes[level] = self.partitions[key].mesh
+        return self.partitions[key]
 
     def __len__(self):
         return len(self.meshes)
@@ -260,9 +293,15 @@ class VCycle:
     coarsest level solved by CG.  Everything stays on the device."""
 
     def __init__(self, hierarchy, degree, make_form, bc_domains=(), nu=2, omega=0.8,
-                 coarse_rtol=1e-2, coarse_maxit=200):
+                 coarse_rtol=1e-2, coarse_maxit=200, allreduce=None):
+        """``allreduce``: callable summing a float over the ranks (partitioned hierarchies)."""
         from .assemble import DirichletBC, FunctionSpace, assemble
-        self.spaces = [FunctionSpace(m, degree) for m in hierarchy.meshes]
+        self.allreduce = allreduce
+        if hierarchy.partitions is None:
+            self.spaces = [FunctionSpace(m, degree) for m in hierarchy.meshes]
+        else:
+            parts = [hierarchy.partition(l, degree) for l in range(len(hierarchy))]
+            self.spaces = [FunctionSpace(pt.mesh, degree, partition=pt) for pt in parts]
         self.bcs = [[DirichletBC(V, 0.0, s) for s in bc_domains] for V in self.spaces]
         self.ops = [assemble(make_form(V), bcs=b, mat_type="matfree") for V, b in zip(self.spaces, self.bcs)]
         self.transfers = [TransferManager(self.spaces[l], self.spaces[l + 1]) for l in range(len(self.spaces) - 1)]
@@ -290,9 +329,9 @@ class VCycle:
             _lib.check(L.fdb_vec_aypx(n, -1.0, b.device_ptr, w["t"].device_ptr))        # t = b - A x
             _lib.check(L.fdb_vec_pointwise_mult(n, w["t"].device_ptr, self.invdiag[l].device_ptr,
                                                 w["t"].device_ptr))
-            w["t"]._device_written()
+            _touched(w["t"])
             _lib.check(L.fdb_vec_axpy(n, self.omega, w["t"].device_ptr, x.device_ptr))
-            x._device_written()
+            _touched(x)
 
     def apply(self, l, b, x):
         """One V-cycle on level l for A x = b, starting from the x passed in."""
@@ -302,12 +341,13 @@ class VCycle:
         A, w = self.ops[l], self._work[l]
         n = b._data.size
         if l == 0:
-            cg(A, b, x, rtol=self.coarse_rtol, maxit=self.coarse_maxit)
+            cg(A, b, x, rtol=self.coarse_rtol, maxit=self.coarse_maxit, allreduce=self.allreduce)
+            _touched(x)
             return x
         self._smooth(l, b, x)
         A.mult(x, w["r"])
         _lib.check(L.fdb_vec_aypx(n, -1.0, b.device_ptr, w["r"].device_ptr))             # r = b - A x
-        w["r"]._device_written()
+        _touched(w["r"])
         for bc in self.bcs[l]:
             bc.zero(w["r"])
         wc = self._work[l - 1]
@@ -322,43 +362,52 @@ class VCycle:
         for bc in self.bcs[l]:
             bc.zero(w["e"])
         _lib.check(L.fdb_vec_axpy(n, 1.0, w["e"].device_ptr, x.device_ptr))
-        x._device_written()
+        _touched(x)
         self._smooth(l, b, x)
         return x
 
 
-def pcg(A, b, x, M, rtol=1e-8, maxit=200):
+def pcg(A, b, x, M, rtol=1e-8, maxit=200, allreduce=None):
     """Preconditioned CG (``ksp_type cg`` with a multigrid ``pc``): ``M(r, z)`` applies the
-    preconditioner (e.g. ``lambda r, z: vcycle.apply(top, r, z)`` from z = 0)."""
+    preconditioner (e.g. ``lambda r, z: vcycle.apply(top, r, z)`` from z = 0).  ``allreduce``:
+    callable summing a float over the ranks; inner products then run over the OWNED dofs."""
+    import ctypes as C
     from . import _lib
     L = _lib.lib()
     V = b.dataset
     r, z, p, Ap = (op2.Dat(V) for _ in range(4))
     n = b._data.size
+    n_owned = b.dataset.set.size * b.cdim
+
+    def dot(u, v):
+        out = C.c_double()
+        _lib.check(L.fdb_vec_dot(n_owned, u.device_ptr, v.device_ptr, C.byref(out)))
+        return allreduce(out.value) if allreduce else out.value
     A.mult(x, Ap)
     _lib.check(L.fdb_memcpy_d2d(r.device_ptr, b.device_ptr, b.nbytes))
     r._device_written()
     _lib.check(L.fdb_vec_axpy(n, -1.0, Ap.device_ptr, r.device_ptr))
-    r0 = r.norm()
+    _touched(r)
+    r0 = np.sqrt(dot(r, r))
     hist = [r0]
     z.zero(); z.device_ptr
     M(r, z)
     _lib.check(L.fdb_memcpy_d2d(p.device_ptr, z.device_ptr, z.nbytes))
     p._device_written()
-    rz = r.inner(z)
+    rz = dot(r, z)
     it = 0
     while it < maxit and hist[-1] > rtol * r0:
         A.mult(p, Ap)
-        alpha = rz / p.inner(Ap)
+        alpha = rz / dot(p, Ap)
         _lib.check(L.fdb_vec_axpy(n, alpha, p.device_ptr, x.device_ptr))
         _lib.check(L.fdb_vec_axpy(n, -alpha, Ap.device_ptr, r.device_ptr))
-        x._device_written(); r._device_written()
-        hist.append(r.norm())
+        _touched(x, r)
+        hist.append(np.sqrt(dot(r, r)))
         z.zero(); z.device_ptr
         M(r, z)
-        rz_new = r.inner(z)
+        rz_new = dot(r, z)
         _lib.check(L.fdb_vec_aypx(n, rz_new / rz, z.device_ptr, p.device_ptr))            # p = z + beta p
-        p._device_written()
+        _touched(p)
         rz = rz_new
         it += 1
     return it, hist

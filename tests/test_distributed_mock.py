@@ -102,3 +102,76 @@ def test_distributed_generic_parloops(world):
         assert out["generic"] < 1e-12 * out["scale"], (rank, out)
         assert out["ismat"] < 1e-12 * out["scale"], (rank, out)
         assert out["dx"] < 1e-12 and out["ds"] < 1e-12, (rank, out)
+
+
+def _mg_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import _mock_engine as me
+    from firedrake_b200 import mg
+    from firedrake_b200.assemble import helmholtz
+    from oracle import oracle
+
+    def allreduce(v):
+        t = torch.tensor([v], dtype=torch.float64)
+        dist.all_reduce(t)
+        return float(t.item())
+
+    nx = 2 * world
+    rhs = lambda P: np.sin(3.0 * P[:, 0]) * (1 + P[:, 1]) + P[:, 2] ** 2
+    with me.install(oracle) as eng:
+        # serial reference (no communication)
+        eng.dist = None
+        h = mg.MeshHierarchy(nx, 4, 4, 2, warp=0.03)
+        vc = mg.VCycle(h, 1, helmholtz, bc_domains=("bottom",), coarse_rtol=1e-10)
+        V, A = vc.spaces[2], vc.ops[2]
+        b = V.dat(rhs(V.V.dof_coordinates()))
+        for bc in vc.bcs[2]:
+            bc.zero(b)
+        x = V.dat()
+        x.device_ptr
+        n_serial, _ = mg.pcg(A, b, x, lambda r, z: vc.apply(2, r, z), rtol=1e-9)
+        key = lambda L: (L[:, 0] * 1000 + L[:, 1]) * 1000 + L[:, 2]
+        look = dict(zip(key(V.V.dof_lattice()).tolist(), x.data_ro.tolist()))
+        # the same hierarchy cut into slabs
+        eng.dist = dist
+        hp = mg.MeshHierarchy(nx, 4, 4, 2, rank=rank, nranks=world, warp=0.03)
+        vp = mg.VCycle(hp, 1, helmholtz, bc_domains=("bottom",), coarse_rtol=1e-10, allreduce=allreduce)
+        W, B = vp.spaces[2], vp.ops[2]
+        bp = W.dat(rhs(W.V.dof_coordinates()))
+        for bc in vp.bcs[2]:
+            bc.zero(bp)
+        xp = W.dat()
+        xp.device_ptr
+        n_par, hist = mg.pcg(B, bp, xp, lambda r, z: vp.apply(2, r, z), rtol=1e-9, allreduce=allreduce)
+        no = W.V.owned_node_count
+        ref = np.array([look[k] for k in key(W.V.dof_lattice()[:no]).tolist()])
+        err = float(np.abs(xp.data_ro[:no] - ref).max() / np.abs(ref).max())
+    q.put((rank, n_serial, n_par, err))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_distributed_multigrid(world):
+    """The V-cycle on a slab-partitioned hierarchy (transfers through ghost rows, restricted
+    residuals summed into their owners, all-reduced inner products) converges like the serial one
+    and to the same solution."""
+    from oracle import oracle
+    oracle.build()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_mg_worker, args=(r, world, port, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    res = [q.get(timeout=600) for _ in range(world)]
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    for rank, n_serial, n_par, err in res:
+        assert abs(n_par - n_serial) <= 1, res
+        assert err < 1e-7, res
