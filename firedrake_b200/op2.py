@@ -384,6 +384,9 @@ class Dat:
         n = self._data.size
         _lib.check(fn(n, *scalars, other.device_ptr, self.device_ptr))
         self._device_written()
+        # the algebra ran over every local row, but `other`'s ghost rows need not be current
+        # (pyop2/types/dat.py:622-678: a write invalidates the halo)
+        self.halo_valid = self.halo_valid and other.halo_valid
 
     def axpy(self, alpha, other):
         """self += alpha * other"""
@@ -426,6 +429,7 @@ class Dat:
         if isinstance(other, Dat):
             _lib.check(L.fdb_vec_pointwise_mult(self._data.size, self.device_ptr, other.device_ptr,
                                                 self.device_ptr), "pointwise_mult")
+            self.halo_valid = self.halo_valid and other.halo_valid
         else:
             _lib.check(L.fdb_vec_scale(self._data.size, float(other), self.device_ptr), "scale")
         self._device_written()
