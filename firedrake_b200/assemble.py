@@ -336,6 +336,7 @@ class DirichletBC:
     def __init__(self, V: FunctionSpace, g, sub_domain):
         self.V = V
         subs = sub_domain if isinstance(sub_domain, (list, tuple)) else [sub_domain]
+        self.sub_domains = tuple(subs)
         nodes = np.unique(np.concatenate([V.boundary_nodes(s) for s in subs])).astype(np.int32)
         self.nodes = nodes
         self.node_set = op2.Subset(V.node_set, nodes)
@@ -577,6 +578,74 @@ def cg(A, b: op2.Dat, x: op2.Dat, rtol=1e-8, atol=0.0, maxit=1000, allreduce=Non
         it += 1
     x._device_written()
     return it, hist
+
+
+def solve(form: Form, L: op2.Dat, u: op2.Dat, bcs=(), solver_parameters=None, hierarchy=None, allreduce=None):
+    """``solve(a == L, u, bcs=bcs, solver_parameters=...)`` for the supported forms
+    (firedrake/solving.py:128-260 -> LinearVariationalSolver): assemble the
+    operator, lift the Dirichlet values, run the Krylov solver on the device.
+
+    ``L``: the assembled right-hand side (a Dat, e.g. ``assemble(mass(V), u=f)``).
+    ``solver_parameters`` (PETSc option names, the subset that makes sense here):
+    ``mat_type`` "matfree" (default) | "aij" | "is"; ``ksp_type`` "cg"; ``pc_type`` "none" (default) |
+    "jacobi" | "mg" (needs ``hierarchy``, a mg.MeshHierarchy whose finest mesh is ``form.V.mesh``);
+    ``ksp_rtol`` (1e-8), ``ksp_max_it`` (1000).  Returns (iterations, residual history)."""
+    from . import _lib
+    sp = {"mat_type": "matfree", "ksp_type": "cg", "pc_type": "none", "ksp_rtol": 1e-8, "ksp_max_it": 1000}
+    sp.update(solver_parameters or {})
+    if sp["ksp_type"] != "cg":
+        raise NotImplementedError("ksp_type cg only (the supported forms are symmetric positive definite)")
+    V = form.V
+    bcs = tuple(bcs)
+    lib = _lib.lib()
+    n = L._data.size
+    # lifting (firedrake/assemble.py:1243-1254 + linear solver's rhs): u = g on the constrained nodes,
+    # solve A (u - g) = L - K g on the free rows with homogeneous conditions
+    g = V.dat()
+    g.device_ptr
+    for bc in bcs:
+        bc.apply(g)
+    lift = any(not (np.isscalar(bc.g) and bc.g == 0.0) for bc in bcs)
+    b = V.dat()
+    L.copy(b)
+    if lift:
+        Kg = OneFormAssembler(form, g, ()).assemble()
+        b.axpy(-1.0, Kg)
+    for bc in bcs:
+        bc.zero(b)
+    A = assemble(form, bcs=bcs, mat_type=sp["mat_type"])
+    u.zero()
+    u.device_ptr
+    pc = sp["pc_type"]
+    if pc == "none":
+        its, hist = cg(A, b, u, rtol=sp["ksp_rtol"], maxit=sp["ksp_max_it"], allreduce=allreduce)
+    else:
+        from . import mg as _mg
+        if pc == "jacobi":
+            ctx = A if isinstance(A, ImplicitMatrixContext) else ImplicitMatrixContext(form, bcs)
+            d = ctx.getDiagonal(V.dat())
+            op2.par_loop(op2.Kernel("static void recip(double *w) { *w = 1.0 / *w; }", "recip"), V.node_set,
+                         d(op2.RW))
+
+            def M(r, z):
+                _lib.check(lib.fdb_vec_pointwise_mult(n, r.device_ptr, d.device_ptr, z.device_ptr))
+                z._device_written()
+        elif pc == "mg":
+            if hierarchy is None:
+                raise ValueError("pc_type mg needs the mesh hierarchy")
+            vc = _mg.VCycle(hierarchy, V.degree, lambda W: Form(W, form.alpha, form.beta),
+                            bc_domains=tuple(s for bc in bcs for s in bc.sub_domains), allreduce=allreduce)
+            top = len(hierarchy) - 1
+            M = lambda r, z: vc.apply(top, r, z)
+        else:
+            raise NotImplementedError(f"pc_type {pc!r}")
+        its, hist = _mg.pcg(A, b, u, M, rtol=sp["ksp_rtol"], maxit=sp["ksp_max_it"], allreduce=allreduce)
+    if lift:
+        u.axpy(1.0, g)
+    else:
+        for bc in bcs:
+            bc.apply(u)
+    return its, hist
 
 
 class DGAdvection:

@@ -107,3 +107,8 @@ def test_dat_algebra_host_logic(mock):
     c.data[:] = 1.0                                   # host write, then device op must see it
     c += b
     assert np.allclose(c.data_ro, 1 + b0)
+
+
+@pytest.mark.parametrize("pc", ["none", "jacobi", "mg"])
+def test_solve_front_end_host_logic(mock, pc):
+    tj.test_solve_front_end(mock, pc)

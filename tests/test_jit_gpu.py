@@ -382,3 +382,21 @@ def test_affine_cell_variant(engine, oracle, p, monkeypatch):
                                x.data_ro.copy(), V.V.cell_node_map, V.V.offset, mesh.coord_map, mesh.coord_offset,
                                1, alpha, beta)
         assert np.abs(y.data_ro - yo).max() < 1e-12 * np.abs(yo).max()
+
+
+@pytest.mark.parametrize("pc", ["none", "jacobi", "mg"])
+def test_solve_front_end(engine, pc):
+    """solve(a == L, u, bcs, solver_parameters) (firedrake/solving.py): the reference's
+    strong-BC Poisson problem (tests/firedrake/extrusion/test_poisson_strong_bcs_extrusion.py:
+    u = 0 on the bottom, 42 on the top, exact solution 42 z) with each preconditioner."""
+    from firedrake_b200 import mg
+    from firedrake_b200.assemble import DirichletBC, FunctionSpace, poisson, solve
+    h = mg.MeshHierarchy(2, 2, 2, 2)
+    V = FunctionSpace(h[2], 2)
+    bcs = [DirichletBC(V, 0.0, "bottom"), DirichletBC(V, 42.0, "top")]
+    u = V.dat()
+    its, hist = solve(poisson(V), V.dat(), u, bcs=bcs, hierarchy=h,
+                      solver_parameters={"pc_type": pc, "ksp_rtol": 1e-12})
+    z = V.V.dof_coordinates()[:, 2]
+    assert np.abs(u.data_ro - 42.0 * z).max() < 1e-7, (pc, its, hist[-1])
+    assert its < {"none": 200, "jacobi": 200, "mg": 15}[pc]
