@@ -262,6 +262,106 @@ static void {name}(double *out, const double *X, const double *f{", " + sig if s
     return CStringKernel(code, name)
 
 
+def variable_coefficient_kernel(degree, beta=0.0, name="varcoef_action"):
+    """C source of the 1-form ``action(inner(kappa*grad(u), grad(v))*dx + beta*inner(u, v)*dx, u)``
+    with a COEFFICIENT FIELD kappa in the same Q_p (x) P_p space -- a form outside the hand-written
+    set, written the way TSFC's spectral mode would (sum factorisation, tsfc/spectral.py:24-191;
+    coefficients are tabulated like arguments, tsfc/fem.py:710-804) and run through the generic
+    wrapper builder.  Arguments: y (INC), coords, u, kappa."""
+    from .fiat_lite import interval_element
+    from .codegen import CStringKernel
+    el = interval_element(degree)
+    n = degree + 1
+    tab = lambda a: "{" + ", ".join("{" + ", ".join(repr(float(v)) for v in r) + "}" for r in a) + "}"
+    vec = lambda a: "{" + ", ".join(repr(float(v)) for v in a) + "}"
+    code = f"""
+#define VN {n}
+static const double VB[VN][VN] = {tab(el.B)};      /* VB[q][a] */
+static const double VD[VN][VN] = {tab(el.D)};      /* VD[q][a] */
+static const double VX[VN] = {vec(el.xq)};
+static const double VW[VN] = {vec(el.wq)};
+/* out = (T applied along direction dir) in;  tr = 0: out[q] = sum_a T[q][a] in[a];  tr = 1: transpose */
+static inline void vc_apply(const double T[VN][VN], int dir, int tr, const double *in, double *out)
+{{
+    const int st = dir == 0 ? VN * VN : (dir == 1 ? VN : 1);
+    for (int i = 0; i < VN * VN * VN; ++i) {{
+        const int k = (i / st) % VN, base = i - k * st;
+        double s = 0.0;
+        for (int a = 0; a < VN; ++a) s += (tr ? T[a][k] : T[k][a]) * in[base + a * st];
+        out[i] = s;
+    }}
+}}
+static inline void vc_tensor(const double (*T0)[VN], const double (*T1)[VN], const double (*T2)[VN], int tr,
+                             const double *in, double *out)
+{{
+    double t1[VN * VN * VN], t2[VN * VN * VN];
+    vc_apply(T0, 0, tr, in, t1);
+    vc_apply(T1, 1, tr, t1, t2);
+    vc_apply(T2, 2, tr, t2, out);
+}}
+static void {name}(double *y, const double *X, const double *u, const double *kappa)
+{{
+    double U[VN * VN * VN], G[3][VN * VN * VN], K[VN * VN * VN], t[VN * VN * VN];
+    vc_tensor(VB, VB, VB, 0, u, U);
+    vc_tensor(VD, VB, VB, 0, u, G[0]);
+    vc_tensor(VB, VD, VB, 0, u, G[1]);
+    vc_tensor(VB, VB, VD, 0, u, G[2]);
+    vc_tensor(VB, VB, VB, 0, kappa, K);
+    for (int qx = 0; qx < VN; ++qx) for (int qy = 0; qy < VN; ++qy) for (int qz = 0; qz < VN; ++qz) {{
+        const int q = (qx * VN + qy) * VN + qz;
+        const double xi[3] = {{VX[qx], VX[qy], VX[qz]}};
+        double J[3][3] = {{{{0}}}};
+        for (int v = 0; v < 8; ++v) {{
+            const int b[3] = {{(v >> 2) & 1, (v >> 1) & 1, v & 1}};
+            for (int d = 0; d < 3; ++d) {{
+                double g = b[d] ? 1.0 : -1.0;
+                for (int e = 0; e < 3; ++e) if (e != d) g *= b[e] ? xi[e] : 1.0 - xi[e];
+                for (int c = 0; c < 3; ++c) J[c][d] += X[v * 3 + c] * g;
+            }}
+        }}
+        double R[3][3];                              /* cofactor rows: R[k] . J[:, m] = det * delta_km */
+        R[0][0] = J[1][1] * J[2][2] - J[2][1] * J[1][2]; R[0][1] = J[2][1] * J[0][2] - J[0][1] * J[2][2];
+        R[0][2] = J[0][1] * J[1][2] - J[1][1] * J[0][2];
+        R[1][0] = J[1][2] * J[2][0] - J[2][2] * J[1][0]; R[1][1] = J[2][2] * J[0][0] - J[0][2] * J[2][0];
+        R[1][2] = J[0][2] * J[1][0] - J[1][2] * J[0][0];
+        R[2][0] = J[1][0] * J[2][1] - J[2][0] * J[1][1]; R[2][1] = J[2][0] * J[0][1] - J[0][0] * J[2][1];
+        R[2][2] = J[0][0] * J[1][1] - J[1][0] * J[0][1];
+        const double det = J[0][0] * R[0][0] + J[1][0] * R[0][1] + J[2][0] * R[0][2];
+        const double w = VW[qx] * VW[qy] * VW[qz];
+        double h[3], f[3];
+        for (int c = 0; c < 3; ++c) h[c] = R[0][c] * G[0][q] + R[1][c] * G[1][q] + R[2][c] * G[2][q];
+        for (int k = 0; k < 3; ++k)
+            f[k] = K[q] * w / fabs(det) * (R[k][0] * h[0] + R[k][1] * h[1] + R[k][2] * h[2]);
+        G[0][q] = f[0]; G[1][q] = f[1]; G[2][q] = f[2];
+        U[q] *= {float(beta)!r} * w * fabs(det);
+    }}
+    vc_tensor(VD, VB, VB, 1, G[0], t);  for (int i = 0; i < VN * VN * VN; ++i) y[i] += t[i];
+    vc_tensor(VB, VD, VB, 1, G[1], t);  for (int i = 0; i < VN * VN * VN; ++i) y[i] += t[i];
+    vc_tensor(VB, VB, VD, 1, G[2], t);  for (int i = 0; i < VN * VN * VN; ++i) y[i] += t[i];
+    vc_tensor(VB, VB, VB, 1, U, t);     for (int i = 0; i < VN * VN * VN; ++i) y[i] += t[i];
+}}
+#undef VN
+"""
+    return CStringKernel(code, name)
+
+
+def assemble_variable_coefficient(V: "FunctionSpace", kappa: op2.Dat, u: op2.Dat, beta=0.0, tensor=None, bcs=()):
+    """``assemble(action(inner(kappa*grad(u), grad(v))*dx + beta*inner(u, v)*dx, u))`` for a scalar
+    coefficient field ``kappa`` in V (generic path)."""
+    if V.cdim != 1:
+        raise NotImplementedError("scalar spaces only")
+    if tensor is None:
+        tensor = V.dat()
+    tensor.zero()
+    tensor.device_ptr
+    op2.par_loop(variable_coefficient_kernel(V.degree, beta), V.cell_set, tensor(op2.INC, V.cell_node_map),
+                 V.coordinates(op2.READ, V.coord_map), u(op2.READ, V.cell_node_map),
+                 kappa(op2.READ, V.cell_node_map))
+    for bc in bcs:
+        bc.zero(tensor)
+    return tensor
+
+
 def assemble_functional(V: "FunctionSpace", f: op2.Dat, measure="dx", integrand="avg"):
     """``assemble(f*dx)`` / ``assemble(f*ds_b)`` / ``ds_t`` / ``ds_v`` / ``ds`` for a scalar
     ``f`` in V: rank-0 parloops with a Global INC argument (firedrake/assemble.py

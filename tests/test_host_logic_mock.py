@@ -112,3 +112,7 @@ def test_dat_algebra_host_logic(mock):
 @pytest.mark.parametrize("pc", ["none", "jacobi", "mg"])
 def test_solve_front_end_host_logic(mock, pc):
     tj.test_solve_front_end(mock, pc)
+
+
+def test_variable_coefficient_host_logic(mock, oracle):
+    tj.test_variable_coefficient_form(mock, oracle)

@@ -400,3 +400,22 @@ def test_solve_front_end(engine, pc):
     z = V.V.dof_coordinates()[:, 2]
     assert np.abs(u.data_ro - 42.0 * z).max() < 1e-7, (pc, its, hist[-1])
     assert its < {"none": 200, "jacobi": 200, "mg": 15}[pc]
+
+
+def test_variable_coefficient_form(engine, oracle):
+    """inner(kappa*grad u, grad v)*dx with a coefficient field, generic path: kappa == 1 must
+    equal the hand-written Poisson kernel; kappa = 2 + x must equal 2*Poisson + the x-weighted part
+    (linearity in kappa)."""
+    from firedrake_b200.assemble import (FunctionSpace, OneFormAssembler, assemble_variable_coefficient,
+                                         interpolate, poisson)
+    mesh = ExtrudedHexMesh(4, 3, 5, warp=0.05, permute_seed=2)
+    V = FunctionSpace(mesh, 2)
+    u = V.dat(np.random.default_rng(0).standard_normal(V.node_count))
+    one, xk, kap = interpolate(V, "1.0"), interpolate(V, "x[0]"), interpolate(V, "2.0 + x[0]")
+    y1 = assemble_variable_coefficient(V, one, u)
+    yf = OneFormAssembler(poisson(V), u).assemble()
+    scale = np.abs(yf.data_ro).max()
+    assert np.abs(y1.data_ro - yf.data_ro).max() < 1e-12 * scale
+    yx = assemble_variable_coefficient(V, xk, u)
+    yk = assemble_variable_coefficient(V, kap, u)
+    assert np.abs(yk.data_ro - (2 * y1.data_ro + yx.data_ro)).max() < 1e-12 * scale
