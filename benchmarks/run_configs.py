@@ -65,6 +65,45 @@ def matrix_case(name, n, p, steps=3):
             "csr_GB": mat.nnz * 12 / 1e9}
 
 
+def blocked_matrix_case(name, n, p, cdim, steps=2):
+    """config 4, explicit: vector-valued space -> blocked CSR (not yet validated on a GPU)."""
+    mesh = ExtrudedHexMesh(n, n, n, warp=0.05)
+    V = FunctionSpace(mesh, p, cdim=cdim)
+    t0 = time.perf_counter()
+    mat = op2.Mat(op2.Sparsity((V.dof_dset, V.dof_dset), [(V.cell_node_map, V.cell_node_map, None)]))
+    _lib.check(_lib.lib().fdb_synchronize())
+    t_sparsity = time.perf_counter() - t0
+    a = helmholtz(V)
+    ms = timed(lambda: assemble(a, tensor=mat), steps, warm=1)
+    return {"case": name, "n": n, "degree": p, "cdim": cdim, "dofs": V.node_count * cdim, "block_nnz": mat.nnz,
+            "sparsity_s": t_sparsity, "assemble_ms": ms, "dofs_per_s": V.node_count * cdim / ms * 1e3,
+            "baij_GB": mat.nnz * (8 * cdim * cdim + 4) / 1e9}
+
+
+def generic_vs_fast_case(name, n, steps=5):
+    """The generic NVRTC wrapper around a plain-C Q1 Poisson kernel against the hand-written
+    kernel on the same problem (not yet validated on a GPU)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_codegen as tc
+    mesh = ExtrudedHexMesh(n, n, n, warp=0.05)
+    V = FunctionSpace(mesh, 1)
+    u = V.dat(np.random.default_rng(0).standard_normal(V.node_count))
+    yg, yf = V.dat(), V.dat()
+    k = op2.Kernel(tc.Q1_POISSON, "q1_poisson")
+
+    def generic():
+        yg.zero()
+        yg.device_ptr
+        op2.par_loop(k, V.cell_set, yg(op2.INC, V.cell_node_map), V.coordinates(op2.READ, V.coord_map),
+                     u(op2.READ, V.cell_node_map))
+    asm = OneFormAssembler(poisson(V), u)
+    ms_g = timed(generic, steps)
+    ms_f = timed(lambda: asm.assemble(yf), steps)
+    err = float(np.abs(yg.data_ro - yf.data_ro).max() / np.abs(yf.data_ro).max())
+    return {"case": name, "n": n, "dofs": V.node_count, "generic_ms": ms_g, "fast_ms": ms_f,
+            "ratio": ms_g / ms_f, "rel_diff": err}
+
+
 def cg_case(name, n, p, iters=20):
     mesh = ExtrudedHexMesh(n, n, n, warp=0.05)
     V = FunctionSpace(mesh, p)
@@ -107,6 +146,8 @@ def dg_case(name, n, steps=10, fused=False):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--unvalidated", action="store_true",
+                    help="also run the cases whose code paths have not passed on a GPU yet (DESIGN.md 7b)")
     args = ap.parse_args()
     _lib.init(0)
     q = args.quick
@@ -125,6 +166,12 @@ def main():
         lambda: matrix_case("Poisson CG2 matrix", 16 if q else 48, 2),
         lambda: matrix_case("Poisson CG3 matrix", 8 if q else 32, 3),
     ]
+    if args.unvalidated:
+        jobs += [
+            lambda: matrix_case("Poisson CG4 matrix (new instantiation)", 8 if q else 24, 4),
+            lambda: blocked_matrix_case("config4 vector Helmholtz CG4 explicit (blocked CSR)", 8 if q else 32, 4, 3),
+            lambda: generic_vs_fast_case("generic NVRTC wrapper vs hand-written kernel, Poisson CG1", 32 if q else 128),
+        ]
     for j in jobs:
         try:
             print(json.dumps(j()), flush=True)
