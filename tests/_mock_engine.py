@@ -77,6 +77,24 @@ class MockEngine:
     def fdb_synchronize(self):
         return 0
 
+    # timers (bench / run_configs): wall clock stands in for CUDA events
+    def fdb_timer_create(self, out):
+        _obj(out).value = 1
+        return 0
+
+    def fdb_timer_start(self, t):
+        import time
+        self._t0 = time.perf_counter()
+        return 0
+
+    def fdb_timer_stop(self, t, ms):
+        import time
+        _obj(ms).value = (time.perf_counter() - self._t0) * 1e3
+        return 0
+
+    def fdb_timer_destroy(self, t):
+        return 0
+
     def fdb_launch_count(self):
         return self.launches
 
