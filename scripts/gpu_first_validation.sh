@@ -27,3 +27,5 @@ for f in ("general", "affine"):
     except Exception as e:
         print(f, "failed", e)
 PY
+FDB_RUN_UNVALIDATED=1 python benchmarks/run_configs.py --unvalidated > gpurun_out/run_configs_unvalidated.jsonl 2>&1; tail -4 gpurun_out/run_configs_unvalidated.jsonl
+python benchmarks/mg_solve.py --coarse 16 --levels 3 --degree 3 > gpurun_out/mg_solve.json 2>&1; tail -1 gpurun_out/mg_solve.json
