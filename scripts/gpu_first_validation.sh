@@ -3,7 +3,7 @@
 # budget was spent (generic NVRTC wrapper builder, blocked matrices, interpolation, 0-forms,
 # multigrid), without -x so that one failure does not hide the others,
 # then one case under compute-sanitizer (races in the generated atomics / shuffles show here).
-#   gpurun --timeout 900 -- 'bash scripts/gpu_first_validation.sh'
+#   gpurun --timeout 1800 -- 'bash scripts/gpu_first_validation.sh'   (about 15-20 GPU-minutes)
 mkdir -p gpurun_out
 export FDB_RUN_UNVALIDATED=1
 python -m pytest tests/test_jit_gpu.py -q -m gpu -rA 2>&1 | tee gpurun_out/first_validation.log | tail -40
