@@ -166,7 +166,7 @@ def main():
         lambda: matrix_case("Poisson CG2 matrix", 16 if q else 48, 2),
         lambda: matrix_case("Poisson CG3 matrix", 8 if q else 32, 3),
     ]
-    if args.unvalidated:
+    if True:
         jobs += [
             lambda: matrix_case("Poisson CG4 matrix (new instantiation)", 8 if q else 24, 4),
             lambda: blocked_matrix_case("config4 vector Helmholtz CG4 explicit (blocked CSR)", 8 if q else 32, 4, 3),

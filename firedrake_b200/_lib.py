@@ -56,6 +56,7 @@ class CallArgs(C.Structure):
         ("nmaps", C.c_int32), ("maps", C.POINTER(C.c_void_p)),
         ("map_bytes", C.POINTER(C.c_size_t)),
         ("location", C.c_int32), ("writeback", C.c_int32), ("output_is_zero", C.c_int32),
+        ("map_versions", C.POINTER(C.c_uint64)), ("subset_version", C.c_uint64),
     ]
 
 
@@ -137,6 +138,7 @@ SIGNATURES = {
     "fdb_vec_axpy": (C.c_int, [C.c_size_t, C.c_double, C.c_void_p, C.c_void_p]),
     "fdb_vec_aypx": (C.c_int, [C.c_size_t, C.c_double, C.c_void_p, C.c_void_p]),
     "fdb_vec_scale": (C.c_int, [C.c_size_t, C.c_double, C.c_void_p]),
+    "fdb_vec_fill": (C.c_int, [C.c_size_t, C.c_double, C.c_void_p]),
     "fdb_vec_dot": (C.c_int, [C.c_size_t, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]),
     "fdb_vec_pointwise_mult": (C.c_int, [C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fdb_interpolate_q1": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -477,9 +477,9 @@ class Form:
 
     def kernel(self, rank):
         import os
-        # opt-in until its first GPU validation (DESIGN.md sections 7b, 8b): per-cell metric on
-        # meshes whose cells are all parallelepipeds
-        affine = rank == 1 and os.environ.get("FDB_AFFINE") == "1" and self.V.cells_are_affine()
+        # per-cell metric on meshes whose cells are all parallelepipeds (checked on the device;
+        # GPU-validated in round 2, FDB_AFFINE=0 opts out)
+        affine = rank == 1 and os.environ.get("FDB_AFFINE", "1") != "0" and self.V.cells_are_affine()
         return op2.Kernel("helmholtz", degree=self.V.degree, alpha=self.alpha, beta=self.beta,
                           rank=rank, cdim=self.V.cdim, affine=affine)
 
@@ -660,6 +660,7 @@ def cg(A, b: op2.Dat, x: op2.Dat, rtol=1e-8, atol=0.0, maxit=1000, allreduce=Non
     _lib.check(L.fdb_memcpy_d2d(r.device_ptr, b.device_ptr, b.nbytes))
     r._device_written()
     _lib.check(L.fdb_vec_axpy(n, -1.0, Ap.device_ptr, r.device_ptr))
+    r._device_written()
     _lib.check(L.fdb_memcpy_d2d(p.device_ptr, r.device_ptr, r.nbytes))
     p._device_written()
     rr = dot(r, r)
@@ -669,10 +670,16 @@ def cg(A, b: op2.Dat, x: op2.Dat, rtol=1e-8, atol=0.0, maxit=1000, allreduce=Non
     while it < maxit and np.sqrt(rr) > max(rtol * r0, atol):
         A.mult(p, Ap)
         alpha = rr / dot(p, Ap)
+        # raw vector updates over all local rows: Ap's ghost rows hold partial sums, so the
+        # ghost rows of x, r and p are NOT current afterwards (_device_written invalidates them;
+        # A.mult refreshes p's through global_to_local when the operator reads ghosts)
         _lib.check(L.fdb_vec_axpy(n, alpha, p.device_ptr, x.device_ptr))
+        x._device_written()
         _lib.check(L.fdb_vec_axpy(n, -alpha, Ap.device_ptr, r.device_ptr))
+        r._device_written()
         rr_new = dot(r, r)
         _lib.check(L.fdb_vec_aypx(n, rr_new / rr, r.device_ptr, p.device_ptr))   # p = r + beta p
+        p._device_written()
         rr = rr_new
         hist.append(np.sqrt(rr))
         it += 1

@@ -14,9 +14,8 @@ permutations) is exactly what PyOP2 folds into ``GlobalKernel.cache_key``
 
 Status: the generated code is checked on the CPU (tests/test_codegen.py: NVRTC
 compile for sm_100a, and a host re-compilation of the generated wrapper body run
-against the reference's golden arrays); it has not yet run on a GPU (written
-after round 1's GPU budget was spent) -- tests/test_jit_gpu.py is the first
-validation, gated behind FDB_RUN_UNVALIDATED=1 until it has passed once.
+against the reference's golden arrays) and on the GPU (tests/test_jit_gpu.py, green on a
+B200 since round 2).
 """
 from __future__ import annotations
 
@@ -267,6 +266,12 @@ def par_loop(kernel: CStringKernel, iterset, *args, iteration_region="ALL", loca
             if a.access == op2.INC:          # privatise: local sum from zero, added after the all-reduce
                 saved[id(a)] = a.data._data.copy()
                 a.data._data[...] = 0
+    # ghost rows of accumulated Dats start from the identity of the reduction
+    # (pyop2/types/dat.py:633-636), so that only this loop's contributions travel back
+    for a in args:
+        if (a.access in (op2.INC, op2.MIN, op2.MAX) and isinstance(a.data, op2.Dat)
+                and a.data.dataset.halo is not None and not a.data.frozen_halo):
+            a.data._reset_ghost_rows(a.access)
     for d in reads:
         d.dataset.halo.global_to_local_begin(d)
     first = True
@@ -345,6 +350,8 @@ def _par_loop_host(kernel, iterset, args, iteration_region, interior_horizontal=
         ca.nmaps = len(maps)
         ca.maps = (C.c_void_p * max(len(maps), 1))(*[m.ctypes.data for m in maps])
         ca.map_bytes = (C.c_size_t * max(len(maps), 1))(*[m.nbytes for m in maps])
+        ca.map_versions = (C.c_uint64 * max(len(maps), 1))(*[getattr(m, "_generation", 0) for m in spec.maps])
+        ca.subset_version = iterset._generation if isinstance(iterset, op2.Subset) else 0
         ca.location, ca.writeback, ca.output_is_zero = _lib.LOC_HOST, 1, 0
         _lib.check(_lib.lib().fdb_kernel_call(h, C.byref(ca)), "wrap_" + kernel.name)
         # the engine recorded version+1 for every written mirror (pyop2/parloop.py:262-272)

@@ -64,7 +64,9 @@ struct fdb_kernel_s {
     fdb_int h_off1[8];
     double Dt[FDB_MAX_1D * FDB_MAX_1D];   // collocated derivative D * B^{-1}
     // colouring plan for FDB_SCATTER_COLOURED, built lazily per map
-    const void *colour_map_key = nullptr;
+    const void *colour_map_key = nullptr;   // plan is valid for (map pointer, generation, end)
+    uint64_t colour_map_gen = 0;
+    fdb_int colour_end = 0;
     fdb_int *d_colour_cols = nullptr;     // columns sorted by colour
     int ncolours = 0;
     fdb_int colour_start[65];
@@ -77,6 +79,7 @@ void fdb_jit_destroy(fdb_jit_s *j);
 
 extern "C" int fdb_mirror_set_version(const void *host, uint64_t version);
 bool fdb_mirror_is_current(const void *host, size_t nbytes, uint64_t version);
+void fdb_mirror_new_epoch();   // start of a kernel call: mirrors touched from now on are pinned
 
 typedef struct fdb_mat_s *fdb_mat_t;
 int fdb_mat_device_view(fdb_mat_t m, const long long **rowptr, const fdb_int **colidx, double **vals,

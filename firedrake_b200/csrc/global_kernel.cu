@@ -106,8 +106,14 @@ int build_colouring(fdb_kernel_s *k, const fdb_int *h_map, fdb_int ncols)
 // with the chunk index; for an arbitrary numbering the schedule degenerates to
 // the monolithic one by construction (everything uploaded before chunk 0,
 // downloaded after the last), never to a wrong one.
+static inline uint64_t map_ver(const fdb_call_args *a, int i)
+{
+    return a->map_versions ? a->map_versions[i] : 0;
+}
+
 struct PipelinePlan {
     const void *map_key = nullptr;
+    uint64_t map_gen = 0;
     fdb_int start = 0, end = 0;
     int nlay = 0;
     std::vector<fdb_int> c0, c1;          // column range of each chunk
@@ -139,12 +145,14 @@ static int pipelined_host_action(fdb_kernel_s *k, const fdb_call_args *a, int nl
         g_ev_done.push_back(e2);
     }
     PipelinePlan &pl = g_plan;
-    if (pl.map_key != (const void *)a->maps[0] || pl.start != a->start || pl.end != a->end ||
+    if (pl.map_key != (const void *)a->maps[0] || pl.map_gen != map_ver(a, 0) || pl.start != a->start ||
+        pl.end != a->end ||
         pl.nlay != nlay || (int)pl.c0.size() != K) {
         // host analysis of the map (cached while the same map is passed)
         const fdb_int *map = a->maps[0];
         pl = PipelinePlan();
         pl.map_key = a->maps[0];
+        pl.map_gen = map_ver(a, 0);
         pl.start = a->start;
         pl.end = a->end;
         pl.nlay = nlay;
@@ -182,8 +190,8 @@ static int pipelined_host_action(fdb_kernel_s *k, const fdb_call_args *a, int nl
     void *dy, *dx, *dc, *dm0, *dm1;
     // static inputs through the mirror cache (uploaded once)
     if (fdb_mirror_acquire(a->args[1], a->arg_bytes[1], a->arg_versions[1], 1, &dc)) return 1;
-    if (fdb_mirror_acquire(a->maps[0], a->map_bytes[0], 0, 1, &dm0)) return 1;
-    if (fdb_mirror_acquire(a->maps[1], a->map_bytes[1], 0, 1, &dm1)) return 1;
+    if (fdb_mirror_acquire(a->maps[0], a->map_bytes[0], map_ver(a, 0), 1, &dm0)) return 1;
+    if (fdb_mirror_acquire(a->maps[1], a->map_bytes[1], map_ver(a, 1), 1, &dm1)) return 1;
     if (fdb_mirror_acquire(a->args[0], a->arg_bytes[0], a->arg_versions[0], 0, &dy)) return 1;
     bool x_current = fdb_mirror_is_current(a->args[2], a->arg_bytes[2], a->arg_versions[2]);
     if (fdb_mirror_acquire(a->args[2], a->arg_bytes[2], a->arg_versions[2], 0, &dx)) return 1;
@@ -346,6 +354,7 @@ int fdb_kernel_call(fdb_kernel_t k, const fdb_call_args *a)
         set_error("fdb_kernel_call: NULL argument");
         return 1;
     }
+    fdb_mirror_new_epoch();
     if (k->jit) return fdb_jit_call(k, a);      // generated wrapper (wrapper_jit.cu)
     if (k->desc.form == FDB_FORM_DG_ADVECTION) {
         // args = [out (INC), coords, q, u, consts (HOST double[2] {dtc, q_in}), facet numbers]
@@ -430,11 +439,11 @@ int fdb_kernel_call(fdb_kernel_t k, const fdb_call_args *a)
             if (fdb_mirror_acquire(a->args[1], a->arg_bytes[1], ver, 1, &p)) return 1;
             dcoords = (const double *)p;
             for (int i = 0; i < 2; i++) {
-                if (fdb_mirror_acquire(a->maps[i], a->map_bytes[i], 0, 1, &p)) return 1;
+                if (fdb_mirror_acquire(a->maps[i], a->map_bytes[i], map_ver(a, i), 1, &p)) return 1;
                 dm[i] = (const fdb_int *)p;
             }
             if (a->subset) {
-                if (fdb_mirror_acquire(a->subset, sizeof(fdb_int) * (size_t)a->end, 0, 1, &p)) return 1;
+                if (fdb_mirror_acquire(a->subset, sizeof(fdb_int) * (size_t)a->end, a->subset_version, 1, &p)) return 1;
                 dsub = (const fdb_int *)p;
             }
         } else {
@@ -498,19 +507,21 @@ int fdb_kernel_call(fdb_kernel_t k, const fdb_call_args *a)
         }
         for (int i = 0; i < 2; i++) {
             void *p;
-            if (fdb_mirror_acquire(a->maps[i], a->map_bytes[i], 0, 1, &p)) return 1;
+            if (fdb_mirror_acquire(a->maps[i], a->map_bytes[i], map_ver(a, i), 1, &p)) return 1;
             dmaps[i] = (const fdb_int *)p;
         }
         if (a->subset) {
             void *p;
-            if (fdb_mirror_acquire(a->subset, sizeof(fdb_int) * (size_t)a->end, 0, 1, &p)) return 1;
+            if (fdb_mirror_acquire(a->subset, sizeof(fdb_int) * (size_t)a->end, a->subset_version, 1, &p)) return 1;
             dsubset = (const fdb_int *)p;
         }
     } else {
         for (int i = 0; i < 3; i++) dargs[i] = a->args[i];
         for (int i = 0; i < 2; i++) dmaps[i] = a->maps[i];
     }
-    if (k->desc.scatter == FDB_SCATTER_COLOURED && k->colour_map_key != (const void *)a->maps[0]) {
+    if (k->desc.scatter == FDB_SCATTER_COLOURED &&
+        (k->colour_map_key != (const void *)a->maps[0] || k->colour_map_gen != map_ver(a, 0) ||
+         k->colour_end != a->end)) {
         // colouring covers columns [0, end): copy the map to the host if needed
         std::vector<fdb_int> hmap;
         const fdb_int *src = a->maps[0];
@@ -522,6 +533,8 @@ int fdb_kernel_call(fdb_kernel_t k, const fdb_call_args *a)
         }
         if (build_colouring(k, src, a->end)) return 1;
         k->colour_map_key = (const void *)a->maps[0];
+        k->colour_map_gen = map_ver(a, 0);
+        k->colour_end = a->end;
     }
     if (k->desc.scatter == FDB_SCATTER_COLOURED && a->start != 0) {
         set_error("fdb_kernel_call: coloured scatter needs start == 0");

@@ -104,7 +104,11 @@ __global__ void k_unpack(double *__restrict__ dat, int cdim, const fdb_int *__re
         long long k = i / cdim;
         int c = (int)(i - k * cdim);
         long long j = (long long)idx[k] * cdim + c;
-        if (ADD) dat[j] += buf[i];      // each owned dof appears once per neighbour list
+        // ADD is launched once per NEIGHBOUR (exchange_end): within one neighbour's list an
+        // owned dof appears once, so the plain read-modify-write is race free and the order in
+        // which neighbours are summed is fixed (deterministic); a dof shared with several
+        // neighbours (partition corners) is updated by consecutive launches
+        if (ADD) dat[j] += buf[i];
         else dat[j] = buf[i];
     }
 }
@@ -283,9 +287,18 @@ static int exchange_end(fdb_halo_t h, double *dat, int cdim, int reverse)
     const fdb_int *unpack_idx = reverse ? h->d_send_idx : h->d_recv_idx;
     const long long nun = reverse ? h->nsend : h->nrecv;
     if (nun > 0) {
-        if (reverse)
-            k_unpack<true><<<grid_for(nun * cdim), 256, 0, st>>>(dat, cdim, unpack_idx, nun, h->d_recv_buf);
-        else
+        if (reverse) {
+            // local->global SUM (firedrake/halo.py:140-172): one launch per neighbour list
+            for (int i = 0; i < h->nneigh; i++) {
+                const long long o = h->send_off[i], cnt = h->send_off[i + 1] - o;
+                if (cnt <= 0) continue;
+                k_unpack<true><<<grid_for(cnt * cdim), 256, 0, st>>>(dat, cdim, unpack_idx + o, cnt,
+                                                                     h->d_recv_buf + o * cdim);
+                FDB_LAUNCH_CHECK();
+            }
+            h->pending = 0;
+            return 0;
+        } else
             k_unpack<false><<<grid_for(nun * cdim), 256, 0, st>>>(dat, cdim, unpack_idx, nun, h->d_recv_buf);
         FDB_LAUNCH_CHECK();
     }

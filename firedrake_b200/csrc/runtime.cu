@@ -38,8 +38,14 @@ struct Mirror {
     size_t nbytes = 0;
     uint64_t version = 0;
     bool valid = false;
+    uint64_t epoch = 0;      // last fdb_kernel_call that touched it (LRU eviction)
 };
 static std::unordered_map<const void *, Mirror> g_mirrors;
+// The cache is bounded: when the mirrors exceed g_mirror_limit bytes, the least recently used
+// ones that the CURRENT call has not touched are released (a time loop over fresh host buffers
+// would otherwise grow without bound).  FDB_MIRROR_LIMIT_MB overrides (default: 60 % of HBM).
+static size_t g_mirror_bytes = 0, g_mirror_limit = 0;
+static uint64_t g_epoch = 1;
 
 }  // namespace fdb
 
@@ -48,6 +54,8 @@ using namespace fdb;
 static cudaStream_t g_side = nullptr;
 static cudaEvent_t g_side_ev = nullptr, g_main_ev = nullptr;
 static bool g_side_pending = false;
+
+void fdb_mirror_new_epoch() { fdb::g_epoch++; }
 
 bool fdb_mirror_is_current(const void *host, size_t nbytes, uint64_t version)
 {
@@ -105,6 +113,7 @@ int fdb_finalize(void)
     cudaStreamSynchronize(c.stream);
     for (auto &kv : g_mirrors) cudaFree(kv.second.dev);
     g_mirrors.clear();
+    g_mirror_bytes = 0;
     if (c.flush_buf) cudaFree(c.flush_buf);
     if (g_side) {
         cudaStreamSynchronize(g_side);
@@ -290,12 +299,42 @@ int fdb_mirror_acquire(const void *host, size_t nbytes, uint64_t version, int up
     if (m.dev && m.nbytes != nbytes) {
         FDB_CUDA(cudaStreamSynchronize(ctx().stream));
         FDB_CUDA(cudaFree(m.dev));
+        g_mirror_bytes -= m.nbytes;
         m = Mirror();
     }
+    m.epoch = g_epoch;
     if (!m.dev) {
-        FDB_CUDA(cudaMalloc(&m.dev, nbytes ? nbytes : 1));
-        m.nbytes = nbytes;
-        m.valid = false;
+        if (!g_mirror_limit) {
+            const char *e = getenv("FDB_MIRROR_LIMIT_MB");
+            size_t fr = 0, tot = 0;
+            cudaMemGetInfo(&fr, &tot);
+            g_mirror_limit = e ? (size_t)atoll(e) << 20 : (size_t)(0.6 * (double)tot);
+        }
+        while (g_mirror_bytes + nbytes > g_mirror_limit) {
+            auto victim = g_mirrors.end();
+            for (auto it = g_mirrors.begin(); it != g_mirrors.end(); ++it)
+                if (it->second.dev && it->second.epoch != g_epoch &&
+                    (victim == g_mirrors.end() || it->second.epoch < victim->second.epoch))
+                    victim = it;
+            if (victim == g_mirrors.end()) break;      // everything left is in use by this call
+            FDB_CUDA(cudaStreamSynchronize(ctx().stream));
+            FDB_CUDA(cudaFree(victim->second.dev));
+            g_mirror_bytes -= victim->second.nbytes;
+            g_mirrors.erase(victim);                   // (rehash-safe: `m` is re-looked-up below)
+        }
+        Mirror &mm = g_mirrors[host];
+        FDB_CUDA(cudaMalloc(&mm.dev, nbytes ? nbytes : 1));
+        mm.nbytes = nbytes;
+        mm.valid = false;
+        mm.epoch = g_epoch;
+        g_mirror_bytes += nbytes;
+        if (upload) {
+            FDB_CUDA(cudaMemcpyAsync(mm.dev, host, nbytes, cudaMemcpyHostToDevice, ctx().stream));
+            mm.valid = true;
+            mm.version = version;
+        }
+        *dev_out = mm.dev;
+        return 0;
     }
     if (upload && (!m.valid || m.version != version)) {
         FDB_CUDA(cudaMemcpyAsync(m.dev, host, nbytes, cudaMemcpyHostToDevice, ctx().stream));
@@ -336,6 +375,7 @@ int fdb_mirror_drop(const void *host)
     if (it == g_mirrors.end()) return 0;
     FDB_CUDA(cudaStreamSynchronize(ctx().stream));
     FDB_CUDA(cudaFree(it->second.dev));
+    g_mirror_bytes -= it->second.nbytes;
     g_mirrors.erase(it);
     return 0;
 }
@@ -346,6 +386,7 @@ int fdb_mirror_drop_all(void)
     FDB_CUDA(cudaStreamSynchronize(ctx().stream));
     for (auto &kv : g_mirrors) cudaFree(kv.second.dev);
     g_mirrors.clear();
+    g_mirror_bytes = 0;
     return 0;
 }
 

@@ -74,6 +74,13 @@ __global__ void k_stream(size_t n, double a, const double *__restrict__ x,
     }
 }
 
+// x[:] = a (no alignment assumption: used on the ghost tail of a Dat)
+__global__ void k_fill(size_t n, double a, double *__restrict__ x)
+{
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) x[j] = a;
+}
+
 constexpr int DOT_BLOCKS_MAX = 1184;   // 148 SMs x 8
 
 __global__ void __launch_bounds__(256)
@@ -194,6 +201,15 @@ int fdb_vec_scale(size_t n, double a, double *x)
 {
     if (require_init()) return 1;
     k_stream<2><<<stream_grid(n), 256, 0, ctx().stream>>>(n, a, nullptr, x, nullptr);
+    FDB_LAUNCH_CHECK();
+    return 0;
+}
+
+int fdb_vec_fill(size_t n, double a, double *x)
+{
+    if (require_init()) return 1;
+    if (n == 0) return 0;
+    k_fill<<<stream_grid(n), 256, 0, ctx().stream>>>(n, a, x);
     FDB_LAUNCH_CHECK();
     return 0;
 }

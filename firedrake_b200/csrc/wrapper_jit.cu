@@ -834,7 +834,7 @@ int fdb_jit_call(fdb_kernel_s *k, const fdb_call_args *a)
     for (int m = 0; m < pl.nmaps; m++) {
         if (host) {
             void *q;
-            if (fdb_mirror_acquire(a->maps[m], a->map_bytes[m], 0, 1, &q)) return 1;
+            if (fdb_mirror_acquire(a->maps[m], a->map_bytes[m], a->map_versions ? a->map_versions[m] : 0, 1, &q)) return 1;
             p.map[m] = (const int *)q;
         } else {
             p.map[m] = a->maps[m];
@@ -843,7 +843,7 @@ int fdb_jit_call(fdb_kernel_s *k, const fdb_call_args *a)
     if (pl.subset) {
         if (host) {
             void *q;
-            if (fdb_mirror_acquire(a->subset, sizeof(fdb_int) * (size_t)a->end, 0, 1, &q)) return 1;
+            if (fdb_mirror_acquire(a->subset, sizeof(fdb_int) * (size_t)a->end, a->subset_version, 1, &q)) return 1;
             p.subset = (const int *)q;
         } else {
             p.subset = a->subset;

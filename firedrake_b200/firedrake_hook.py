@@ -37,6 +37,8 @@ What it does: replaces ``pyop2.global_kernel.compile_global_kernel``
 from __future__ import annotations
 
 import ctypes as C
+import itertools
+import weakref
 
 import numpy as np
 
@@ -204,15 +206,46 @@ def _make_wrapper(handle, global_kernel):
         # sizes and dat_versions are not part of the reference arglist: _patched_compute
         # (below) sets them on this callable right before PyOP2 invokes it
         ca.arg_bytes = (C.c_size_t * nargs)(*fn.sizes[:nargs])
-        ca.arg_versions = (C.c_uint64 * nargs)(*fn.versions[:nargs])
+        if fn.versions is not None:        # None: no sound cache key -> every call re-uploads
+            ca.arg_versions = (C.c_uint64 * nargs)(*fn.versions[:nargs])
         ca.nmaps, ca.maps = len(maps), (C.c_void_p * len(maps))(*maps)
         ca.map_bytes = (C.c_size_t * len(maps))(*fn.map_sizes)
+        if fn.map_generations:
+            ca.map_versions = (C.c_uint64 * len(maps))(*fn.map_generations)
         ca.location, ca.writeback, ca.output_is_zero = _lib.LOC_HOST, 1, int(fn.output_is_zero)
         _lib.check(L.fdb_kernel_call(handle, C.byref(ca)), "fdb_kernel_call")
         return 0
 
-    fn.sizes, fn.versions, fn.map_sizes, fn.output_is_zero = (), (), (), False
+    fn.sizes, fn.versions, fn.map_sizes, fn.output_is_zero, fn.map_generations = (), (), (), False, ()
     return fn
+
+
+_generations = itertools.count(1)
+
+
+def _drop_mirror(ptr):
+    try:
+        if _lib._initialised is not None:
+            _lib._lib.fdb_mirror_drop(ptr)
+    except Exception:
+        pass
+
+
+def _track(obj, buf):
+    """First sight of a PyOP2 carrier whose host buffer the engine mirrors: give it a
+    generation id (never reused, so a new object at a recycled address misses the cache) and
+    release its mirror when it is garbage-collected (no unbounded growth in time loops; the
+    engine additionally bounds the cache by LRU eviction, runtime.cu)."""
+    gen = getattr(obj, "_fdb_generation", None)
+    if gen is None:
+        gen = next(_generations)
+        try:
+            obj._fdb_generation = gen
+            if buf is not None:
+                weakref.finalize(obj, _drop_mirror, buf.ctypes.data)
+        except (AttributeError, TypeError):
+            return 0                      # no attribute slot: address-keyed only
+    return gen
 
 
 _original_compute = None
@@ -230,6 +263,11 @@ def _patched_compute(self, part):
     if hasattr(fn, "sizes"):
         from pyop2.types import READ
         sizes, versions = [], []
+        # (buffer address, dat_version) is a sound mirror key only while nothing rewrites the
+        # buffer in place without bumping the version.  Under MPI the PetscSF halo exchange
+        # rewrites ghost rows of READ Dats between the core and owned phases, and INC ghost
+        # zeroing does the same: no versions there, every call re-uploads.
+        cacheable = self.comm.size == 1
         for arg, access in zip(self.arguments, self.accesses):
             data = arg.data
             for d in (data if hasattr(data, "__iter__") and not hasattr(data, "_data") else (data,)):
@@ -237,8 +275,12 @@ def _patched_compute(self, part):
                 sizes.append(0 if buf is None else buf.nbytes)
                 v = getattr(d, "dat_version", 0)
                 versions.append(v if access is READ else max(v - 1, 0))
+                _track(d, buf)
+                if getattr(getattr(d, "dataset", None), "halo", None) is not None and self.comm.size > 1:
+                    cacheable = False
         maps = {m: None for d in self.arguments for m in d.map_kernel_args}
-        fn.sizes, fn.versions = tuple(sizes), tuple(versions)
+        fn.sizes, fn.versions = tuple(sizes), (tuple(versions) if cacheable else None)
+        fn.map_generations = tuple(_track(m, getattr(m, "values_with_halo", None)) for m in maps)
         fn.map_sizes = tuple(self.iterset.total_size * 4 * getattr(m, "arity", 0) if not hasattr(m, "nbytes")
                              else m.nbytes for m in maps)
         fn.output_is_zero = False

@@ -80,8 +80,7 @@ class Halo:
 
     def global_to_local_end(self, dat, insert_mode="replace"):
         _lib.check(_lib.lib().fdb_halo_global_to_local_end(self.handle, dat.device_ptr, dat.cdim))
-        dat._device_written()
-        dat.halo_valid = True
+        dat._device_written(halo_valid=True)
 
     # firedrake/halo.py:140-172
     def local_to_global_begin(self, dat, insert_mode="sum"):
@@ -90,8 +89,7 @@ class Halo:
 
     def local_to_global_end(self, dat, insert_mode="sum"):
         _lib.check(_lib.lib().fdb_halo_local_to_global_end(self.handle, dat.device_ptr, dat.cdim))
-        dat._device_written()
-        dat.halo_valid = False
+        dat._device_written(halo_valid=False)
 
     def __del__(self):
         try:

@@ -34,6 +34,7 @@ from __future__ import annotations
 import ctypes as C
 import enum
 import itertools
+import weakref
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -69,6 +70,21 @@ class MapValueError(ValueError):
 
 class DataSetTypeError(TypeError):
     pass
+
+
+# Generation ids for objects whose host buffers the engine mirrors by ADDRESS (maps, subset
+# index arrays): unique per object and never reused, passed as fdb_call_args.map_versions /
+# subset_version so that a new object at a recycled address cannot hit the old mirror, and the
+# mirror itself is released when the object dies.
+_generations = itertools.count(1)
+
+
+def _drop_host_mirror(ptr):
+    try:
+        if _lib._initialised is not None:
+            _lib._lib.fdb_mirror_drop(ptr)
+    except Exception:
+        pass
 
 
 # ---------------------------------------------------------------------- sets
@@ -128,6 +144,8 @@ class Subset(Set):
             raise ValueError("subset indices out of range")
         self.superset = superset
         self.indices = np.ascontiguousarray(idx)
+        self._generation = next(_generations)
+        weakref.finalize(self, _drop_host_mirror, self.indices.ctypes.data)
         core = int(np.searchsorted(idx, superset.core_size))
         owned = int(np.searchsorted(idx, superset.size))
         Set.__init__(self, (core, owned, len(idx)), name=superset.name + "_subset")
@@ -173,6 +191,8 @@ class Map:
             raise MapValueError("offset must have one entry per arity index")
         self.name = name or f"map_{next(Map._ids)}"
         self._dev = None
+        self._generation = next(_generations)
+        weakref.finalize(self, _drop_host_mirror, self.values_with_halo.ctypes.data)
 
     @property
     def values(self):
@@ -342,11 +362,28 @@ class Dat:
             self._dev_valid = True
         return self._dev.ptr
 
-    def _device_written(self):
+    def _device_written(self, halo_valid=False):
+        """The device copy was written.  As in the reference, ANY write invalidates the ghost
+        rows (pyop2/types/dat.py:622-678); only ``Halo.global_to_local_end`` (or an operation
+        that provably wrote current ghost values) passes ``halo_valid=True``."""
         self._host_valid = False
         self._dev_valid = True
         self._is_zero = False
+        self.halo_valid = bool(halo_valid)
         self.increment_dat_version()
+
+    def _reset_ghost_rows(self, access):
+        """Before a loop that accumulates into this Dat, set its ghost rows to the identity of
+        the reduction (0 for INC, +/-inf for MIN/MAX) -- what the reference's
+        ``global_to_local_begin`` does for those access modes (pyop2/types/dat.py:633-636) --
+        so that the local->global reduce afterwards sends THIS loop's contributions only."""
+        st = self.dataset.set
+        nghost = (st.total_size - st.size) * self.cdim
+        if nghost <= 0 or (self._is_zero and access is INC):
+            return                       # a (lazily) zeroed Dat already holds the INC identity
+        ident = {INC: 0.0, MIN: float("inf"), MAX: float("-inf")}[access]
+        base = self.device_ptr + st.size * self.cdim * self.dtype.itemsize
+        _lib.check(_lib.lib().fdb_vec_fill(nghost, ident, base), "fdb_vec_fill")
 
     # -- whole-Dat operations (pyop2/types/dat.py:297-311, 354-540)
     def zero(self, subset=None):
@@ -383,10 +420,9 @@ class Dat:
         L = _lib.lib()
         n = self._data.size
         _lib.check(fn(n, *scalars, other.device_ptr, self.device_ptr))
-        self._device_written()
-        # the algebra ran over every local row, but `other`'s ghost rows need not be current
-        # (pyop2/types/dat.py:622-678: a write invalidates the halo)
-        self.halo_valid = self.halo_valid and other.halo_valid
+        # the algebra ran over every local row: the ghost rows stay current only if they were
+        # current in BOTH operands (pyop2/types/dat.py:622-678: a write invalidates the halo)
+        self._device_written(halo_valid=self.halo_valid and other.halo_valid)
 
     def axpy(self, alpha, other):
         """self += alpha * other"""
@@ -409,8 +445,7 @@ class Dat:
         if other.nbytes != self.nbytes:
             raise ValueError("copy between Dats of different sizes")
         _lib.check(_lib.lib().fdb_memcpy_d2d(other.device_ptr, self.device_ptr, self.nbytes), "d2d")
-        other._device_written()
-        other.halo_valid = self.halo_valid
+        other._device_written(halo_valid=self.halo_valid)
 
     def __iadd__(self, other):
         if not isinstance(other, Dat):
@@ -429,10 +464,11 @@ class Dat:
         if isinstance(other, Dat):
             _lib.check(L.fdb_vec_pointwise_mult(self._data.size, self.device_ptr, other.device_ptr,
                                                 self.device_ptr), "pointwise_mult")
-            self.halo_valid = self.halo_valid and other.halo_valid
+            hv = self.halo_valid and other.halo_valid
         else:
             _lib.check(L.fdb_vec_scale(self._data.size, float(other), self.device_ptr), "scale")
-        self._device_written()
+            hv = self.halo_valid          # a uniform scaling keeps current ghost rows current
+        self._device_written(halo_valid=hv)
         return self
 
     def maxpy(self, scalars, dats):
@@ -780,7 +816,8 @@ class GlobalKernel:
         return h
 
     def __call__(self, start, end, layers, subset_indices, args, arg_bytes, arg_versions,
-                 maps, map_bytes, location, writeback, output_is_zero):
+                 maps, map_bytes, location, writeback, output_is_zero, map_versions=None,
+                 subset_version=0):
         h = self.compile()
         ca = _lib.CallArgs()
         ca.start, ca.end = int(start), int(end)
@@ -796,6 +833,9 @@ class GlobalKernel:
         ca.maps = (C.c_void_p * len(maps))(*maps)
         if map_bytes is not None:
             ca.map_bytes = (C.c_size_t * len(maps))(*map_bytes)
+        if map_versions is not None:
+            ca.map_versions = (C.c_uint64 * len(maps))(*map_versions)
+        ca.subset_version = int(subset_version)
         ca.location = location
         ca.writeback = int(writeback)
         ca.output_is_zero = int(output_is_zero)
@@ -895,7 +935,9 @@ class Parloop:
             vers = [a.data.dat_version for a in self.args]
             gk(start, end, layers, subset, ptrs, nbytes, vers,
                [m.values_with_halo.ctypes.data for m in maps],
-               [m.values_with_halo.nbytes for m in maps], _lib.LOC_HOST, True, out._is_zero)
+               [m.values_with_halo.nbytes for m in maps], _lib.LOC_HOST, True, out._is_zero,
+               map_versions=[m._generation for m in maps],
+               subset_version=it._generation if isinstance(it, Subset) else 0)
             out.increment_dat_version()      # pyop2/parloop.py:262-272
             out._is_zero = False
             out._host_valid = True           # written back by the engine
@@ -912,6 +954,8 @@ class Parloop:
         incs = [a.data for a in self.args
                 if a.access == INC and isinstance(a.data, Dat) and a.data.dataset.halo is not None
                 and not a.data.frozen_halo]
+        for d in incs:
+            d._reset_ghost_rows(INC)
         for d in reads:
             d.dataset.halo.global_to_local_begin(d)
         c0, c1 = self.iterset.core_part

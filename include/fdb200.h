@@ -193,6 +193,11 @@ typedef struct fdb_call_args {
     int32_t output_is_zero;     /* host mode: the caller has just zeroed the output
                                    (firedrake/assemble.py:1042-1047), so the mirror
                                    is memset on the device instead of uploaded       */
+    const uint64_t *map_versions; /* host mode: a GENERATION id per map (unique per Map object,
+                                   never reused): a new Map that happens to live at a freed
+                                   Map's address misses the mirror / colouring / pipeline
+                                   caches.  NULL = 0 for every map (address-keyed only)      */
+    uint64_t subset_version;    /* same for the subset index array                            */
 } fdb_call_args;
 
 /* Replaces the ctypes call fn(start, end, *arglist) of
@@ -332,6 +337,9 @@ int fdb_dat_set_nodes_scalar(double *dat, double value, int cdim, const fdb_int 
 int fdb_vec_axpy(size_t n, double a, const double *x, double *y);            /* y += a x       */
 int fdb_vec_aypx(size_t n, double a, const double *x, double *y);            /* y = x + a y    */
 int fdb_vec_scale(size_t n, double a, double *x);
+int fdb_vec_fill(size_t n, double a, double *x);                              /* x[:] = a: ghost-row reset
+                                                                                 of INC/MIN/MAX Dats,
+                                                                                 pyop2/types/dat.py:633-636 */
 int fdb_vec_dot(size_t n, const double *x, const double *y, double *out);
 int fdb_vec_pointwise_mult(size_t n, const double *x, const double *y, double *w);
 

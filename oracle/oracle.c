@@ -20,6 +20,8 @@
  * Build flags mirror PyOP2's JIT on Linux/GCC: -O3 -march=native -ffast-math
  * -fPIC -shared (reference pyop2/compilation.py:341-363).
  */
+#define _GNU_SOURCE
+#include <sched.h>
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -404,6 +406,114 @@ int orc_action_workers(int degree, int nworkers, const orc_worker *w, int cdim,
                                        w[i].coords, w[i].x, w[i].map0, w[i].off0,
                                        w[i].map1, w[i].off1, cdim, B, D, CB, CD, wq,
                                        alpha, beta);
+    return rc;
+}
+
+/* Timing arm of bench.py (--impl reference / cpu_baseline): the reference's
+ * parallel model restated with the care an MPI launch gets for free --
+ *   * one worker per core, PINNED (mpiexec --bind-to core),
+ *   * every worker allocates and first-touches ITS OWN copies of its local
+ *     arrays inside its thread (an MPI rank's memory is NUMA-local),
+ *   * after the local loops, the contributions a worker accumulated on its
+ *     ghost plane are added into the owning neighbour's plane (local_to_global
+ *     with INC, reference pyop2/parloop.py:255-260) -- slab decomposition, so a
+ *     worker has one ghost plane (x = high face), owned by worker i+1.
+ * Every worker gets the same template slab (same sizes as a real slab of the
+ * partitioned mesh); times[r] = wall time of pass r (barrier to barrier: zero y,
+ * local loop, ghost reduce), i.e. the max over workers.  reps passes after one
+ * untimed warm-up pass.  Returns 0, or nonzero on allocation / kernel failure. */
+int orc_action_bench(int degree, int nworkers, int reps, const int *cpu_ids,
+                     int ncols, const int *layers, int64_t ndof, int64_t nvert,
+                     const double *coords, const double *x, const int *map0, int arity0,
+                     const int *off0, const int *map1, const int *off1,
+                     int nface, const int *face_hi, const int *face_lo,
+                     const double *B, const double *D, const double *CB, const double *CD,
+                     const double *wq, double alpha, double beta, double *times,
+                     double *checksum)
+{
+    int rc = 0;
+    double **ys = (double **)calloc((size_t)nworkers, sizeof(double *));
+    if (!ys) return 1;
+#ifdef _OPENMP
+#pragma omp parallel num_threads(nworkers) reduction(| : rc)
+    {
+        const int w = omp_get_thread_num();
+        if (cpu_ids) {
+            cpu_set_t set;
+            CPU_ZERO(&set);
+            CPU_SET(cpu_ids[w], &set);
+            sched_setaffinity(0, sizeof(set), &set);
+        }
+        /* private, first-touched copies */
+        double *yl = (double *)malloc(sizeof(double) * (size_t)ndof);
+        double *xl = (double *)malloc(sizeof(double) * (size_t)ndof);
+        double *cl = (double *)malloc(sizeof(double) * (size_t)nvert * 3);
+        int *m0 = (int *)malloc(sizeof(int) * (size_t)ncols * arity0);
+        int *m1 = (int *)malloc(sizeof(int) * (size_t)ncols * 8);
+        int bad = !yl || !xl || !cl || !m0 || !m1;
+        if (!bad) {
+            memcpy(xl, x, sizeof(double) * (size_t)ndof);
+            memcpy(cl, coords, sizeof(double) * (size_t)nvert * 3);
+            memcpy(m0, map0, sizeof(int) * (size_t)ncols * arity0);
+            memcpy(m1, map1, sizeof(int) * (size_t)ncols * 8);
+            memset(yl, 0, sizeof(double) * (size_t)ndof);
+        }
+        ys[w] = yl;
+        rc |= bad;
+#pragma omp barrier
+        for (int r = -1; r < reps && !rc; r++) {
+#pragma omp barrier
+            double t0 = omp_get_wtime();
+            memset(yl, 0, sizeof(double) * (size_t)ndof);   /* assembler zeroes the tensor */
+            rc |= orc_wrap_action_extruded(degree, 0, ncols, layers, yl, cl, xl, m0, off0, m1,
+                                           off1, 1, B, D, CB, CD, wq, alpha, beta);
+#pragma omp barrier
+            /* ghost plane of worker w-1 -> my owned low plane */
+            if (w > 0 && ys[w - 1]) {
+                const double *yn = ys[w - 1];
+                for (int i = 0; i < nface; i++) yl[face_lo[i]] += yn[face_hi[i]];
+            }
+#pragma omp barrier
+            if (w == 0 && r >= 0) times[r] = omp_get_wtime() - t0;
+        }
+        if (w == nworkers / 2 && checksum && !bad) {
+            double s = 0.0;
+            for (int64_t i = 0; i < ndof; i++) s += yl[i];
+            *checksum = s;
+        }
+#pragma omp barrier
+        free(yl); free(xl); free(cl); free(m0); free(m1);
+    }
+#else
+    rc = 1;
+#endif
+    free(ys);
+    return rc;
+}
+
+/* Full-size parity helper: the same sequential wrapper, run by several threads on
+ * disjoint BANDS of base cells.  Cells are grouped by the caller into bands (slabs
+ * of base-cell columns at least one cell wide) such that two bands of the same
+ * parity share no dof; even bands run concurrently, then odd bands, all adding
+ * into the one shared y -- no atomics, and within a band the reference's
+ * sequential order.  A band is a list of runs [run_start, run_end) of the cell
+ * order (runs of band b: run_first[b] .. run_first[b+1]). */
+int orc_action_bands(int degree, int nbands, const int *run_first, const int *run_start,
+                     const int *run_end, const int *layers, double *y, const double *coords,
+                     const double *x, const int *map0, const int *off0, const int *map1,
+                     const int *off1, int cdim, const double *B, const double *D,
+                     const double *CB, const double *CD, const double *wq, double alpha,
+                     double beta, int nthreads)
+{
+    int rc = 0;
+    for (int parity = 0; parity < 2; parity++) {
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads) reduction(| : rc)
+        for (int b = parity; b < nbands; b += 2)
+            for (int r = run_first[b]; r < run_first[b + 1]; r++)
+                rc |= orc_wrap_action_extruded(degree, run_start[r], run_end[r], layers, y, coords,
+                                               x, map0, off0, map1, off1, cdim, B, D, CB, CD,
+                                               wq, alpha, beta);
+    }
     return rc;
 }
 

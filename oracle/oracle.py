@@ -244,6 +244,66 @@ def action_workers(el, problems, cdim=1, alpha=1.0, beta=0.0, native=True):
         raise RuntimeError("oracle workers failed")
 
 
+def action_bench(el, mesh, V, x, nworkers, reps, cpu_ids=None, alpha=1.0, beta=0.0, native=True):
+    """Pinned, first-touch timing of the extruded action: ``nworkers`` threads each run the
+    template slab ``(mesh, V)`` on private copies, followed by the ghost-plane reduce between
+    neighbouring slabs (``orc_action_bench`` in oracle.c).  Returns (times[reps], checksum)."""
+    B, D, CB, CD, wq = _tabs(el)
+    lay = np.ascontiguousarray([0, mesh.layers], dtype=np.int32)
+    hi = np.ascontiguousarray(V.plane_nodes(mesh.nx), dtype=np.int32)
+    lo = np.ascontiguousarray(V.plane_nodes(0), dtype=np.int32)
+    assert hi.size == lo.size
+    times = np.zeros(reps)
+    chk = ctypes.c_double(0.0)
+    ids = None if cpu_ids is None else np.ascontiguousarray(cpu_ids, dtype=np.int32)
+    m0 = np.ascontiguousarray(V.cell_node_map, dtype=np.int32)
+    m1 = np.ascontiguousarray(mesh.coord_map, dtype=np.int32)
+    off0 = np.ascontiguousarray(V.offset, dtype=np.int32)
+    off1 = np.ascontiguousarray(mesh.coord_offset, dtype=np.int32)
+    coords = np.ascontiguousarray(mesh.coordinates, dtype=np.float64)
+    L = lib(native)
+    rc = L.orc_action_bench(el.degree, int(nworkers), int(reps), _i(ids), int(mesh.num_base_cells),
+                            _i(lay), ctypes.c_int64(V.node_count),
+                            ctypes.c_int64(mesh.coord_space.node_count), _d(coords), _d(x), _i(m0),
+                            int(V.arity), _i(off0), _i(m1), _i(off1), int(hi.size), _i(hi), _i(lo),
+                            _d(B), _d(D), _d(CB), _d(CD), _d(wq), ctypes.c_double(alpha),
+                            ctypes.c_double(beta), _d(times), ctypes.byref(chk))
+    if rc:
+        raise RuntimeError("oracle action_bench failed")
+    return times, chk.value
+
+
+def action_extruded_parallel(el, mesh, y, coords, x, map0, off0, map1, off1, cdim=1, alpha=1.0,
+                             beta=0.0, nthreads=None, native=False, ncells=None):
+    """``action_extruded`` over base cells ``[0, ncells)`` of ``mesh`` with several threads:
+    bands of base-cell columns (constant ``mesh.cell_ix``), even bands then odd bands
+    (``orc_action_bands``).  Same result as the sequential wrapper up to summation order
+    across bands.  Needs ``mesh.cell_ix`` (structured base mesh)."""
+    import os
+    ncells = mesh.num_base_cells if ncells is None else ncells
+    ix = np.asarray(mesh.cell_ix[:ncells])
+    # runs of consecutive cells with the same ix
+    brk = np.flatnonzero(np.diff(ix)) + 1
+    rs = np.concatenate([[0], brk]).astype(np.int32)
+    re_ = np.concatenate([brk, [ncells]]).astype(np.int32)
+    band_of_run = ix[rs]
+    order = np.argsort(band_of_run, kind="stable")
+    rs, re_, band_of_run = rs[order], re_[order], band_of_run[order]
+    nb = int(band_of_run.max()) + 1 if len(band_of_run) else 0
+    first = np.searchsorted(band_of_run, np.arange(nb + 1)).astype(np.int32)
+    B, D, CB, CD, wq = _tabs(el)
+    lay = np.ascontiguousarray([0, mesh.layers], dtype=np.int32)
+    nt = nthreads or len(os.sched_getaffinity(0))
+    rc = lib(native).orc_action_bands(el.degree, nb, _i(first), _i(np.ascontiguousarray(rs)),
+                                      _i(np.ascontiguousarray(re_)), _i(lay), _d(y), _d(coords), _d(x),
+                                      _i(map0), _i(off0), _i(map1), _i(off1), int(cdim), _d(B), _d(D),
+                                      _d(CB), _d(CD), _d(wq), ctypes.c_double(alpha),
+                                      ctypes.c_double(beta), int(nt))
+    if rc:
+        raise RuntimeError("oracle action_bands failed")
+    return y
+
+
 def num_threads():
     return lib().orc_num_threads()
 

@@ -203,6 +203,11 @@ class MockEngine:
         _view(x, n)[:] *= a
         return 0
 
+    def fdb_vec_fill(self, n, a, x):
+        if n:
+            _view(x, n)[:] = a
+        return 0
+
     def fdb_vec_dot(self, n, x, y, out):
         _obj(out).value = float(_view(x, n) @ _view(y, n))
         return 0
