@@ -148,6 +148,7 @@ def main():
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--unvalidated", action="store_true",
                     help="also run the cases whose code paths have not passed on a GPU yet (DESIGN.md 7b)")
+    ap.add_argument("--only", default=None, help="run only the cases whose name contains this substring")
     args = ap.parse_args()
     _lib.init(0)
     q = args.quick
@@ -172,6 +173,9 @@ def main():
             lambda: blocked_matrix_case("config4 vector Helmholtz CG4 explicit (blocked CSR)", 8 if q else 32, 4, 3),
             lambda: generic_vs_fast_case("generic NVRTC wrapper vs hand-written kernel, Poisson CG1", 32 if q else 128),
         ]
+    if args.only:
+        import inspect
+        jobs = [j for j in jobs if args.only in inspect.getsource(j)]
     for j in jobs:
         try:
             print(json.dumps(j()), flush=True)

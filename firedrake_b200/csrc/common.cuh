@@ -70,6 +70,8 @@ struct fdb_kernel_s {
     fdb_int *d_colour_cols = nullptr;     // columns sorted by colour
     int ncolours = 0;
     fdb_int colour_start[65];
+    // dense B^T D B path (bdb_matrix.cu): tabulated reference gradients / values, built lazily
+    double *d_bdb_table = nullptr;
     // non-NULL: this handle is a generated wrapper around an arbitrary local kernel
     fdb_jit_s *jit = nullptr;
 };
@@ -91,6 +93,10 @@ int fdb_mat_scalar_view_end(fdb_mat_t blocked, fdb_mat_t view);
 int fdb_launch_helmholtz_matrix(fdb_kernel_s *k, fdb_int start, fdb_int end, int nlay,
                                 const fdb_int *subset, fdb_mat_t mat, const double *coords,
                                 const fdb_int *map0, const fdb_int *map1, double *diag_out);
+
+int fdb_launch_helmholtz_matrix_dmma(fdb_kernel_s *k, fdb_int start, fdb_int end, int nlay,
+                                     const fdb_int *subset, fdb_mat_t mat, const double *coords,
+                                     const fdb_int *map0, const fdb_int *map1);
 
 int fdb_launch_tri_p1(fdb_kernel_s *k, fdb_int start, fdb_int end, const fdb_int *subset, double *y,
                       const double *coords, const double *x, const fdb_int *map, fdb_mat_t mat);

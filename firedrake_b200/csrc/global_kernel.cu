@@ -342,6 +342,7 @@ int fdb_kernel_destroy(fdb_kernel_t k)
         if (k->d_off0) cudaFree(k->d_off0);
         if (k->d_off1) cudaFree(k->d_off1);
         if (k->d_colour_cols) cudaFree(k->d_colour_cols);
+        if (k->d_bdb_table) cudaFree(k->d_bdb_table);
     }
     delete k;
     return 0;

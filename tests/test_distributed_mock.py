@@ -76,6 +76,39 @@ def _worker(rank, world, port, q):
         z.device_ptr
         A.mult(u3, z)
         out["ismat"] = float(np.abs(z.data_ro[:no] - np.array([look_mat[k] for k in key(lat[:no]).tolist()])).max())
+        # advisor (round 1): a SECOND INC loop into the same Dat without zero() in between must add
+        # this loop's contributions once (ghost rows restart from the INC identity)
+        u4 = interpolate(V, expr)
+        op2.par_loop(op2.Kernel(tc.Q1_POISSON, "q1_poisson"), V.cell_set, yg(op2.INC, V.cell_node_map),
+                     V.coordinates(op2.READ, V.coord_map), u4(op2.READ, V.cell_node_map))
+        out["twice"] = float(np.abs(yg.data_ro[:no] - 2 * np.array([look_gen[k] for k in key(lat[:no]).tolist()])).max())
+        # advisor (round 1): CG on the unassembled (mat_type="is") operator, pc none: the raw vector
+        # updates leave stale ghost rows that every mult must refresh
+        from firedrake_b200.assemble import cg
+        import torch
+
+        def allreduce(v):
+            t = torch.tensor([v], dtype=torch.float64)
+            dist.all_reduce(t)
+            return float(t.item())
+        eng.dist = None
+        gb = G.dat(np.cos(glat[:, 0] * 0.7) + 0.1 * glat[:, 1] - 0.05 * glat[:, 2] ** 2)
+        for bc in [DirichletBC(G, 0.0, "top")]:
+            bc.zero(gb)
+        gx = G.dat()
+        gx.device_ptr
+        n_ser, _ = cg(gA, gb, gx, rtol=1e-11, maxit=500)
+        look_sol = dict(zip(key(glat).tolist(), gx.data_ro.tolist()))
+        eng.dist = dist
+        bl = V.dat(np.cos(lat[:, 0] * 0.7) + 0.1 * lat[:, 1] - 0.05 * lat[:, 2] ** 2)
+        for bc in [DirichletBC(V, 0.0, "top")]:
+            bc.zero(bl)
+        xl = V.dat()
+        xl.device_ptr
+        n_par, _ = cg(A, bl, xl, rtol=1e-11, maxit=500, allreduce=allreduce)
+        sol = np.array([look_sol[k] for k in key(lat[:no]).tolist()])
+        out["cg_is"] = float(np.abs(xl.data_ro[:no] - sol).max() / np.abs(sol).max())
+        out["cg_its"] = (n_ser, n_par)
         out["dx"] = abs(assemble_functional(V, u2, "dx") - ref["dx"])
         out["ds"] = abs(assemble_functional(V, u2, "ds") - ref["ds"])
         out["scale"] = float(np.abs(gy.data_ro).max())
@@ -102,6 +135,8 @@ def test_distributed_generic_parloops(world):
         assert out["generic"] < 1e-12 * out["scale"], (rank, out)
         assert out["ismat"] < 1e-12 * out["scale"], (rank, out)
         assert out["dx"] < 1e-12 and out["ds"] < 1e-12, (rank, out)
+        assert out["twice"] < 1e-12 * out["scale"], (rank, out)
+        assert out["cg_is"] < 1e-8 and abs(out["cg_its"][0] - out["cg_its"][1]) <= 2, (rank, out)
 
 
 def _mg_worker(rank, world, port, q):

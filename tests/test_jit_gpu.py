@@ -138,13 +138,16 @@ def test_generic_extruded_action_equals_fast_path_and_oracle(engine, oracle):
     assert np.abs(yf.data_ro - yo).max() < 1e-12 * scale
 
 
-@pytest.mark.parametrize("p,cdim", [(2, 3), (1, 2)])
+@pytest.mark.parametrize("p,cdim", [(2, 3), (1, 2), (3, 3), (4, 3)])
 def test_vector_space_matrix_fast_path(engine, oracle, p, cdim):
     """assemble(a) on a VectorFunctionSpace (config 4's explicit matrix): blocked CSR ==
-    kron(scalar oracle matrix, I), with node Dirichlet conditions, and SpMV == matrix-free."""
+    kron(scalar oracle matrix, I), with node Dirichlet conditions, and SpMV == matrix-free.
+    p >= 3 runs the dense B^T D B kernel on the fp64 tensor pipe (bdb_matrix.cu), (4, 3) being
+    config 4's own instance; reference scatter: pyop2/codegen/builder.py:573-625."""
     from firedrake_b200.assemble import DirichletBC, FunctionSpace, assemble, helmholtz
     import test_matrix_gpu as tm
-    mesh = ExtrudedHexMesh(3, 3, 4, warp=0.05, permute_seed=2)
+    mesh = ExtrudedHexMesh(3, 3, 4, warp=0.05, permute_seed=2) if p < 4 else \
+        ExtrudedHexMesh(2, 2, 3, warp=0.05, permute_seed=2)
     V = FunctionSpace(mesh, p, cdim=cdim)
     bcs = [DirichletBC(V, 0.0, "bottom")]
     A = assemble(helmholtz(V), bcs=bcs)
