@@ -43,6 +43,10 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--halo", default="exec", choices=["exec", "sum"],
+                    help="partitioned runs: 'exec' = redundant execution of one exec-halo cell column per rank, "
+                         "no local->global reduce (SURVEY.md 8e option ii); 'sum' = the reference's owned cells + "
+                         "ghost-sum reduce")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     return ap.parse_args()
 
@@ -111,7 +115,7 @@ def make_problem(args, rank, world, pinned):
     n, p = args.n, args.degree
     if args.permute >= 0 and world > 1:
         raise SystemExit("--permute is a single-GPU stress option")
-    part = SlabPartition(n, n, n, p, rank, world, warp=args.warp)
+    part = SlabPartition(n, n, n, p, rank, world, warp=args.warp, exec_halo=args.halo == "exec")
     mesh, V = part.mesh, part.V
     if args.permute >= 0:
         from firedrake_b200.utility_meshes import ExtrudedHexMesh
@@ -119,6 +123,7 @@ def make_problem(args, rank, world, pinned):
         V = mesh.function_space(p)
     halo = Halo(part.neighbours) if world > 1 else None
     cells = op2.ExtrudedSet(op2.Set(part.cell_sizes), mesh.layers)
+    cells.owner_computes = part.exec_halo
     nodes = op2.Set(part.node_sizes)
     vnodes = op2.Set(mesh.coord_space.node_count)
     m0 = op2.Map(cells, nodes, V.arity, V.cell_node_map, offset=V.offset)
@@ -221,6 +226,45 @@ def cpu_baseline(args, seconds, reps=5):
             "passes": [float(v) for v in ts], "dofs_per_pass": P * owned}
 
 
+def cpu_cg_baseline(mesh, V, p, b, bc_nodes, iters):
+    """cpu_baseline leg of benchmarks/cg_multi.py (config 5): unpreconditioned CG on the host cores
+    with the oracle's operator (banded multi-threaded action, Dirichlet rows as in
+    firedrake/matrix_free/operators.py:225-239) and OpenMP vector algebra -- the reference's
+    'solve stays on the host' path restated.  ``iters`` fixed iterations from x = 0; returns
+    (seconds, residual history)."""
+    from firedrake_b200.fiat_lite import interval_element
+    from oracle import oracle
+    el = interval_element(p)
+    coords = np.ascontiguousarray(mesh.coordinates)
+    n = V.node_count
+    xin, Ap = np.empty(n), np.empty(n)
+
+    def mult(v, out):
+        np.copyto(xin, v)
+        xin[bc_nodes] = 0.0
+        out[:] = 0.0
+        oracle.action_extruded_parallel(el, mesh, out, coords, xin, V.cell_node_map, V.offset, mesh.coord_map,
+                                        mesh.coord_offset, native=True)
+        out[bc_nodes] = v[bc_nodes]
+
+    x = np.zeros(n)
+    r = b.copy()
+    pv = r.copy()
+    t0 = time.perf_counter()
+    rr = oracle.vec_dot(r, r)
+    hist = [float(np.sqrt(rr))]
+    for _ in range(iters):
+        mult(pv, Ap)
+        alpha = rr / oracle.vec_dot(pv, Ap)
+        oracle.vec_axpy(alpha, pv, x)
+        oracle.vec_axpy(-alpha, Ap, r)
+        rr_new = oracle.vec_dot(r, r)
+        oracle.vec_aypx(rr_new / rr, r, pv)
+        rr = rr_new
+        hist.append(float(np.sqrt(rr)))
+    return time.perf_counter() - t0, hist
+
+
 def run_reference(args):
     """--impl reference: K 'steps', each one bounded pass of the CPU arm (above)."""
     reps = max(5, min(args.steps, 10))
@@ -253,6 +297,23 @@ def oracle_parity(args, part, mesh, V, x, y, rank, world, dist):
     el = interval_element(args.degree)
     xh = np.ascontiguousarray(x.data_ro_with_halos if hasattr(x, "data_ro_with_halos") else x.data_with_halos)
     yh = np.ascontiguousarray(y.data_ro_with_halos if hasattr(y, "data_ro_with_halos") else y.data_with_halos)
+    if world > 1:
+        # ghost rows of x straight from their owners' HOST copies over gloo (independent of the
+        # device halo exchange under test)
+        import torch
+        xh = xh.copy()
+        flat = xh.reshape(-1)
+        reqs, bufs = [], []
+        for nb, send, recv in part.neighbours:
+            if len(send):
+                reqs.append(dist.isend(torch.from_numpy(np.ascontiguousarray(flat[send])), nb))
+        for nb, send, recv in part.neighbours:
+            if len(recv):
+                t = torch.empty(len(recv), dtype=torch.float64)
+                dist.recv(t, nb)
+                flat[recv] = t.numpy()
+        for r in reqs:
+            r.wait()
     yo = np.zeros(V.node_count)
     ncpu = len(os.sched_getaffinity(0))
     t0 = time.perf_counter()
@@ -260,7 +321,7 @@ def oracle_parity(args, part, mesh, V, x, y, rank, world, dist):
                                     V.cell_node_map, V.offset, mesh.coord_map, mesh.coord_offset,
                                     nthreads=max(1, ncpu // world), native=True)
     t_or = time.perf_counter() - t0
-    if world > 1:
+    if world > 1 and not part.exec_halo:
         import torch
         # ghost plane (my left face, owned by rank-1) -> owner adds (local_to_global, SUM)
         reqs = []
@@ -268,7 +329,7 @@ def oracle_parity(args, part, mesh, V, x, y, rank, world, dist):
             send = torch.from_numpy(np.ascontiguousarray(yo[V.plane_nodes(0)]))
             reqs.append(dist.isend(send, rank - 1))
         if rank < world - 1:
-            hi = V.plane_nodes(mesh.nx)
+            hi = V.plane_nodes(part.x1 - part.x0)
             recv = torch.empty(len(hi), dtype=torch.float64)
             dist.recv(recv, rank + 1)
             yo[hi] += recv.numpy()
@@ -411,7 +472,7 @@ def main():
 
     e2e = None
     if not args.no_e2e:
-        nst = max(1, min(args.steps, 5))
+        nst = max(1, args.steps)
         if world == 1:
             hloop = op2.Parloop(gk, cells, [y(op2.INC, m0), X(op2.READ, m1), x(op2.READ, m0)], location="host")
             def hstep():
@@ -424,6 +485,7 @@ def main():
         else:
             def hstep():
                 x.data_with_halos[0] += 0.0      # host write -> H2D of the local x
+                x.halo_valid = False             # ... whose ghost rows are stale again
                 y.zero()
                 loop()                           # exchanges + kernels on device-resident mirrors
                 return float(y.data_ro[0])       # D2H of the local y
@@ -455,7 +517,10 @@ def main():
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args),
                    "quadrature": f"Gauss-Legendre {p + 1}^3 (dx(degree={2 * p}))",
-                   "parallelism": f"{world} slab(s) along x, NCCL halo exchange of one {n * p + 1}^2-dof face per neighbour"
+                   "parallelism": (f"{world} slab(s) along x, NCCL halo exchange; "
+                                   + ("exec-halo mode: one redundant cell column per rank, ghost reads of x only "
+                                      f"({p + 1} planes of {n * p + 1}^2 dofs), no ghost-sum reduce" if args.halo == "exec"
+                                      else f"one {n * p + 1}^2-dof face per neighbour each way (ghost read + ghost sum)"))
                                   if world > 1 else "single GPU",
                    "l2": "inputs (x,y: %.1f GB per rank) exceed the 126 MB L2; no flush needed"
                          % (2 * 8 * V.node_count / 1e9),

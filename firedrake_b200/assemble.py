@@ -39,6 +39,9 @@ class FunctionSpace:
         else:
             cell_sizes, node_sizes, halo = mesh.num_base_cells, V.node_count, None
         self.cell_set = op2.ExtrudedSet(op2.Set(cell_sizes), mesh.layers)
+        # exec-halo partition: a property of the WHOLE distributed set (the last rank holds no
+        # exec cells but must follow the same protocol)
+        self.cell_set.owner_computes = bool(getattr(partition, "exec_halo", False))
         self.node_set = op2.Set(node_sizes)
         self.dof_dset = op2.DataSet(self.node_set, cdim, halo=halo)
         self.vertex_set = op2.Set(mesh.coord_space.node_count)

@@ -257,26 +257,12 @@ struct Unit {
 // the trilinear terms of the coordinate field vanish, the Jacobian is constant per cell and the
 // metric G = (alpha / |det|) K K^T (K = cofactor rows) is formed once per cell instead of at
 // each of the N^3 quadrature points.
-// NOROT (round 2): the rolled zeta loop no longer keeps U / Vp column-rotated in registers (64
-// IMAD.MOV per trip, 8 % of all issued instructions at p = 3).  The only quantities the loop needs
-// at a RUN-TIME zeta index -- the xi-derivative gx[qx][qz] going in and the xi-flux fx[qx][qz]
-// coming out -- pass through a lane-private shared-memory scratch ([N*N slots][32 lanes], conflict
-// free), exactly as the eta-derivative / eta-flux already pass through the tile; the Dt-along-xi
-// contractions move out of the loop as full static-index contractions (same flop count).  The
-// scratch aliases s_u: the gather of the NEXT unit is issued after the loop instead of inside it.
-// Not for MASS (the mass term needs a second run-time-indexed slab) nor MATRIX.
-// CD1: cdim == 1 folded at compile time (one IMAD.WIDE per gather / scatter address instead of
-// IMAD.WIDE + LEA + LEA.HI.X).
-template <int N, bool MASS, bool ATOMIC, int MINB, bool MATRIX = false, bool SLIM = false, bool AFFINE = false,
-          bool NOROT = false, bool CD1 = false>
+template <int N, bool MASS, bool ATOMIC, int MINB, bool MATRIX = false, bool SLIM = false, bool AFFINE = false>
 __global__ void __launch_bounds__(WPC<N, SLIM>::value * 32, MINB)
 helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
 {
     static_assert(!(SLIM && MATRIX), "matrix mode keeps the per-cell index buffer");
     static_assert(!(AFFINE && MATRIX), "the affine variant exists for 1-forms only");
-    static_assert(!(NOROT && (MASS || MATRIX)), "the no-rotation loop exists for stiffness-only 1-forms");
-    static_assert(!(CD1 && MATRIX), "matrix mode uses cdim as its unit counter");
-    static_assert(N * N * 32 <= WarpSmem<N, SLIM>::UBUF, "the xi scratch must fit in the value buffer");
     using WS = WarpSmem<N, SLIM>;
     constexpr int CW = WS::CW;
     constexpr int CWS = WS::CWS;
@@ -313,7 +299,7 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
     // worth) handed out by an atomic counter -> locality inside a chunk,
     // dynamic balance across SMs
     auto advance = [&](Unit u) -> Unit {
-        if (!CD1 && u.item >= 0 && u.comp + 1 < P.cdim) {
+        if (u.item >= 0 && u.comp + 1 < P.cdim) {
             u.comp++;
             return u;
         }
@@ -431,8 +417,7 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
             if (!MATRIX) {
 #pragma unroll
                 for (int j = 0; j < N; j++)
-                    cp_async8(su + (part * N + j) * N + t,
-                              CD1 ? P.x + g[j] : P.x + (long long)g[j] * P.cdim + u.comp);
+                    cp_async8(su + (part * N + j) * N + t, P.x + (long long)g[j] * P.cdim + u.comp);
             }
         }
     };
@@ -552,100 +537,6 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
             for (int i = 0; i < N; i++)
 #pragma unroll
                 for (int j = 0; j < N; j++) Vp[i][j] = 0.0;
-            if (NOROT) {
-                // ---- no-rotation quadrature loop (see the comment above the kernel)
-                double *xs = s_u + lane;                     // lane-private scratch: slot s at xs[s * 32]
-                {
-                    double Gx[N][N];
-                    apply_first<N, false>(P.Dt, U, Gx);      // d/d xi at every point, static indices
-                    __syncwarp();                            // every lane has consumed its gathered values
-#pragma unroll
-                    for (int i = 0; i < N; i++)
-#pragma unroll
-                        for (int j = 0; j < N; j++) xs[(i * N + j) * 32] = Gx[i][j];
-                }
-                stageB_coords(nxt);
-#pragma unroll 1
-                for (int qz = 0; qz < N; qz++) {
-                    const double zeta = P.xq[qz];
-                    double dz[N];
-#pragma unroll
-                    for (int j = 0; j < N; j++) dz[j] = P.Dt[qz * N + j];
-                    double ca[3], pb[3], qb[3];
-                    if (!AFFINE) {
-#pragma unroll
-                        for (int a = 0; a < 3; a++) {
-                            ca[a] = fma(A6[a], zeta, A1[a]);       // dx/dxi
-                            pb[a] = fma(c5[a], zeta, c2[a]);
-                            qb[a] = fma(c7[a], zeta, c4[a]);
-                        }
-                    }
-                    const double wyz_a = wy_alpha * P.wq[qz];
-                    double *trow = tile.row_Y(qz);
-                    double *xrow = xs + qz * 32;
-#pragma unroll
-                    for (int qx = 0; qx < N; qx++) {
-                        const double xi = P.xq[qx];
-                        double gz = 0.0;
-#pragma unroll
-                        for (int q = 0; q < N; q++) gz = fma(dz[q], U[qx][q], gz);
-                        const double gx = xrow[qx * N * 32];
-                        const double gy = trow[qx * N * N];
-                        double fx, fy, fz;
-                        if (AFFINE) {
-                            const double wq3 = wyz_a * P.wq[qx];
-                            fx = wq3 * (Gm[0] * gx + Gm[1] * gy + Gm[2] * gz);
-                            fy = wq3 * (Gm[1] * gx + Gm[3] * gy + Gm[4] * gz);
-                            fz = wq3 * (Gm[2] * gx + Gm[4] * gy + Gm[5] * gz);
-                        } else {
-                            double cb[3], cc[3];
-#pragma unroll
-                            for (int a = 0; a < 3; a++) {
-                                cb[a] = fma(qb[a], xi, pb[a]);     // dx/deta
-                                cc[a] = fma(A6[a], xi, A3[a]);     // dx/dzeta
-                            }
-                            double r0[3], r1[3], r2[3];
-                            r0[0] = cb[1] * cc[2] - cb[2] * cc[1];
-                            r0[1] = cb[2] * cc[0] - cb[0] * cc[2];
-                            r0[2] = cb[0] * cc[1] - cb[1] * cc[0];
-                            r1[0] = cc[1] * ca[2] - cc[2] * ca[1];
-                            r1[1] = cc[2] * ca[0] - cc[0] * ca[2];
-                            r1[2] = cc[0] * ca[1] - cc[1] * ca[0];
-                            r2[0] = ca[1] * cb[2] - ca[2] * cb[1];
-                            r2[1] = ca[2] * cb[0] - ca[0] * cb[2];
-                            r2[2] = ca[0] * cb[1] - ca[1] * cb[0];
-                            const double det = ca[0] * r0[0] + ca[1] * r0[1] + ca[2] * r0[2];
-                            const double sc_ = wyz_a * P.wq[qx] * fast_rcp(fabs(det));
-                            double h[3];
-#pragma unroll
-                            for (int a = 0; a < 3; a++) h[a] = r0[a] * gx + r1[a] * gy + r2[a] * gz;
-                            fx = sc_ * (r0[0] * h[0] + r0[1] * h[1] + r0[2] * h[2]);
-                            fy = sc_ * (r1[0] * h[0] + r1[1] * h[1] + r1[2] * h[2]);
-                            fz = sc_ * (r2[0] * h[0] + r2[1] * h[1] + r2[2] * h[2]);
-                        }
-                        trow[qx * N * N] = fy;
-                        xrow[qx * N * 32] = fx;
-#pragma unroll
-                        for (int q = 0; q < N; q++) Vp[qx][q] = fma(dz[q], fz, Vp[qx][q]);
-                    }
-                }
-                {
-                    // xi-flux back through Dt^T (static indices), then the scratch is free again
-                    double Fx[N][N], T2[N][N];
-#pragma unroll
-                    for (int i = 0; i < N; i++)
-#pragma unroll
-                        for (int j = 0; j < N; j++) Fx[i][j] = xs[(i * N + j) * 32];
-                    apply_first<N, true>(P.Dt, Fx, T2);
-#pragma unroll
-                    for (int i = 0; i < N; i++)
-#pragma unroll
-                        for (int j = 0; j < N; j++) Vp[i][j] += T2[i][j];
-                }
-                __syncwarp();                                // scratch reads done before the next gather lands
-#pragma unroll
-                for (int part = 0; part < N; part++) stageB_part(nxt, ubuf ^ 1, part);
-            } else {
             // single-buffered staging: the values / coordinates of `cur` were
             // consumed (and a __syncwarp passed) before this point
             stageB_coords(nxt);
@@ -749,8 +640,6 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
                 }
             }
 
-            }
-
             __syncwarp();            // all lanes are done reading the staged rows of `nxt`
             stageA(nn);
             cp_async_commit();
@@ -826,7 +715,7 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
                     for (int yy = 0; yy < N; yy++) {
                         const int loc = (x * N + yy) * N + t;
                         const int g = SLIM ? smc[loc] + s_off0[loc] * cur.layer : si[loc];
-                        double *dst = CD1 ? P.y + g : P.y + (long long)g * P.cdim + comp;
+                        double *dst = P.y + (long long)g * P.cdim + comp;
                         if (ATOMIC) atomicAdd(dst, u[x][yy]);
                         else *dst += u[x][yy];
                     }
@@ -839,14 +728,13 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
     cp_async_wait<0>();
 }
 
-template <int N, bool MASS, bool ATOMIC, int MINB, bool MATRIX = false, bool SLIM = false, bool AFFINE = false,
-          bool NOROT = false, bool CD1 = false>
+template <int N, bool MASS, bool ATOMIC, int MINB, bool MATRIX = false, bool SLIM = false, bool AFFINE = false>
 int launch_one(int grid_cap_per_sm, cudaStream_t st, HelmParams<N> &P, int sm_count)
 {
     using WS = WarpSmem<N, SLIM>;
     constexpr int WARPS_PER_CTA = WPC<N, SLIM>::value;
     constexpr int T = WARPS_PER_CTA * 32;
-    auto kern = helmholtz_action_kernel<N, MASS, ATOMIC, MINB, MATRIX, SLIM, AFFINE, NOROT, CD1>;
+    auto kern = helmholtz_action_kernel<N, MASS, ATOMIC, MINB, MATRIX, SLIM, AFFINE>;
     static bool configured = false;
     static int occ = 1;
     if (!configured) {
@@ -885,14 +773,6 @@ template <int N, bool ATOMIC>
 int launch_variant(bool mass, int minb, int cap, cudaStream_t st, HelmParams<N> &P, int sm_count,
                    bool affine = false)
 {
-    // stiffness-only scalar 1-forms (Poisson: configs 2 and 5): no-rotation loop, cdim folded
-    static const bool norot_on = !(getenv("FDB_NOROT") && atoi(getenv("FDB_NOROT")) == 0);
-    if (ATOMIC && !mass && P.cdim == 1 && norot_on && (N != 6 || P.nlay_items >= 32 / N)) {
-        constexpr int NB = (N == 4) ? 3 : ((N >= 5) ? 1 : 2);
-        constexpr bool NSL = (N == 6);
-        if (affine) return launch_one<N, false, true, NB, false, NSL, true, true, true>(cap, st, P, sm_count);
-        return launch_one<N, false, true, NB, false, NSL, false, true, true>(cap, st, P, sm_count);
-    }
     if (affine && ATOMIC) {
         // affine cells (caller's promise): per-cell metric; same staging / occupancy choices
         constexpr int AB = (N == 4) ? 3 : ((N >= 5) ? 1 : 2);

@@ -70,6 +70,53 @@ __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, do
                  : "d"(a), "d"(b));
 }
 
+// metric G_q (6 entries, alpha w / |det J| K K^T) and mass factor beta w |det J| of one quadrature point
+template <int N>
+__device__ __forceinline__ void geometry_point(const BdbParams &P, const double *sX, double *g, int q, bool real)
+{
+    if (!real) {
+#pragma unroll
+        for (int e = 0; e < 7; e++) g[e] = 0.0;
+        return;
+    }
+    const int qx = q / (N * N), qy = (q / N) % N, qz = q % N;
+    const double xi = P.xq[qx], eta = P.xq[qy], zeta = P.xq[qz];
+    double ja[3], jb[3], jc[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        const double X000 = sX[0 * 3 + a], X001 = sX[1 * 3 + a], X010 = sX[2 * 3 + a],
+                     X011 = sX[3 * 3 + a], X100 = sX[4 * 3 + a], X101 = sX[5 * 3 + a],
+                     X110 = sX[6 * 3 + a], X111 = sX[7 * 3 + a];
+        const double c1 = X100 - X000, c2 = X010 - X000, c3 = X001 - X000;
+        const double c4 = X110 - X100 - X010 + X000, c5 = X011 - X010 - X001 + X000,
+                     c6 = X101 - X100 - X001 + X000;
+        const double c7 = X111 - X110 - X101 - X011 + X100 + X010 + X001 - X000;
+        ja[a] = c1 + c4 * eta + (c6 + c7 * eta) * zeta;      // dx/dxi
+        jb[a] = c2 + c5 * zeta + (c4 + c7 * zeta) * xi;      // dx/deta
+        jc[a] = c3 + c5 * eta + (c6 + c7 * eta) * xi;        // dx/dzeta
+    }
+    double r0[3], r1[3], r2[3];
+    r0[0] = jb[1] * jc[2] - jb[2] * jc[1];
+    r0[1] = jb[2] * jc[0] - jb[0] * jc[2];
+    r0[2] = jb[0] * jc[1] - jb[1] * jc[0];
+    r1[0] = jc[1] * ja[2] - jc[2] * ja[1];
+    r1[1] = jc[2] * ja[0] - jc[0] * ja[2];
+    r1[2] = jc[0] * ja[1] - jc[1] * ja[0];
+    r2[0] = ja[1] * jb[2] - ja[2] * jb[1];
+    r2[1] = ja[2] * jb[0] - ja[0] * jb[2];
+    r2[2] = ja[0] * jb[1] - ja[1] * jb[0];
+    const double adet = fabs(ja[0] * r0[0] + ja[1] * r0[1] + ja[2] * r0[2]);
+    const double w = P.wq[qx] * P.wq[qy] * P.wq[qz];
+    const double s = P.alpha * w / adet;
+    g[0] = s * (r0[0] * r0[0] + r0[1] * r0[1] + r0[2] * r0[2]);
+    g[1] = s * (r0[0] * r1[0] + r0[1] * r1[1] + r0[2] * r1[2]);
+    g[2] = s * (r0[0] * r2[0] + r0[1] * r2[1] + r0[2] * r2[2]);
+    g[3] = s * (r1[0] * r1[0] + r1[1] * r1[1] + r1[2] * r1[2]);
+    g[4] = s * (r1[0] * r2[0] + r1[1] * r2[1] + r1[2] * r2[2]);
+    g[5] = s * (r2[0] * r2[0] + r2[1] * r2[1] + r2[2] * r2[2]);
+    g[6] = P.beta * w * adet;
+}
+
 template <int N>
 struct BdbCfg {
     static constexpr int ND = N * N * N;
@@ -140,50 +187,7 @@ __global__ void __launch_bounds__(256, (N >= 5) ? 1 : 3) bdb_matrix_kernel(const
             sCol[i] = gc;
         }
         __syncthreads();
-        for (int q = tid; q < C::NCHUNK * KQ; q += 256) {
-            double *g = sG + q * 7;
-            if (q >= Q3) {
-#pragma unroll
-                for (int e = 0; e < 7; e++) g[e] = 0.0;
-                continue;
-            }
-            const int qx = q / (N * N), qy = (q / N) % N, qz = q % N;
-            const double xi = P.xq[qx], eta = P.xq[qy], zeta = P.xq[qz];
-            double ja[3], jb[3], jc[3];
-#pragma unroll
-            for (int a = 0; a < 3; a++) {
-                const double X000 = sX[0 * 3 + a], X001 = sX[1 * 3 + a], X010 = sX[2 * 3 + a],
-                             X011 = sX[3 * 3 + a], X100 = sX[4 * 3 + a], X101 = sX[5 * 3 + a],
-                             X110 = sX[6 * 3 + a], X111 = sX[7 * 3 + a];
-                const double c1 = X100 - X000, c2 = X010 - X000, c3 = X001 - X000;
-                const double c4 = X110 - X100 - X010 + X000, c5 = X011 - X010 - X001 + X000,
-                             c6 = X101 - X100 - X001 + X000;
-                const double c7 = X111 - X110 - X101 - X011 + X100 + X010 + X001 - X000;
-                ja[a] = c1 + c4 * eta + (c6 + c7 * eta) * zeta;      // dx/dxi
-                jb[a] = c2 + c5 * zeta + (c4 + c7 * zeta) * xi;      // dx/deta
-                jc[a] = c3 + c5 * eta + (c6 + c7 * eta) * xi;        // dx/dzeta
-            }
-            double r0[3], r1[3], r2[3];
-            r0[0] = jb[1] * jc[2] - jb[2] * jc[1];
-            r0[1] = jb[2] * jc[0] - jb[0] * jc[2];
-            r0[2] = jb[0] * jc[1] - jb[1] * jc[0];
-            r1[0] = jc[1] * ja[2] - jc[2] * ja[1];
-            r1[1] = jc[2] * ja[0] - jc[0] * ja[2];
-            r1[2] = jc[0] * ja[1] - jc[1] * ja[0];
-            r2[0] = ja[1] * jb[2] - ja[2] * jb[1];
-            r2[1] = ja[2] * jb[0] - ja[0] * jb[2];
-            r2[2] = ja[0] * jb[1] - ja[1] * jb[0];
-            const double adet = fabs(ja[0] * r0[0] + ja[1] * r0[1] + ja[2] * r0[2]);
-            const double w = P.wq[qx] * P.wq[qy] * P.wq[qz];
-            const double s = P.alpha * w / adet;
-            g[0] = s * (r0[0] * r0[0] + r0[1] * r0[1] + r0[2] * r0[2]);
-            g[1] = s * (r0[0] * r1[0] + r0[1] * r1[1] + r0[2] * r1[2]);
-            g[2] = s * (r0[0] * r2[0] + r0[1] * r2[1] + r0[2] * r2[2]);
-            g[3] = s * (r1[0] * r1[0] + r1[1] * r1[1] + r1[2] * r1[2]);
-            g[4] = s * (r1[0] * r2[0] + r1[1] * r2[1] + r1[2] * r2[2]);
-            g[5] = s * (r2[0] * r2[0] + r2[1] * r2[1] + r2[2] * r2[2]);
-            g[6] = P.beta * w * adet;
-        }
+        for (int q = tid; q < C::NCHUNK * KQ; q += 256) geometry_point<N>(P, sX, sG + q * 7, q, q < Q3);
 
         double acc[C::MT][C::NT][2];
 #pragma unroll
@@ -262,6 +266,196 @@ __global__ void __launch_bounds__(256, (N >= 5) ? 1 : 3) bdb_matrix_kernel(const
     }
 }
 
+// ---- symmetric variant for NP = 128 (p = 4, config 4) -----------------------------------------
+// A = L^T (D L) is symmetric (G_q is), so only the upper triangle of the 16 x 16 grid of 8 x 8
+// DMMA tiles is computed: 136 tiles instead of 256.  Warps 0..5 own the six off-diagonal 32 x 32
+// super-blocks (16 tiles each), warps 6 and 7 the upper tiles of two diagonal super-blocks each
+// (2 x 10 tiles); the accumulator shrinks from 64 to 40 doubles per thread, which lets TWO cells
+// be resident per SM: one cell's scatter (n^2 RED.ADD.F64, the mirrored entry written from the same
+// register) overlaps the other cell's DMMAs.
+__device__ __forceinline__ constexpr int dtile(int m, int n)   // index of tile (m <= n) in a 4x4 upper triangle
+{
+    return m * 4 - m * (m - 1) / 2 + (n - m);
+}
+
+template <int N>
+__global__ void __launch_bounds__(256, 2) bdb_matrix_sym_kernel(const __grid_constant__ BdbParams P)
+{
+    using C = BdbCfg<N>;
+    constexpr int ND = C::ND, NP = C::NP, S = C::S, Q3 = C::Q3;
+    static_assert(NP == 128, "the symmetric tiling is written for a 128 x 128 padded element matrix");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *sL = reinterpret_cast<double *>(smem_raw);        // [2][KR][S]
+    double *sR = sL + 2 * KR * S;                              // [KR][S]
+    double *sG = sR + KR * S;                                  // [NCHUNK*KQ][7]
+    double *sX = sG + C::NCHUNK * KQ * 7;                      // [24]
+    long long *sRow = reinterpret_cast<long long *>(sX + 24);  // [NP]
+    int *sCol = reinterpret_cast<int *>(sRow + NP);            // [NP]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gid = lane >> 2, tig = lane & 3;
+    const long long ncells = (long long)P.ncols * P.nlay;
+    // off-diagonal super-block of warps 0..5: (0,1) (0,2) (0,3) (1,2) (1,3) (2,3)
+    const int bi = warp < 3 ? 0 : (warp < 5 ? 1 : 2);
+    const int bj = warp < 3 ? warp + 1 : (warp < 5 ? warp - 1 : 3);
+    const bool offdiag = warp < 6;
+    const int d0 = (warp - 6) * 2;                             // diagonal super-blocks d0, d0 + 1 (warps 6, 7)
+
+    for (long long cell = blockIdx.x; cell < ncells; cell += gridDim.x) {
+        const int ci = (int)(cell / P.nlay), layer = (int)(cell - (long long)ci * P.nlay);
+        const int col = P.collist ? P.collist[ci] : P.col0 + ci;
+        __syncthreads();
+        auto stage_L = [&](int chunk, int buf) {
+            const double *src = P.table + (size_t)chunk * KR * NP;
+            double *dst = sL + buf * KR * S;
+            for (int e = tid; e < KR * NP / 2; e += 256) {
+                const int row = e / (NP / 2), c2 = e - row * (NP / 2);
+                cp_async16(dst + row * S + 2 * c2, src + row * NP + 2 * c2);
+            }
+            cp_async_commit();
+        };
+        stage_L(0, 0);
+        if (tid < 24) {
+            const int v = tid / 3, a = tid - v * 3;
+            const int g = P.map1[(long long)col * 8 + v] + P.off1[v] * layer;
+            sX[tid] = P.coords[(long long)g * 3 + a];
+        }
+        for (int i = tid; i < NP; i += 256) {
+            long long rs = -1;
+            int gc = -1;
+            if (i < ND) {
+                const int g = P.map0[(long long)col * ND + i] + P.off0[i] * layer;
+                int gr = P.row_lg ? P.row_lg[g] : g;
+                gc = P.col_lg ? P.col_lg[g] : g;
+                if (gr >= 0) rs = P.rank_tab ? P.rowptr[gr] : (long long)gr;
+            }
+            sRow[i] = rs;
+            sCol[i] = gc;
+        }
+        __syncthreads();
+        for (int q = tid; q < C::NCHUNK * KQ; q += 256) geometry_point<N>(P, sX, sG + q * 7, q, q < Q3);
+
+        double acc[40];
+#pragma unroll
+        for (int e = 0; e < 40; e++) acc[e] = 0.0;
+
+        for (int chunk = 0; chunk < C::NCHUNK; chunk++) {
+            const int buf = chunk & 1;
+            cp_async_wait_all();
+            __syncthreads();
+            if (chunk + 1 < C::NCHUNK) stage_L(chunk + 1, buf ^ 1);
+            const double *L = sL + buf * KR * S;
+            for (int e = tid; e < KQ * NP; e += 256) {
+                const int ql = e / NP, j = e - ql * NP;
+                const double *g = sG + (chunk * KQ + ql) * 7;
+                const double l0 = L[(ql * 4 + 0) * S + j], l1 = L[(ql * 4 + 1) * S + j],
+                             l2 = L[(ql * 4 + 2) * S + j], l3 = L[(ql * 4 + 3) * S + j];
+                sR[(ql * 4 + 0) * S + j] = g[0] * l0 + g[1] * l1 + g[2] * l2;
+                sR[(ql * 4 + 1) * S + j] = g[1] * l0 + g[3] * l1 + g[4] * l2;
+                sR[(ql * 4 + 2) * S + j] = g[2] * l0 + g[4] * l1 + g[5] * l2;
+                sR[(ql * 4 + 3) * S + j] = g[6] * l3;
+            }
+            __syncthreads();
+            if (offdiag) {
+#pragma unroll
+                for (int ks = 0; ks < KR / 4; ks++) {
+                    double af[4], bf[4];
+                    const double *Lk = L + (ks * 4 + tig) * S + bi * 32 + gid;
+                    const double *Rk = sR + (ks * 4 + tig) * S + bj * 32 + gid;
+#pragma unroll
+                    for (int m = 0; m < 4; m++) af[m] = Lk[m * 8];
+#pragma unroll
+                    for (int n = 0; n < 4; n++) bf[n] = Rk[n * 8];
+#pragma unroll
+                    for (int m = 0; m < 4; m++)
+#pragma unroll
+                        for (int n = 0; n < 4; n++)
+                            dmma_m8n8k4(acc[(m * 4 + n) * 2], acc[(m * 4 + n) * 2 + 1], af[m], bf[n]);
+                }
+            } else {
+#pragma unroll
+                for (int ks = 0; ks < KR / 4; ks++) {
+#pragma unroll
+                    for (int d = 0; d < 2; d++) {
+                        double af[4], bf[4];
+                        const double *Lk = L + (ks * 4 + tig) * S + (d0 + d) * 32 + gid;
+                        const double *Rk = sR + (ks * 4 + tig) * S + (d0 + d) * 32 + gid;
+#pragma unroll
+                        for (int m = 0; m < 4; m++) {
+                            af[m] = Lk[m * 8];
+                            bf[m] = Rk[m * 8];
+                        }
+#pragma unroll
+                        for (int m = 0; m < 4; m++)
+#pragma unroll
+                            for (int n = m; n < 4; n++)
+                                dmma_m8n8k4(acc[(d * 10 + dtile(m, n)) * 2], acc[(d * 10 + dtile(m, n)) * 2 + 1],
+                                            af[m], bf[n]);
+                    }
+                }
+            }
+        }
+
+        // ---- scatter: (i, j) and, off the diagonal tiles, the mirrored (j, i)
+        const unsigned short *rk = nullptr;
+        if (P.rank_tab) {
+            const int v = P.nlay < 3 ? layer : (layer == 0 ? 0 : (layer == P.nlay - 1 ? 2 : 1));
+            rk = P.rank_tab + ((long long)col * P.nvar + v) * ND * ND;
+        }
+        auto add = [&](int i, int j, double val) {     // row (test) dof i, column (trial) dof j
+            const long long rs = sRow[i];
+            const int gc = sCol[j];
+            if (rs < 0 || gc < 0) return;
+            long long pos;
+            if (rk) {
+                pos = rs + rk[j * ND + i];
+            } else {
+                long long lo = P.rowptr[rs], hi = P.rowptr[rs + 1];
+                while (hi - lo > 1) {
+                    const long long mid = (lo + hi) >> 1;
+                    if (P.colidx[mid] <= gc) lo = mid; else hi = mid;
+                }
+                pos = lo;
+            }
+            atomicAdd(P.vals + pos, val);
+        };
+        if (offdiag) {
+#pragma unroll
+            for (int m = 0; m < 4; m++) {
+                const int i = bi * 32 + m * 8 + gid;
+#pragma unroll
+                for (int n = 0; n < 4; n++)
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const int j = bj * 32 + n * 8 + tig * 2 + h;
+                        if (i < ND && j < ND) {
+                            add(i, j, acc[(m * 4 + n) * 2 + h]);
+                            add(j, i, acc[(m * 4 + n) * 2 + h]);
+                        }
+                    }
+            }
+        } else {
+#pragma unroll
+            for (int d = 0; d < 2; d++)
+#pragma unroll
+                for (int m = 0; m < 4; m++) {
+                    const int i = (d0 + d) * 32 + m * 8 + gid;
+#pragma unroll
+                    for (int n = m; n < 4; n++)
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            const int j = (d0 + d) * 32 + n * 8 + tig * 2 + h;
+                            if (i < ND && j < ND) {
+                                const double val = acc[(d * 10 + dtile(m, n)) * 2 + h];
+                                add(i, j, val);
+                                if (n != m) add(j, i, val);      // diagonal tiles hold both halves themselves
+                            }
+                        }
+                }
+        }
+    }
+}
+
 // table T[(q*4 + r)][NP]: r < 3 reference gradient component r of basis i at point q, r = 3 its value
 template <int N>
 int build_table(fdb_kernel_s *k)
@@ -321,7 +515,8 @@ int launch_bdb(fdb_kernel_s *k, fdb_int start, fdb_int end, int nlay, const fdb_
         P.wq[i] = k->desc.wq[i];
     }
     if (P.ncols <= 0 || nlay <= 0) return 0;
-    auto kern = bdb_matrix_kernel<N>;
+    static const bool sym_on = !(getenv("FDB_BDB_SYM") && atoi(getenv("FDB_BDB_SYM")) == 0);
+    auto kern = (C::NP == 128 && sym_on) ? bdb_matrix_sym_kernel<(C::NP == 128 ? N : 5)> : bdb_matrix_kernel<N>;
     static bool configured = false;
     static int occ = 1;
     if (!configured) {

@@ -91,6 +91,7 @@ def _drop_host_mirror(ptr):
 class Set:
     """Iteration/data set with ``[core | owned | ghost]`` partitions."""
     _extruded = False
+    owner_computes = False     # True: partitioned with exec-halo entries, INC loops need no reduce
 
     def __init__(self, size, name=None):
         if isinstance(size, (int, np.integer)):
@@ -954,6 +955,22 @@ class Parloop:
         incs = [a.data for a in self.args
                 if a.access == INC and isinstance(a.data, Dat) and a.data.dataset.halo is not None
                 and not a.data.frozen_halo]
+        base = self.iterset.superset if isinstance(self.iterset, Subset) else self.iterset
+        if getattr(base, "owner_computes", False) and not isinstance(self.iterset, Subset):
+            # the set is partitioned with EXEC-HALO entries (partition.SlabPartition(exec_halo=True),
+            # flagged on every rank, including those that hold no exec cells themselves): executing
+            # them redundantly completes every owned row locally, so INC Dats need no local->global
+            # reduce (SURVEY.md section 8e option (ii)); their ghost rows are left holding partial
+            # sums and are marked stale, as after the reference's reduce
+            for d in reads:
+                d.dataset.halo.global_to_local_begin(d)
+            self._compute(self.iterset.core_part)
+            for d in reads:
+                d.dataset.halo.global_to_local_end(d)
+            self._compute((self.iterset.core_size, self.iterset.total_size))   # owned + exec halo
+            for d in incs:
+                d._device_written(halo_valid=False)
+            return
         for d in incs:
             d._reset_ghost_rows(INC)
         for d in reads:

@@ -56,7 +56,7 @@ class ExtrudedHexMesh:
     """
 
     def __init__(self, nx, ny, nz, Lx=1.0, Ly=1.0, Lz=1.0, warp=0.0,
-                 permute_seed=None, ix0=0, nx_global=None, ghost_left=False):
+                 permute_seed=None, ix0=0, nx_global=None, ghost_left=False, halo_right=False):
         """``ix0``/``nx_global``/``ghost_left`` describe one slab of a larger
         mesh partitioned along x (firedrake_b200.partition): this mesh holds
         base cells ix0 .. ix0+nx-1 of an nx_global-wide mesh of x-extent Lx;
@@ -70,18 +70,24 @@ class ExtrudedHexMesh:
         self.ix0 = int(ix0)
         self.nx_global = int(nx_global) if nx_global is not None else self.nx
         self.ghost_left = bool(ghost_left)
+        self.halo_right = bool(halo_right)
         nx, ny = self.nx, self.ny
         ncell = nx * ny
         ix, iy = np.divmod(np.arange(ncell, dtype=np.int64), ny)
         if permute_seed is not None:
             perm = np.random.default_rng(permute_seed).permutation(ncell)
             ix, iy = ix[perm], iy[perm]
+        # cell classes: 0 core, 1 owned (touches the left ghost plane), 2 exec halo
+        cls = np.zeros(ncell, dtype=np.int64)
         if self.ghost_left:
-            order = np.argsort(ix == 0, kind="stable")      # ix == 0 cells last
-            ix, iy = ix[order], iy[order]
-            self.num_core_cells = int((ix != 0).sum())
-        else:
-            self.num_core_cells = ncell
+            cls[ix == 0] = 1
+        if self.halo_right:
+            cls[ix == nx - 1] = 2
+        if self.ghost_left or self.halo_right:
+            order = np.argsort(cls, kind="stable")
+            ix, iy, cls = ix[order], iy[order], cls[order]
+        self.num_core_cells = int((cls == 0).sum())
+        self.num_owned_cells = int((cls <= 1).sum())
         self.cell_ix, self.cell_iy = ix, iy
         self.num_base_cells = ncell
         self.layers = self.nz + 1          # node layers, as in ExtrudedSet
@@ -105,9 +111,15 @@ class ExtrudedHexMesh:
         self.num_entities = NV + NEy + NEx + ncell
         self._rank = _first_touch_rank(clo, self.num_entities)
         self.ghost_entities = np.zeros(0, dtype=np.int64)
-        if self.ghost_left:
-            # canonical plane order: vertices iy = 0..ny, then y-edges iy = 0..ny-1
-            ghosts = self.plane_entities(0)
+        if self.ghost_left or self.halo_right:
+            # canonical plane order: vertices iy = 0..ny, then y-edges iy = 0..ny-1; the right
+            # halo region follows in the order of column_region_entities()
+            parts = []
+            if self.ghost_left:
+                parts.append(self.plane_entities(0))
+            if self.halo_right:
+                parts.append(self.column_region_entities(nx - 1))
+            ghosts = np.concatenate(parts)
             is_ghost = np.zeros(self.num_entities, dtype=bool)
             is_ghost[ghosts] = True
             owned = np.nonzero(~is_ghost)[0]
@@ -146,6 +158,14 @@ class ExtrudedHexMesh:
         """Base entities on the plane x-index ``i`` (local), canonical order."""
         return np.concatenate([self._vertex(i, np.arange(self.ny + 1)),
                                self._yedge(i, np.arange(self.ny))]).astype(np.int64)
+
+    def column_region_entities(self, c):
+        """Base entities of cell column ``c`` (local) that lie strictly to the right of the plane
+        ``c``: x-edges, faces, then the plane ``c + 1`` -- canonical order shared by both sides of
+        an exec-halo exchange."""
+        return np.concatenate([self._xedge(c, np.arange(self.ny + 1)),
+                               self._face(c, np.arange(self.ny)),
+                               self.plane_entities(c + 1)]).astype(np.int64)
 
     def exterior_vertical_facets(self):
         """(base cells, local facet numbers) of the base mesh's exterior facets: local facet
@@ -294,6 +314,13 @@ class ExtrudedFunctionSpace:
         """All nodes on the plane x-index ``i`` in canonical order (entity by
         entity, bottom to top): the send/recv lists of the slab halo."""
         ents = self.mesh.plane_entities(i)
+        st, sz = self._ent_start[ents], self._ent_colsize[ents]
+        return np.concatenate([np.arange(a, a + b) for a, b in zip(st, sz)]).astype(IntType)
+
+    def column_region_nodes(self, c):
+        """All nodes of the base entities ``mesh.column_region_entities(c)`` (entity by entity,
+        bottom to top): send/recv list of the exec-halo region of cell column ``c``."""
+        ents = self.mesh.column_region_entities(c)
         st, sz = self._ent_start[ents], self._ent_colsize[ents]
         return np.concatenate([np.arange(a, a + b) for a, b in zip(st, sz)]).astype(IntType)
 

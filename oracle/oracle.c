@@ -517,6 +517,28 @@ int orc_action_bands(int degree, int nbands, const int *run_first, const int *ru
     return rc;
 }
 
+/* Vector algebra of the host Krylov baseline (bench.py cpu_cg_baseline): what PETSc's Vec
+ * operations do across the ranks of the reference's MPI run, here across OpenMP threads. */
+void orc_vec_axpy(int64_t n, double a, const double *x, double *y)      /* y += a x */
+{
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; i++) y[i] += a * x[i];
+}
+
+void orc_vec_aypx(int64_t n, double a, const double *x, double *y)      /* y = x + a y */
+{
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; i++) y[i] = x[i] + a * y[i];
+}
+
+double orc_vec_dot(int64_t n, const double *x, const double *y)
+{
+    double s = 0.0;
+#pragma omp parallel for schedule(static) reduction(+ : s)
+    for (int64_t i = 0; i < n; i++) s += x[i] * y[i];
+    return s;
+}
+
 int orc_num_threads(void)
 {
 #ifdef _OPENMP

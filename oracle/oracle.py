@@ -90,6 +90,7 @@ def lib(native=False):
         path = build()
     L = ctypes.CDLL(path)
     L.orc_build_sparsity.restype = ctypes.c_int64
+    L.orc_vec_dot.restype = ctypes.c_double
     _lib[key] = L
     L._path = path
     return L
@@ -302,6 +303,18 @@ def action_extruded_parallel(el, mesh, y, coords, x, map0, off0, map1, off1, cdi
     if rc:
         raise RuntimeError("oracle action_bands failed")
     return y
+
+
+def vec_axpy(a, x, y, native=True):
+    lib(native).orc_vec_axpy(ctypes.c_int64(x.size), ctypes.c_double(a), _d(x), _d(y))
+
+
+def vec_aypx(a, x, y, native=True):
+    lib(native).orc_vec_aypx(ctypes.c_int64(x.size), ctypes.c_double(a), _d(x), _d(y))
+
+
+def vec_dot(x, y, native=True):
+    return float(lib(native).orc_vec_dot(ctypes.c_int64(x.size), _d(x), _d(y)))
 
 
 def num_threads():

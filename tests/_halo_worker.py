@@ -17,11 +17,15 @@ from oracle import oracle                                   # noqa: E402
 
 rank, world, dist = comm_init_from_env()
 worst = 0.0
-for p, (nx, ny, nz) in [(1, (6, 4, 5)), (3, (7, 5, 9)), (2, (9, 3, 4))]:
-    part = SlabPartition(nx, ny, nz, p, rank, world, warp=0.05)
+# (degree, mesh, exec-halo partition?): the reference protocol (ghost-sum reduce) and the
+# owner-computes one (redundant exec-halo column, no reduce; SURVEY.md section 8e option (ii))
+for p, (nx, ny, nz), exec_halo in [(1, (6, 4, 5), False), (3, (7, 5, 9), False), (2, (9, 3, 4), False),
+                                   (3, (7, 5, 9), True), (1, (6, 4, 5), True), (4, (5, 3, 4), True)]:
+    part = SlabPartition(nx, ny, nz, p, rank, world, warp=0.05, exec_halo=exec_halo)
     mesh, V = part.mesh, part.V
     halo = Halo(part.neighbours)
     cells = op2.ExtrudedSet(op2.Set(part.cell_sizes), mesh.layers)
+    cells.owner_computes = part.exec_halo
     nodes = op2.Set(part.node_sizes)
     vnodes = op2.Set(mesh.coord_space.node_count)
     m0 = op2.Map(cells, nodes, V.arity, V.cell_node_map, offset=V.offset)

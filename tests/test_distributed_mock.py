@@ -76,6 +76,23 @@ def _worker(rank, world, port, q):
         z.device_ptr
         A.mult(u3, z)
         out["ismat"] = float(np.abs(z.data_ro[:no] - np.array([look_mat[k] for k in key(lat[:no]).tolist()])).max())
+        # exec-halo (owner-computes) partition: redundant execution of the right neighbour's first
+        # cell column replaces the local->global reduce (SURVEY.md section 8e option (ii))
+        for pdeg in (1, 3):
+            eng.dist = None
+            Gp = FunctionSpace(gm, pdeg)
+            gup = interpolate(Gp, expr)
+            gyp = OneFormAssembler(helmholtz(Gp), gup).assemble()
+            lookp = dict(zip(key(Gp.V.dof_lattice()).tolist(), gyp.data_ro.tolist()))
+            eng.dist = dist
+            parte = SlabPartition(nx, ny, nz, pdeg, rank, world, warp=0.05, exec_halo=True)
+            Ve = FunctionSpace(parte.mesh, pdeg, partition=parte)
+            ue = interpolate(Ve, expr)
+            ue.halo_valid = False
+            ye = OneFormAssembler(helmholtz(Ve), ue).assemble()
+            noe = Ve.V.owned_node_count
+            late = Ve.V.dof_lattice()
+            out["exec%d" % pdeg] = float(np.abs(ye.data_ro[:noe] - np.array([lookp[k] for k in key(late[:noe]).tolist()])).max())
         # advisor (round 1): a SECOND INC loop into the same Dat without zero() in between must add
         # this loop's contributions once (ghost rows restart from the INC identity)
         u4 = interpolate(V, expr)
@@ -136,6 +153,7 @@ def test_distributed_generic_parloops(world):
         assert out["ismat"] < 1e-12 * out["scale"], (rank, out)
         assert out["dx"] < 1e-12 and out["ds"] < 1e-12, (rank, out)
         assert out["twice"] < 1e-12 * out["scale"], (rank, out)
+        assert out["exec1"] < 1e-12 * out["scale"] and out["exec3"] < 1e-11 * out["scale"], (rank, out)
         assert out["cg_is"] < 1e-8 and abs(out["cg_its"][0] - out["cg_its"][1]) <= 2, (rank, out)
 
 
