@@ -452,23 +452,42 @@ def main():
         pass
     peak_gbs = peaks.get("hbm_gbs", 6650.0)
     abytes = algorithmic_bytes(V, mesh)
-    achieved = abytes / (kernel_ms * 1e-3) / 1e9
-    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one launch, from the
-    # `ncu --set full` capture summarised in profiles/r01_action_cg3_n256_summary.txt
-    # (8.28 GB read: x, coordinates and the y lines the atomics fetch; 3.86 GB written: y)
-    NCU_TRAFFIC = {(256, 3, 1): 12.14e9}
-    FP64_PEAK = 37.1   # TFLOP/s: tools/microbench_fp64.cu on this pool (DFMA 34.2, DMMA 37.1, shared pipe)
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                "frac": achieved / peak_gbs, "traffic": NCU_TRAFFIC.get((n, p, world)),
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
-                "kernel": f"helmholtz_action_kernel<{p + 1},false,true,3>", "kernel_ms": kernel_ms,
-                "algorithmic_bytes_per_launch": abytes,
-                "note": "this kernel is fp64-pipe-bound, not HBM-bound (DESIGN.md section 4): the binding "
-                        "fraction is fp64.frac; the HBM fraction is reported because the contract asks for it",
-                "fp64": {"flop_per_cell": kern.num_flops, "achieved_tflops":
-                         kern.num_flops * mesh.num_cells / (kernel_ms * 1e-3) / 1e12,
-                         "peak_tflops": FP64_PEAK, "peak_source": "measured DMMA/DFMA microbenchmark, profiles/"}}
-    roofline["fp64"]["frac"] = roofline["fp64"]["achieved_tflops"] / FP64_PEAK
+    hbm_achieved = abytes / (kernel_ms * 1e-3) / 1e9
+    kname = f"helmholtz_action_kernel<{p + 1},false,true,3>"
+    counts = {}
+    try:
+        counts = json.load(open(os.path.join(ROOT, "profiles", "kernel_counts.json"))).get(kname, {})
+    except Exception:
+        pass
+    # The kernel is fp64-pipe bound: the binding roofline is the fp64 FMA rate,
+    # 64 lanes/clk/SM (the DMMA/DFMA microbenchmark of profiles/r01_microbench_fp64.txt reaches 37.1 of
+    # these 37.2 TFLOP/s; MEASURED_PEAKS.json carries no fp64 figure).  Work = SASS-counted flops per
+    # cell (profiles/kernel_counts.json) when this kernel instance has been counted, else the model.
+    ctx_sm = C.c_int()
+    _lib.check(L.fdb_device_info(None, 0, C.byref(ctx_sm), None), "fdb_device_info")
+    sm_count = ctx_sm.value or 148
+    clk_hz = (clocks.get("sm_max_mhz") or 1965.0) * 1e6
+    fp64_peak = sm_count * 64 * 2 * clk_hz / 1e12
+    ncell_rank = mesh.num_cells
+    flop_cell = counts.get("flop_per_cell", kern.num_flops)
+    tf = flop_cell * ncell_rank / (kernel_ms * 1e-3) / 1e12
+    traffic = (counts.get("dram_bytes_per_launch") or {}).get(str(n)) if world == 1 else None
+    roofline = {"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
+                "traffic": traffic, "kernel": kname, "kernel_ms": kernel_ms,
+                "flop_per_cell": flop_cell,
+                "flop_source": "SASS count (profiles/kernel_counts.json, profiles/r02_action_cg3.sass)" if counts
+                               else "model 24 n^4 + 130 n^3 (kernel instance not counted)",
+                "peak_source": f"{sm_count} SMs x 64 fp64 FMA lanes/clk x 2 x {clk_hz / 1e9:.3f} GHz (clocks.sm_max_mhz); "
+                               "microbenchmark: 37.1 TFLOP/s (profiles/r01_microbench_fp64.txt)",
+                "traffic_source": "ncu --set full capture, profiles/r01_action_cg3_n256_summary.txt" if traffic else None,
+                "hbm": {"achieved": hbm_achieved, "peak": peak_gbs, "unit": "GB/s", "frac": hbm_achieved / peak_gbs,
+                        "algorithmic_bytes_per_launch": abytes,
+                        "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
+                        "note": "reported because the contract asks for it; with geometry recomputed at every "
+                                "quadrature point this workload cannot be HBM bound (SURVEY.md section 8d)"}}
+    if counts:
+        # share of the fp64 pipe's issue slots actually used (2 cycles per warp instruction per SMSP)
+        roofline["fp64_pipe_frac"] = (counts["fp64_instr_per_cell"] * ncell_rank / (sm_count * 64 * clk_hz)) / (kernel_ms * 1e-3)
 
     e2e = None
     if not args.no_e2e:

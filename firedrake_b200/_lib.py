@@ -96,6 +96,8 @@ SIGNATURES = {
     "fdb_synchronize": (C.c_int, []),
     "fdb_device_info": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
     "fdb_launch_count": (C.c_uint64, []),
+    "fdb_set_option": (C.c_int, [C.c_char_p, C.c_int]),
+    "fdb_get_option": (C.c_int, [C.c_char_p, C.POINTER(C.c_int)]),
     "fdb_malloc": (C.c_void_p, [C.c_size_t]),
     "fdb_free": (C.c_int, [C.c_void_p]),
     "fdb_memset": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t]),

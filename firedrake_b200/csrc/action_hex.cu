@@ -925,10 +925,12 @@ int fdb_launch_helmholtz_matrix(fdb_kernel_s *k, fdb_int start, fdb_int end, int
                                 const fdb_int *subset, fdb_mat_t mat, const double *coords,
                                 const fdb_int *map0, const fdb_int *map1, double *diag_out)
 {
-    // explicit matrices of degree >= 3: dense B^T D B on the fp64 tensor pipe (bdb_matrix.cu);
-    // FDB_MATRIX_DMMA=0 keeps the sum-factorised column-by-column kernel, =1 also takes degree 2
-    static const int dmma = getenv("FDB_MATRIX_DMMA") ? atoi(getenv("FDB_MATRIX_DMMA")) : -1;
-    if (mat && dmma != 0 && k->n1d <= 5 && k->n1d >= (dmma == 1 ? 3 : 4))
+    // explicit matrices: dense B^T D B on the fp64 tensor pipe (bdb_matrix.cu) where it is the
+    // faster kernel -- degree 4 (symmetric tiling, 11.9 ms against 18.2 ms for config 4 at 32^3);
+    // option "matrix_kernel": 0 keeps the sum-factorised column-by-column kernel everywhere, 1 takes
+    // the DMMA kernel for every instantiated degree (2..4)
+    const int dmma = fdb_opt_matrix_kernel;
+    if (mat && dmma != 0 && k->n1d <= 5 && k->n1d >= (dmma == 1 ? 3 : 5))
         return fdb_launch_helmholtz_matrix_dmma(k, start, end, nlay, subset, mat, coords, map0, map1);
     switch (k->n1d) {
     case 2: return launch_matrix_n<2>(k, start, end, nlay, subset, mat, coords, map0, map1, diag_out);
@@ -944,6 +946,11 @@ int fdb_launch_helmholtz_action(fdb_kernel_s *k, fdb_int start, fdb_int end, int
                                 const fdb_int *subset, double *y, const double *coords,
                                 const double *x, const fdb_int *map0, const fdb_int *map1)
 {
+    // degree 1 on extruded columns: one thread per cell (q1_action.cu); FDB_Q1_THREAD=0 opts out
+    static const bool q1_thread = !(getenv("FDB_Q1_THREAD") && atoi(getenv("FDB_Q1_THREAD")) == 0);
+    if (q1_thread && k->n1d == 2 && k->desc.cdim == 1 && k->desc.scatter == FDB_SCATTER_ATOMIC &&
+        k->desc.cell == FDB_CELL_HEX_EXTRUDED && nlay >= 16 && !k->desc.affine_cells)
+        return fdb_launch_q1_action(k, start, end, nlay, subset, y, coords, x, map0, map1);
     switch (k->n1d) {
     case 2: return launch_n<2>(k, start, end, nlay, subset, y, coords, x, map0, map1);
     case 3: return launch_n<3>(k, start, end, nlay, subset, y, coords, x, map0, map1);

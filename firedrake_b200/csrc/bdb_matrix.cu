@@ -456,6 +456,200 @@ __global__ void __launch_bounds__(256, 2) bdb_matrix_sym_kernel(const __grid_con
     }
 }
 
+// ---- symmetric variant for NP = 64 (p = 3): TWO cells per CTA ---------------------------------
+// 8 x 8 grid of DMMA tiles, upper triangle = 36 tiles, 4 warps per cell: two warps share the
+// off-diagonal 32 x 32 super-block (8 tiles each), two take the upper tiles of a diagonal
+// super-block (10 each).  The cell-independent L chunk is staged once for both cells.
+template <int N>
+__global__ void __launch_bounds__(256, 3) bdb_matrix_sym64_kernel(const __grid_constant__ BdbParams P)
+{
+    using C = BdbCfg<N>;
+    constexpr int ND = C::ND, NP = C::NP, S = C::S, Q3 = C::Q3;
+    static_assert(NP == 64, "written for a 64 x 64 element matrix");
+    constexpr int QP = C::NCHUNK * KQ;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *sL = reinterpret_cast<double *>(smem_raw);        // [2][KR][S]
+    double *sR = sL + 2 * KR * S;                              // [2 cells][KR][S]
+    double *sG = sR + 2 * KR * S;                              // [2][QP][7]
+    double *sX = sG + 2 * QP * 7;                              // [2][24]
+    long long *sRow = reinterpret_cast<long long *>(sX + 48);  // [2][NP]
+    int *sCol = reinterpret_cast<int *>(sRow + 2 * NP);        // [2][NP]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int slot = warp >> 2, w4 = warp & 3;
+    const int gid = lane >> 2, tig = lane & 3;
+    const long long ncells = (long long)P.ncols * P.nlay;
+    const long long npairs = (ncells + 1) / 2;
+
+    for (long long pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+        __syncthreads();
+        auto stage_L = [&](int chunk, int buf) {
+            const double *src = P.table + (size_t)chunk * KR * NP;
+            double *dst = sL + buf * KR * S;
+            for (int e = tid; e < KR * NP / 2; e += 256) {
+                const int row = e / (NP / 2), c2 = e - row * (NP / 2);
+                cp_async16(dst + row * S + 2 * c2, src + row * NP + 2 * c2);
+            }
+            cp_async_commit();
+        };
+        stage_L(0, 0);
+        int colv[2], layv[2];
+        bool live[2];
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            const long long cell = 2 * pair + c;
+            live[c] = cell < ncells;
+            const long long cc = live[c] ? cell : ncells - 1;
+            const int ci = (int)(cc / P.nlay);
+            layv[c] = (int)(cc - (long long)ci * P.nlay);
+            colv[c] = P.collist ? P.collist[ci] : P.col0 + ci;
+        }
+        if (tid < 48) {
+            const int c = tid / 24, t = tid - c * 24, v = t / 3, a = t - v * 3;
+            const int g = P.map1[(long long)colv[c] * 8 + v] + P.off1[v] * layv[c];
+            sX[tid] = P.coords[(long long)g * 3 + a];
+        }
+        if (tid < 2 * NP) {
+            const int c = tid / NP, i = tid - c * NP;
+            long long rs = -1;
+            int gc = -1;
+            if (i < ND && live[c]) {
+                const int g = P.map0[(long long)colv[c] * ND + i] + P.off0[i] * layv[c];
+                int gr = P.row_lg ? P.row_lg[g] : g;
+                gc = P.col_lg ? P.col_lg[g] : g;
+                if (gr >= 0) rs = P.rank_tab ? P.rowptr[gr] : (long long)gr;
+            }
+            sRow[tid] = rs;
+            sCol[tid] = gc;
+        }
+        __syncthreads();
+        for (int e = tid; e < 2 * QP; e += 256) {
+            const int c = e / QP, q = e - c * QP;
+            geometry_point<N>(P, sX + c * 24, sG + e * 7, q, q < Q3);
+        }
+        double acc[20];
+#pragma unroll
+        for (int e = 0; e < 20; e++) acc[e] = 0.0;
+
+        for (int chunk = 0; chunk < C::NCHUNK; chunk++) {
+            const int buf = chunk & 1;
+            cp_async_wait_all();
+            __syncthreads();
+            if (chunk + 1 < C::NCHUNK) stage_L(chunk + 1, buf ^ 1);
+            const double *L = sL + buf * KR * S;
+            for (int e = tid; e < 2 * KQ * NP; e += 256) {
+                const int c = e / (KQ * NP), r = e - c * (KQ * NP);
+                const int ql = r / NP, j = r - ql * NP;
+                const double *g = sG + (c * QP + chunk * KQ + ql) * 7;
+                double *R = sR + c * KR * S;
+                const double l0 = L[(ql * 4 + 0) * S + j], l1 = L[(ql * 4 + 1) * S + j],
+                             l2 = L[(ql * 4 + 2) * S + j], l3 = L[(ql * 4 + 3) * S + j];
+                R[(ql * 4 + 0) * S + j] = g[0] * l0 + g[1] * l1 + g[2] * l2;
+                R[(ql * 4 + 1) * S + j] = g[1] * l0 + g[3] * l1 + g[4] * l2;
+                R[(ql * 4 + 2) * S + j] = g[2] * l0 + g[4] * l1 + g[5] * l2;
+                R[(ql * 4 + 3) * S + j] = g[6] * l3;
+            }
+            __syncthreads();
+            const double *R = sR + slot * KR * S;
+            if (w4 < 2) {
+#pragma unroll
+                for (int ks = 0; ks < KR / 4; ks++) {
+                    double af[2], bf[4];
+                    const double *Lk = L + (ks * 4 + tig) * S + w4 * 16 + gid;
+                    const double *Rk = R + (ks * 4 + tig) * S + 32 + gid;
+#pragma unroll
+                    for (int m = 0; m < 2; m++) af[m] = Lk[m * 8];
+#pragma unroll
+                    for (int n = 0; n < 4; n++) bf[n] = Rk[n * 8];
+#pragma unroll
+                    for (int m = 0; m < 2; m++)
+#pragma unroll
+                        for (int n = 0; n < 4; n++)
+                            dmma_m8n8k4(acc[(m * 4 + n) * 2], acc[(m * 4 + n) * 2 + 1], af[m], bf[n]);
+                }
+            } else {
+                const int d = w4 - 2;
+#pragma unroll
+                for (int ks = 0; ks < KR / 4; ks++) {
+                    double af[4], bf[4];
+                    const double *Lk = L + (ks * 4 + tig) * S + d * 32 + gid;
+                    const double *Rk = R + (ks * 4 + tig) * S + d * 32 + gid;
+#pragma unroll
+                    for (int m = 0; m < 4; m++) {
+                        af[m] = Lk[m * 8];
+                        bf[m] = Rk[m * 8];
+                    }
+#pragma unroll
+                    for (int m = 0; m < 4; m++)
+#pragma unroll
+                        for (int n = m; n < 4; n++)
+                            dmma_m8n8k4(acc[dtile(m, n) * 2], acc[dtile(m, n) * 2 + 1], af[m], bf[n]);
+                }
+            }
+        }
+
+        if (!live[slot]) continue;
+        const unsigned short *rk = nullptr;
+        if (P.rank_tab) {
+            const int layer = layv[slot];
+            const int v = P.nlay < 3 ? layer : (layer == 0 ? 0 : (layer == P.nlay - 1 ? 2 : 1));
+            rk = P.rank_tab + ((long long)colv[slot] * P.nvar + v) * ND * ND;
+        }
+        const long long *row = sRow + slot * NP;
+        const int *colg = sCol + slot * NP;
+        auto add = [&](int i, int j, double val) {
+            const long long rs = row[i];
+            const int gc = colg[j];
+            if (rs < 0 || gc < 0) return;
+            long long pos;
+            if (rk) {
+                pos = rs + rk[j * ND + i];
+            } else {
+                long long lo = P.rowptr[rs], hi = P.rowptr[rs + 1];
+                while (hi - lo > 1) {
+                    const long long mid = (lo + hi) >> 1;
+                    if (P.colidx[mid] <= gc) lo = mid; else hi = mid;
+                }
+                pos = lo;
+            }
+            atomicAdd(P.vals + pos, val);
+        };
+        if (w4 < 2) {
+#pragma unroll
+            for (int m = 0; m < 2; m++) {
+                const int i = w4 * 16 + m * 8 + gid;
+#pragma unroll
+                for (int n = 0; n < 4; n++)
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const int j = 32 + n * 8 + tig * 2 + h;
+                        if (i < ND && j < ND) {
+                            add(i, j, acc[(m * 4 + n) * 2 + h]);
+                            add(j, i, acc[(m * 4 + n) * 2 + h]);
+                        }
+                    }
+            }
+        } else {
+            const int d = w4 - 2;
+#pragma unroll
+            for (int m = 0; m < 4; m++) {
+                const int i = d * 32 + m * 8 + gid;
+#pragma unroll
+                for (int n = m; n < 4; n++)
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const int j = d * 32 + n * 8 + tig * 2 + h;
+                        if (i < ND && j < ND) {
+                            const double val = acc[dtile(m, n) * 2 + h];
+                            add(i, j, val);
+                            if (n != m) add(j, i, val);
+                        }
+                    }
+            }
+        }
+    }
+}
+
 // table T[(q*4 + r)][NP]: r < 3 reference gradient component r of basis i at point q, r = 3 its value
 template <int N>
 int build_table(fdb_kernel_s *k)
@@ -516,19 +710,30 @@ int launch_bdb(fdb_kernel_s *k, fdb_int start, fdb_int end, int nlay, const fdb_
     }
     if (P.ncols <= 0 || nlay <= 0) return 0;
     static const bool sym_on = !(getenv("FDB_BDB_SYM") && atoi(getenv("FDB_BDB_SYM")) == 0);
-    auto kern = (C::NP == 128 && sym_on) ? bdb_matrix_sym_kernel<(C::NP == 128 ? N : 5)> : bdb_matrix_kernel<N>;
+    void (*kern)(const BdbParams) = bdb_matrix_kernel<N>;
+    int smem = C::SMEM_BYTES;
+    int cells_per_cta = 1;
+    if (sym_on && C::NP == 128) {
+        kern = bdb_matrix_sym_kernel<(C::NP == 128 ? N : 5)>;
+    } else if (sym_on && C::NP == 64) {
+        kern = bdb_matrix_sym64_kernel<(C::NP == 64 ? N : 4)>;
+        using C4 = BdbCfg<4>;
+        smem = (4 * KR * C4::S + 2 * C4::NCHUNK * KQ * 7 + 48) * 8 + 2 * C4::NP * 8 + 2 * C4::NP * 4 + 16;
+        cells_per_cta = 2;
+    }
     static bool configured = false;
     static int occ = 1;
     if (!configured) {
-        FDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        FDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, C::SMEM_BYTES));
+        FDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        FDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
         if (occ < 1) occ = 1;
         configured = true;
     }
     const long long ncells = (long long)P.ncols * nlay;
     long long grid = (long long)c.sm_count * occ;
-    if (grid > ncells) grid = ncells;
-    kern<<<(int)grid, 256, C::SMEM_BYTES, c.stream>>>(P);
+    const long long nwork = (ncells + cells_per_cta - 1) / cells_per_cta;
+    if (grid > nwork) grid = nwork;
+    kern<<<(int)grid, 256, smem, c.stream>>>(P);
     FDB_LAUNCH_CHECK();
     return 0;
 }

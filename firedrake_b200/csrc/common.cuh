@@ -51,6 +51,8 @@ int require_init();
 
 }  // namespace fdb
 
+extern int fdb_opt_matrix_kernel;   // fdb_set_option("matrix_kernel", ...)
+
 struct fdb_jit_s;   // NVRTC-compiled generic wrapper (wrapper_jit.cu)
 
 // kernel object behind fdb_kernel_t
@@ -104,6 +106,10 @@ int fdb_launch_dg_advection(fdb_kernel_s *k, fdb_int start, fdb_int end, const f
                             double *out, const double *coords, const double *q, const double *u,
                             const double *consts_host, const unsigned *facet, const fdb_int *dgmap,
                             const fdb_int *cgmap, const fdb_int *nbr);
+
+int fdb_launch_q1_action(fdb_kernel_s *k, fdb_int start, fdb_int end, int nlay, const fdb_int *subset,
+                         double *y, const double *coords, const double *x, const fdb_int *map0,
+                         const fdb_int *map1);
 
 // launchers implemented in the kernel translation units
 int fdb_launch_helmholtz_action(fdb_kernel_s *k, fdb_int start, fdb_int end, int nlay,

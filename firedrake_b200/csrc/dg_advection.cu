@@ -11,6 +11,8 @@
 // These are small, HBM/latency-bound kernels (~50-100 flop per dof): one
 // thread per cell / facet, coalesced 128-bit loads of the map rows, grid sized
 // to the SM count; the scatter is a handful of RED.ADD.F64 per thread.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -354,6 +356,167 @@ __global__ void __launch_bounds__(128) dg_fused_kernel(const __grid_constant__ D
     }
 }
 
+// ---- round 2: the fused kernel specialised on the number of quadrature points -----------------
+// Same integrals as dg_fused_kernel, reorganised so that the straight-line code per cell drops from
+// ~2300 to ~900 fp64 instructions (SASS count in profiles/r02_dg_advection.txt):
+//   * NQ is a template parameter: every loop unrolls, the DQ1 tabulation phi_i(x_k) is 2*NQ registers;
+//   * bilinear geometry and velocity are expanded once per cell (X = C0 + C1 x + C2 y + C3 xy);
+//   * |det J| w K^{-T} grad = sign(det) w adj(J)^T grad: the cell term needs NO division;
+//   * the scaled facet normal cof(J) n_ref has length ds and is CONSTANT along a straight edge:
+//     u.n ds = u.(cof(J) n_ref), so the facet terms need no sqrt / rsqrt and no per-point geometry;
+//   * the neighbour's trace is reduced to its two edge coefficients before the point loop.
+// Results agree with the generic kernel to rounding (tests/test_dg_advection_gpu.py, 1e-12).
+template <int NQ>
+__global__ void __launch_bounds__(128) dg_fused_nq_kernel(const __grid_constant__ DgParams P)
+{
+    double Phi[2][NQ];                       // phi_i(x_k)
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int k = 0; k < NQ; k++) Phi[i][k] = P.Bend[i] * (1.0 - P.xq[k]) + P.Bend[2 + i] * P.xq[k];
+    const double dPhi[2] = {P.Bend[2] - P.Bend[0], P.Bend[3] - P.Bend[1]};
+    for (int i = P.start + blockIdx.x * blockDim.x + threadIdx.x; i < P.end; i += gridDim.x * blockDim.x) {
+        const int n = P.subset ? P.subset[i] : i;
+        const int4 dg = *reinterpret_cast<const int4 *>(P.dgmap + 4 * (long long)n);
+        const int4 cg = *reinterpret_cast<const int4 *>(P.cgmap + 4 * (long long)n);
+        const int4 nb4 = *reinterpret_cast<const int4 *>(P.nbr + 4 * (long long)n);
+        const uint4 nf4 = *reinterpret_cast<const uint4 *>(P.nbr_facet + 4 * (long long)n);
+        const int dgi[4] = {dg.x, dg.y, dg.z, dg.w}, cgi[4] = {cg.x, cg.y, cg.z, cg.w};
+        const int nb[4] = {nb4.x, nb4.y, nb4.z, nb4.w};
+        const unsigned nf[4] = {nf4.x, nf4.y, nf4.z, nf4.w};
+        // neighbour rows first: the longest dependent chain (map row -> q values)
+        double qn[4][4];
+#pragma unroll
+        for (int f = 0; f < 4; f++) {
+            const int4 dn = *reinterpret_cast<const int4 *>(P.dgmap + 4 * (long long)(nb[f] >= 0 ? nb[f] : n));
+            qn[f][0] = P.q[dn.x]; qn[f][1] = P.q[dn.y]; qn[f][2] = P.q[dn.z]; qn[f][3] = P.q[dn.w];
+        }
+        Q1Cell K;
+        load_cell(P, cgi, K);
+        double ql[2][2], A[2][2] = {{0, 0}, {0, 0}};
+#pragma unroll
+        for (int k = 0; k < 4; k++) ql[k >> 1][k & 1] = P.q[dgi[k]];
+        // bilinear expansions  f(x, y) = F0 + F1 x + F2 y + F3 x y  (component a)
+        double C1[2], C2[2], C3[2], U0[2], U1[2], U2[2], U3[2];
+#pragma unroll
+        for (int a = 0; a < 2; a++) {
+            C1[a] = K.c[4 + a] - K.c[a];
+            C2[a] = K.c[2 + a] - K.c[a];
+            C3[a] = K.c[6 + a] - K.c[4 + a] - K.c[2 + a] + K.c[a];
+            U0[a] = K.u[a];
+            U1[a] = K.u[4 + a] - K.u[a];
+            U2[a] = K.u[2 + a] - K.u[a];
+            U3[a] = K.u[6 + a] - K.u[4 + a] - K.u[2 + a] + K.u[a];
+        }
+        // orientation of the cell (constant sign of det J on a valid cell): at the centre
+        const double detc = (C1[0] + 0.5 * C3[0]) * (C2[1] + 0.5 * C3[1]) - (C2[0] + 0.5 * C3[0]) * (C1[1] + 0.5 * C3[1]);
+        const double sg = detc < 0.0 ? -1.0 : 1.0;
+        // ---- cell integral
+#pragma unroll
+        for (int qx = 0; qx < NQ; qx++) {
+            const double x = P.xq[qx];
+            const double J01 = fma(C3[0], x, C2[0]), J11 = fma(C3[1], x, C2[1]);      // dX/dy
+            const double uy0 = fma(U3[0], x, U2[0]), uy1 = fma(U3[1], x, U2[1]);      // du/dy (reference)
+            const double ub0 = fma(U1[0], x, U0[0]), ub1 = fma(U1[1], x, U0[1]);      // u = ub + uy * y
+            const double qa = ql[0][0] * Phi[0][qx] + ql[1][0] * Phi[1][qx];           // q = qa phi_0(y) + qb phi_1(y)
+            const double qb = ql[0][1] * Phi[0][qx] + ql[1][1] * Phi[1][qx];
+            double T0[2] = {0, 0}, T1[2] = {0, 0};       // sums over qy of phi_ay(y) * (.) and dphi_ay * (.)
+#pragma unroll
+            for (int qy = 0; qy < NQ; qy++) {
+                const double y = P.xq[qy];
+                const double J00 = fma(C3[0], y, C1[0]), J10 = fma(C3[1], y, C1[1]);  // dX/dx
+                const double ux0 = fma(U3[0], y, U1[0]), ux1 = fma(U3[1], y, U1[1]);  // du/dx (reference)
+                const double uv0 = fma(uy0, y, ub0), uv1 = fma(uy1, y, ub1);
+                const double qv = qa * Phi[0][qy] + qb * Phi[1][qy];
+                const double sc = P.dt * sg * P.wq[qx] * P.wq[qy] * qv;
+                const double a0 = J11 * uv0 - J01 * uv1;                 // coefficient of d/dx(phi)
+                const double a1 = J00 * uv1 - J10 * uv0;                 // coefficient of d/dy(phi)
+                const double dd = J11 * ux0 - J10 * uy0 - J01 * ux1 + J00 * uy1;   // det * div u
+                // A[ax][ay] += sc * (a0 dphi_ax phi_ay + a1 phi_ax dphi_ay + dd phi_ax phi_ay)
+#pragma unroll
+                for (int ay = 0; ay < 2; ay++) {
+                    T0[ay] = fma(sc * a0, Phi[ay][qy], T0[ay]);
+                    T1[ay] = fma(sc, fma(a1, dPhi[ay], dd * Phi[ay][qy]), T1[ay]);
+                }
+            }
+#pragma unroll
+            for (int ax = 0; ax < 2; ax++)
+#pragma unroll
+                for (int ay = 0; ay < 2; ay++) A[ax][ay] += dPhi[ax] * T0[ay] + Phi[ax][qx] * T1[ay];
+        }
+        // ---- the four facets (f = 0: x = 0, 1: x = 1, 2: y = 0, 3: y = 1)
+#pragma unroll
+        for (int f = 0; f < 4; f++) {
+            const int e = f & 1;
+            const double xe = (double)e, sgn = e ? 1.0 : -1.0;
+            // scaled outward normal (constant along the edge), |nn| = ds
+            double nn0, nn1;
+            if (f < 2) {        // n_ref = (sgn, 0): cof(J) n_ref = sgn (J11, -J01) at x = xe
+                nn0 = sg * sgn * fma(C3[1], xe, C2[1]);
+                nn1 = -sg * sgn * fma(C3[0], xe, C2[0]);
+            } else {            // n_ref = (0, sgn): cof(J) n_ref = sgn (-J10, J00) at y = xe
+                nn0 = -sg * sgn * fma(C3[1], xe, C1[1]);
+                nn1 = sg * sgn * fma(C3[0], xe, C1[0]);
+            }
+            // my trace: q(s) = ta phi_0(s) + tb phi_1(s)
+            double ta, tb;
+            if (f < 2) {
+                ta = ql[0][0] * P.Bend[e * 2] + ql[1][0] * P.Bend[e * 2 + 1];
+                tb = ql[0][1] * P.Bend[e * 2] + ql[1][1] * P.Bend[e * 2 + 1];
+            } else {
+                ta = ql[0][0] * P.Bend[e * 2] + ql[0][1] * P.Bend[e * 2 + 1];
+                tb = ql[1][0] * P.Bend[e * 2] + ql[1][1] * P.Bend[e * 2 + 1];
+            }
+            // the neighbour's trace on ITS local facet nf
+            const bool interior = nb[f] >= 0;
+            const int en = (int)(nf[f] & 1u);
+            const double b0 = P.Bend[en * 2], b1 = P.Bend[en * 2 + 1];
+            const bool nvert = nf[f] < 2u;
+            const double na = nvert ? qn[f][0] * b0 + qn[f][2] * b1 : qn[f][0] * b0 + qn[f][1] * b1;
+            const double nbv = nvert ? qn[f][1] * b0 + qn[f][3] * b1 : qn[f][2] * b0 + qn[f][3] * b1;
+            // velocity along the edge: u(s) = ue + us * s
+            double ue0, ue1, us0, us1;
+            if (f < 2) {
+                ue0 = fma(U1[0], xe, U0[0]); ue1 = fma(U1[1], xe, U0[1]);
+                us0 = fma(U3[0], xe, U2[0]); us1 = fma(U3[1], xe, U2[1]);
+            } else {
+                ue0 = fma(U2[0], xe, U0[0]); ue1 = fma(U2[1], xe, U0[1]);
+                us0 = fma(U3[0], xe, U1[0]); us1 = fma(U3[1], xe, U1[1]);
+            }
+            const double un_e = ue0 * nn0 + ue1 * nn1, un_s = us0 * nn0 + us1 * nn1;   // u.n ds = un_e + un_s s
+            double E[2] = {0, 0};                   // sum_k w_k phi_j(s_k) flux_k
+#pragma unroll
+            for (int k = 0; k < NQ; k++) {
+                const double uds = fma(un_s, P.xq[k], un_e);
+                const double qv = ta * Phi[0][k] + tb * Phi[1][k];
+                double flux;
+                if (!interior) {
+                    flux = (uds < 0.0 ? uds * P.q_in : 0.0) + (uds > 0.0 ? uds * qv : 0.0);
+                } else {
+                    const double qnv = na * Phi[0][k] + nbv * Phi[1][k];
+                    flux = fmax(uds, 0.0) * qv - fmax(-uds, 0.0) * qnv;
+                }
+                const double wf = P.dt * P.wq[k] * flux;
+                E[0] = fma(wf, Phi[0][k], E[0]);
+                E[1] = fma(wf, Phi[1][k], E[1]);
+            }
+            if (f < 2) {
+#pragma unroll
+                for (int ax = 0; ax < 2; ax++)
+#pragma unroll
+                    for (int ay = 0; ay < 2; ay++) A[ax][ay] -= P.Bend[e * 2 + ax] * E[ay];
+            } else {
+#pragma unroll
+                for (int ax = 0; ax < 2; ax++)
+#pragma unroll
+                    for (int ay = 0; ay < 2; ay++) A[ax][ay] -= P.Bend[e * 2 + ay] * E[ax];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) P.out[dgi[k]] += A[k >> 1][k & 1];
+    }
+}
+
 }  // namespace
 
 int fdb_launch_dg_advection(fdb_kernel_s *k, fdb_int start, fdb_int end, const fdb_int *subset,
@@ -391,7 +554,14 @@ int fdb_launch_dg_advection(fdb_kernel_s *k, fdb_int start, fdb_int end, const f
     case FDB_INTEGRAL_CELL: dg_cell_kernel<<<(int)blocks, 128, 0, c.stream>>>(P); break;
     case FDB_INTEGRAL_EXTERIOR_FACET: dg_exterior_kernel<<<(int)blocks, 128, 0, c.stream>>>(P); break;
     case FDB_INTEGRAL_INTERIOR_FACET: dg_interior_kernel<<<(int)blocks, 128, 0, c.stream>>>(P); break;
-    case FDB_INTEGRAL_FUSED: dg_fused_kernel<<<(int)blocks, 128, 0, c.stream>>>(P); break;
+    case FDB_INTEGRAL_FUSED: {
+        static const bool generic = getenv("FDB_DG_GENERIC") && atoi(getenv("FDB_DG_GENERIC"));
+        if (!generic && P.nq == 2) dg_fused_nq_kernel<2><<<(int)blocks, 128, 0, c.stream>>>(P);
+        else if (!generic && P.nq == 3) dg_fused_nq_kernel<3><<<(int)blocks, 128, 0, c.stream>>>(P);
+        else if (!generic && P.nq == 4) dg_fused_nq_kernel<4><<<(int)blocks, 128, 0, c.stream>>>(P);
+        else dg_fused_kernel<<<(int)blocks, 128, 0, c.stream>>>(P);
+        break;
+    }
     default: fdb::set_error("dg advection: bad integral type"); return 1;
     }
     FDB_LAUNCH_CHECK();

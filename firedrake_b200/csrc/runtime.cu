@@ -51,6 +51,8 @@ static uint64_t g_epoch = 1;
 
 using namespace fdb;
 
+int fdb_opt_matrix_kernel = getenv("FDB_MATRIX_DMMA") ? atoi(getenv("FDB_MATRIX_DMMA")) : -1;
+
 static cudaStream_t g_side = nullptr;
 static cudaEvent_t g_side_ev = nullptr, g_main_ev = nullptr;
 static bool g_side_pending = false;
@@ -153,6 +155,34 @@ int fdb_device_info(char *name, int name_len, int *sm_count, size_t *total_mem)
 }
 
 uint64_t fdb_launch_count(void) { return ctx().launches; }
+
+static int *option_slot(const char *name)
+{
+    if (name && !strcmp(name, "matrix_kernel")) return &fdb_opt_matrix_kernel;
+    return nullptr;
+}
+
+int fdb_set_option(const char *name, int value)
+{
+    int *s = option_slot(name);
+    if (!s) {
+        set_error("fdb_set_option: unknown option '%s'", name ? name : "(null)");
+        return 1;
+    }
+    *s = value;
+    return 0;
+}
+
+int fdb_get_option(const char *name, int *value)
+{
+    int *s = option_slot(name);
+    if (!s) {
+        set_error("fdb_get_option: unknown option '%s'", name ? name : "(null)");
+        return 1;
+    }
+    *value = *s;
+    return 0;
+}
 
 void *fdb_malloc(size_t nbytes)
 {

@@ -850,6 +850,44 @@ class GlobalKernel:
             pass
 
 
+class _PhaseTimer:
+    """FDB_PHASE_TIMING=1: synchronise after every phase of a partitioned parloop and accumulate
+    host wall time per phase (diagnostics only: the synchronisation removes all overlap)."""
+    _inst = None
+
+    def __init__(self, on):
+        self.on, self.t, self.acc = on, None, {}
+        if on:
+            import atexit
+            atexit.register(self.report)
+
+    @classmethod
+    def get(cls):
+        if cls._inst is None:
+            import os
+            cls._inst = cls(os.environ.get("FDB_PHASE_TIMING") == "1")
+        if cls._inst.on:
+            import time
+            _lib.check(_lib.lib().fdb_synchronize())
+            cls._inst.t = time.perf_counter()
+        return cls._inst
+
+    def mark(self, name):
+        if self.on:
+            import time
+            _lib.check(_lib.lib().fdb_synchronize())
+            now = time.perf_counter()
+            a = self.acc.setdefault(name, [0, 0.0])
+            a[0] += 1
+            a[1] += now - self.t
+            self.t = now
+
+    def report(self):
+        import os
+        print("phase timing rank", os.environ.get("RANK", "0"),
+              {k: "%d x %.3f ms" % (n, 1e3 * t / n) for k, (n, t) in self.acc.items()}, flush=True)
+
+
 class Parloop:
     """pyop2/parloop.py:167-260.  ``args`` are ``LegacyArg``s in TSFC argument
     order (output, coordinates, coefficient).  ``__call__`` follows the
@@ -962,12 +1000,17 @@ class Parloop:
             # them redundantly completes every owned row locally, so INC Dats need no local->global
             # reduce (SURVEY.md section 8e option (ii)); their ghost rows are left holding partial
             # sums and are marked stale, as after the reference's reduce
+            ph = _PhaseTimer.get()
             for d in reads:
                 d.dataset.halo.global_to_local_begin(d)
+            ph.mark("g2l_begin")
             self._compute(self.iterset.core_part)
+            ph.mark("core")
             for d in reads:
                 d.dataset.halo.global_to_local_end(d)
+            ph.mark("g2l_end")
             self._compute((self.iterset.core_size, self.iterset.total_size))   # owned + exec halo
+            ph.mark("owned+exec")
             for d in incs:
                 d._device_written(halo_valid=False)
             return

@@ -41,6 +41,14 @@ int fdb_device_info(char *name, int name_len, int *sm_count, size_t *total_mem);
  * "gpu_launches" claim is read from here, not estimated) */
 uint64_t fdb_launch_count(void);
 
+/* Engine options (kernel selection knobs; each also has an environment default):
+ *   "matrix_kernel"  -1 auto (dense B^T D B on the fp64 tensor pipe for degree 4, the sum-factorised
+ *                       column kernel otherwise), 0 always sum-factorised, 1 DMMA wherever instantiated
+ *                       (degrees 2..4)                                   [env FDB_MATRIX_DMMA]
+ * Returns nonzero for an unknown name. */
+int fdb_set_option(const char *name, int value);
+int fdb_get_option(const char *name, int *value);
+
 /* --------------------------------------------------------- device-resident data
  * Device storage for Dat/Map/Global payloads when the caller keeps data on the
  * GPU across calls.  Layout is exactly the host

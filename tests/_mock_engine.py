@@ -95,6 +95,13 @@ class MockEngine:
     def fdb_timer_destroy(self, t):
         return 0
 
+    def fdb_set_option(self, name, value):
+        return 0
+
+    def fdb_get_option(self, name, out):
+        _obj(out).value = -1
+        return 0
+
     def fdb_launch_count(self):
         return self.launches
 

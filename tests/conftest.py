@@ -24,3 +24,13 @@ def oracle():
     from oracle import oracle as orc
     orc.build()
     return orc
+
+
+@pytest.fixture(params=[0, 1], ids=["sumfact", "dmma"])
+def matrix_kernel(request, engine):
+    """Both element-matrix kernels: the sum-factorised column kernel (action_hex.cu, MATRIX mode)
+    and the dense B^T D B kernel on the fp64 tensor pipe (bdb_matrix.cu, degrees 2..4)."""
+    from firedrake_b200 import _lib
+    _lib.check(engine.fdb_set_option(b"matrix_kernel", request.param))
+    yield request.param
+    _lib.check(engine.fdb_set_option(b"matrix_kernel", -1))

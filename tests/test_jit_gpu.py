@@ -139,7 +139,7 @@ def test_generic_extruded_action_equals_fast_path_and_oracle(engine, oracle):
 
 
 @pytest.mark.parametrize("p,cdim", [(2, 3), (1, 2), (3, 3), (4, 3)])
-def test_vector_space_matrix_fast_path(engine, oracle, p, cdim):
+def test_vector_space_matrix_fast_path(engine, oracle, matrix_kernel, p, cdim):
     """assemble(a) on a VectorFunctionSpace (config 4's explicit matrix): blocked CSR ==
     kron(scalar oracle matrix, I), with node Dirichlet conditions, and SpMV == matrix-free.
     p >= 3 runs the dense B^T D B kernel on the fp64 tensor pipe (bdb_matrix.cu), (4, 3) being

@@ -42,9 +42,10 @@ def test_sparsity_matches_reference_semantics(engine, oracle, p):
     assert np.array_equal(rowptr, ro) and np.array_equal(colidx, co)
 
 
-@pytest.mark.parametrize("p,alpha,beta", [(1, 1.0, 0.0), (2, 1.0, 1.0), (3, 1.0, 0.0), (3, 0.0, 1.0)])
-def test_matrix_matches_oracle(engine, oracle, p, alpha, beta):
-    mesh = ExtrudedHexMesh(3, 3, 4, warp=0.05, permute_seed=2)
+@pytest.mark.parametrize("p,alpha,beta", [(1, 1.0, 0.0), (2, 1.0, 1.0), (3, 1.0, 0.0), (3, 0.0, 1.0), (4, 1.0, 1.0)])
+def test_matrix_matches_oracle(engine, oracle, matrix_kernel, p, alpha, beta):
+    mesh = ExtrudedHexMesh(3, 3, 4, warp=0.05, permute_seed=2) if p < 4 else \
+        ExtrudedHexMesh(2, 2, 3, warp=0.05, permute_seed=2)
     V, cells, nodes, m0, m1, X = setup(mesh, p)
     mat = op2.Mat(op2.Sparsity((nodes, nodes), [(m0, m0, None)]))
     k = op2.Kernel("helmholtz", degree=p, alpha=alpha, beta=beta, rank=2)
@@ -56,7 +57,7 @@ def test_matrix_matches_oracle(engine, oracle, p, alpha, beta):
     assert np.abs(vals - vo).max() < 1e-12 * np.abs(vo).max()
 
 
-def test_bc_lgmaps_diagonal_and_matvec(engine, oracle):
+def test_bc_lgmaps_diagonal_and_matvec(engine, oracle, matrix_kernel):
     """reference tests/firedrake/regression/test_matrix_free.py:98-127 on the
     device: assembled (BC rows/cols dropped, unit diagonal) A.mult(x) equals the
     matrix-free action with the BC protocol of matrix_free/operators.py:211-242."""
