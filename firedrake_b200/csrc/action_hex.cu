@@ -926,11 +926,12 @@ int fdb_launch_helmholtz_matrix(fdb_kernel_s *k, fdb_int start, fdb_int end, int
                                 const fdb_int *map0, const fdb_int *map1, double *diag_out)
 {
     // explicit matrices: dense B^T D B on the fp64 tensor pipe (bdb_matrix.cu) where it is the
-    // faster kernel -- degree 4 (symmetric tiling, 11.9 ms against 18.2 ms for config 4 at 32^3);
+    // faster kernel -- degrees 3 and 4 (symmetric tilings: CG3 64^3 15.4 against 23.3 ms, config 4 at
+    // 32^3 11.9 against 18.2 ms; at degree 2 the sum-factorised kernel wins, 1.26 against 1.73 ms);
     // option "matrix_kernel": 0 keeps the sum-factorised column-by-column kernel everywhere, 1 takes
     // the DMMA kernel for every instantiated degree (2..4)
     const int dmma = fdb_opt_matrix_kernel;
-    if (mat && dmma != 0 && k->n1d <= 5 && k->n1d >= (dmma == 1 ? 3 : 5))
+    if (mat && dmma != 0 && k->n1d <= 5 && k->n1d >= (dmma == 1 ? 3 : 4))
         return fdb_launch_helmholtz_matrix_dmma(k, start, end, nlay, subset, mat, coords, map0, map1);
     switch (k->n1d) {
     case 2: return launch_matrix_n<2>(k, start, end, nlay, subset, mat, coords, map0, map1, diag_out);

@@ -42,8 +42,8 @@ int fdb_device_info(char *name, int name_len, int *sm_count, size_t *total_mem);
 uint64_t fdb_launch_count(void);
 
 /* Engine options (kernel selection knobs; each also has an environment default):
- *   "matrix_kernel"  -1 auto (dense B^T D B on the fp64 tensor pipe for degree 4, the sum-factorised
- *                       column kernel otherwise), 0 always sum-factorised, 1 DMMA wherever instantiated
+ *   "matrix_kernel"  -1 auto (dense B^T D B on the fp64 tensor pipe for degrees 3 and 4, the
+ *                       sum-factorised column kernel otherwise), 0 always sum-factorised, 1 DMMA wherever instantiated
  *                       (degrees 2..4)                                   [env FDB_MATRIX_DMMA]
  * Returns nonzero for an unknown name. */
 int fdb_set_option(const char *name, int value);
