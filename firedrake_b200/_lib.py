@@ -141,6 +141,11 @@ SIGNATURES = {
     "fdb_vec_aypx": (C.c_int, [C.c_size_t, C.c_double, C.c_void_p, C.c_void_p]),
     "fdb_vec_scale": (C.c_int, [C.c_size_t, C.c_double, C.c_void_p]),
     "fdb_vec_fill": (C.c_int, [C.c_size_t, C.c_double, C.c_void_p]),
+    "fdb_asm_create": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "fdb_asm_destroy": (C.c_int, [C.c_void_p]),
+    "fdb_asm_update": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
+    "fdb_asm_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fdb_asm_get_blocks": (C.c_int, [C.c_void_p, C.c_void_p]),
     "fdb_vec_dot": (C.c_int, [C.c_size_t, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]),
     "fdb_vec_pointwise_mult": (C.c_int, [C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fdb_interpolate_q1": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -332,6 +332,20 @@ int fdb_mat_mult(fdb_mat_t m, const double *x, double *y);
 /* copy the CSR arrays to the host (any pointer may be NULL); rowptr is int64 */
 int fdb_mat_get_csr(fdb_mat_t m, long long *rowptr, fdb_int *colidx, double *vals);
 
+
+/* ------------------------------------------- batched patch solves (section 8f row f4)
+ * TinyASM's BlockJacobi on the device (tinyasm/tinyasm.cpp:27-120): patches are dof lists
+ * (CSR-like: patch_ptr[npatch+1] offsets into patch_dofs; for a blocked matrix a dof is
+ * node*bs + component).  fdb_asm_update = updateValuesPerBlock (extract P[d_p, d_p], invert in
+ * place: Gauss-Jordan with partial pivoting, one CTA per patch); fdb_asm_apply = solve
+ * (x[d_p] += inv_p b[d_p] for every patch, additive; device pointers). */
+typedef struct fdb_asm_s *fdb_asm_t;
+int fdb_asm_create(int npatch, const long long *patch_ptr_host, const fdb_int *patch_dofs_host, fdb_asm_t *out);
+int fdb_asm_destroy(fdb_asm_t a);
+int fdb_asm_update(fdb_asm_t a, fdb_mat_t mat, int *nsingular);
+int fdb_asm_apply(fdb_asm_t a, const double *b, double *x);
+int fdb_asm_get_blocks(fdb_asm_t a, double *out_host);
+
 /* --------------------------------------------------------- Dat subset ops (K5)
  * DirichletBC.zero / DirichletBC.set on a node subset (firedrake/bcs.py:192-221,
  * pyop2/types/dat.py:297-311).  Device pointers. */
