@@ -501,6 +501,17 @@ def main():
                 return float(y._data[0])
             path = ("op2.Parloop(location='host') -> fdb_kernel_call(FDB_LOC_HOST): pinned host Dats; the "
                     "engine overlaps H2D of x | kernel | D2H of y over 32 column chunks (3 streams)")
+        elif args.halo == "exec":
+            hloop = op2.Parloop(gk, cells, [y(op2.INC, m0), X(op2.READ, m1), x(op2.READ, m0)], location="host")
+            def hstep():
+                x.data_with_halos[0] += 0.0      # host write: bumps dat_version -> H2D of the local x
+                x.halo_valid = False             # ... whose ghost rows are stale again
+                y.zero()
+                hloop()                          # Parloop._call_host_partitioned
+                return float(y._data[0])
+            path = ("per rank, op2.Parloop(location='host') on the exec-halo partition: core cells through the chunked "
+                    "H2D x | kernel | D2H y pipeline of fdb_kernel_call(FDB_LOC_HOST), remaining owned x rows uploaded, "
+                    "ghost rows over NCCL, boundary cells on the mirrors, the row ranges they touch downloaded again")
         else:
             def hstep():
                 x.data_with_halos[0] += 0.0      # host write -> H2D of the local x

@@ -112,6 +112,9 @@ SIGNATURES = {
     "fdb_host_unregister": (C.c_int, [C.c_void_p]),
     "fdb_mirror_acquire": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint64, C.c_int, C.POINTER(C.c_void_p)]),
     "fdb_mirror_writeback": (C.c_int, [C.c_void_p]),
+    "fdb_mirror_upload_range": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t]),
+    "fdb_mirror_download_range": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int]),
+    "fdb_mirror_set_version": (C.c_int, [C.c_void_p, C.c_uint64]),
     "fdb_mirror_drop": (C.c_int, [C.c_void_p]),
     "fdb_mirror_drop_all": (C.c_int, []),
     "fdb_kernel_create": (C.c_int, [C.POINTER(KernelDesc), C.POINTER(C.c_void_p)]),

@@ -398,6 +398,38 @@ int fdb_mirror_set_version(const void *host, uint64_t version)
     return 0;
 }
 
+// Partial transfers between a host buffer and its mirror (the partitioned host path of
+// op2.Parloop: rows the chunked pipeline did not move).  Asynchronous on the engine stream;
+// `sync` waits for the download before returning.
+int fdb_mirror_upload_range(const void *host, size_t offset, size_t nbytes)
+{
+    if (require_init()) return 1;
+    auto it = g_mirrors.find(host);
+    if (it == g_mirrors.end() || offset + nbytes > it->second.nbytes) {
+        set_error("fdb_mirror_upload_range: %p has no mirror of at least %zu bytes", host, offset + nbytes);
+        return 1;
+    }
+    if (nbytes)
+        FDB_CUDA(cudaMemcpyAsync((char *)it->second.dev + offset, (const char *)host + offset, nbytes,
+                                 cudaMemcpyHostToDevice, ctx().stream));
+    return 0;
+}
+
+int fdb_mirror_download_range(void *host, size_t offset, size_t nbytes, int sync)
+{
+    if (require_init()) return 1;
+    auto it = g_mirrors.find(host);
+    if (it == g_mirrors.end() || offset + nbytes > it->second.nbytes) {
+        set_error("fdb_mirror_download_range: %p has no mirror of at least %zu bytes", host, offset + nbytes);
+        return 1;
+    }
+    if (nbytes)
+        FDB_CUDA(cudaMemcpyAsync((char *)host + offset, (const char *)it->second.dev + offset, nbytes,
+                                 cudaMemcpyDeviceToHost, ctx().stream));
+    if (sync) FDB_CUDA(cudaStreamSynchronize(ctx().stream));
+    return 0;
+}
+
 int fdb_mirror_drop(const void *host)
 {
     if (require_init()) return 1;

@@ -989,7 +989,11 @@ class Parloop:
                  if a.access == READ and isinstance(a.data, Dat) and a.data.dataset.halo is not None
                  and not a.data.halo_valid]
         if reads and self.location != "device":
-            raise NotImplementedError("halo exchanges run on device-resident Dats")
+            base0 = self.iterset.superset if isinstance(self.iterset, Subset) else self.iterset
+            if getattr(base0, "owner_computes", False) and len(self.args) == 3 and not isinstance(self.iterset, Subset):
+                return self._call_host_partitioned()
+            raise NotImplementedError("halo exchanges on host-resident Dats need an exec-halo partition "
+                                      "(SlabPartition(exec_halo=True)); otherwise use location='device'")
         incs = [a.data for a in self.args
                 if a.access == INC and isinstance(a.data, Dat) and a.data.dataset.halo is not None
                 and not a.data.frozen_halo]
@@ -1045,6 +1049,83 @@ class Parloop:
             d.dataset.halo.local_to_global_end(d)
 
     compute = __call__
+
+    # -- host-resident Dats on a partitioned mesh (exec-halo protocol) -------------------------------
+    def _host_plan(self):
+        """Row ranges of the partitioned host path, read off the map once: ``upto`` = rows the core
+        cells touch (the engine's chunked pipeline uploads exactly those), ``ranges`` = owned rows the
+        boundary cells (owned-non-core + exec halo) touch, merged into a few contiguous ranges."""
+        if getattr(self, "_hplan", None) is None:
+            it = self.iterset
+            m = self.args[0].map
+            mp = m.values_with_halo.astype(np.int64)
+            nlay = it.layers - 1 if it._extruded else 1
+            off = (m.offset if m.offset is not None else np.zeros(m.arity, dtype=IntType)).astype(np.int64)
+            owned = self.args[0].data.dataset.set.size
+            top = mp + off[None, :] * (nlay - 1) + 1
+            upto = int(top[:it.core_size].max()) if it.core_size else 0
+            lo = mp[it.core_size:].ravel()
+            hi = top[it.core_size:].ravel()
+            keep = lo < owned
+            lo, hi = lo[keep], np.minimum(hi[keep], owned)
+            order = np.argsort(lo, kind="stable")
+            ranges = []
+            for a, b in zip(lo[order].tolist(), hi[order].tolist()):
+                if ranges and a - ranges[-1][1] <= 65536:
+                    ranges[-1][1] = max(ranges[-1][1], b)
+                else:
+                    ranges.append([a, b])
+            self._hplan = (min(upto, owned), owned, ranges)
+        return self._hplan
+
+    def _call_host_partitioned(self):
+        """``location="host"`` on an exec-halo partition: pinned host Dats in, host Dats out, every
+        PCIe transfer overlapped with compute where the data dependences allow --
+        1. core cells through the engine's chunked pipeline (H2D of x | kernel | D2H of y, three streams),
+        2. the owned rows of x the core cells never read are uploaded, ghost rows arrive from their
+           owners (NCCL, device to device: the host copies of ghost rows are stale by definition),
+        3. boundary cells (owned-non-core + exec halo) on the mirrors,
+        4. the few row ranges of y they touch are downloaded again."""
+        it = self.iterset
+        out, X, x = (a.data for a in self.args)
+        m0, m1 = self.args[0].map, self.args[1].map
+        L = _lib.lib()
+        upto, owned, ranges = self._host_plan()
+        self._compute(it.core_part)                               # 1. (host path: pipelined when large)
+        rowb = x.cdim * x.dtype.itemsize
+
+        def mirror(buf, version, upload):
+            d = C.c_void_p()
+            _lib.check(L.fdb_mirror_acquire(buf.ctypes.data, buf.nbytes, int(version), int(upload), C.byref(d)),
+                       "fdb_mirror_acquire")
+            return d.value
+        xd = mirror(x._data, x.dat_version, 0)
+        if it.core_size == 0:                                     # nothing ran yet: whole upload, zero output
+            upto = 0
+            yd0 = mirror(out._data, out.dat_version, 0)
+            _lib.check(L.fdb_memset(yd0, 0, out._data.nbytes))
+            out.increment_dat_version()
+        if owned > upto:                                          # 2.
+            _lib.check(L.fdb_mirror_upload_range(x._data.ctypes.data, upto * rowb, (owned - upto) * rowb),
+                       "fdb_mirror_upload_range")
+        halo = x.dataset.halo
+        _lib.check(L.fdb_halo_global_to_local_begin(halo.handle, xd, x.cdim))
+        _lib.check(L.fdb_halo_global_to_local_end(halo.handle, xd, x.cdim))
+        _lib.check(L.fdb_mirror_set_version(x._data.ctypes.data, int(x.dat_version)))
+        if it.total_size > it.core_size:                          # 3.
+            yd = mirror(out._data, out.dat_version, 0)
+            Xd = mirror(X._data, X.dat_version, 1)
+            md = [mirror(m.values_with_halo, m._generation, 1) for m in (m0, m1)]
+            layers = it.layers_array.ravel() if it._extruded else None
+            self.global_kernel(it.core_size, it.total_size, layers, None, [yd, Xd, xd], None, None, md, None,
+                               _lib.LOC_DEVICE, False, False)
+            yb = out._data
+            orow = out.cdim * out.dtype.itemsize
+            for k, (a, b) in enumerate(ranges):                   # 4.
+                _lib.check(L.fdb_mirror_download_range(yb.ctypes.data, a * orow, (b - a) * orow,
+                                                       int(k == len(ranges) - 1)), "fdb_mirror_download_range")
+        out._host_valid, out._dev_valid, out._is_zero = True, False, False
+        out.halo_valid = False
 
 
 def par_loop(kernel: Kernel, iterset: Set, *args, location="device", scatter="atomic"):

@@ -84,6 +84,11 @@ int fdb_host_unregister(void *hptr);
 int fdb_mirror_acquire(const void *host, size_t nbytes, uint64_t version,
                        int upload, void **dev_out);
 int fdb_mirror_writeback(void *host);
+/* partial transfers host <-> mirror (byte offset / length inside the buffer), asynchronous on the
+ * engine stream (download: `sync` waits), and the version the mirror is current for */
+int fdb_mirror_upload_range(const void *host, size_t offset, size_t nbytes);
+int fdb_mirror_download_range(void *host, size_t offset, size_t nbytes, int sync);
+int fdb_mirror_set_version(const void *host, uint64_t version);
 int fdb_mirror_drop(const void *host);
 int fdb_mirror_drop_all(void);
 

@@ -54,6 +54,17 @@ for p, (nx, ny, nz), exec_halo in [(1, (6, 4, 5), False), (3, (7, 5, 9), False),
     ref = np.array([lookup[kk] for kk in key(lat[:no]).tolist()])
     err = np.abs(y.data_ro[:no] - ref).max() / np.abs(gy).max()
     worst = max(worst, err)
+    if exec_halo:
+        # the same loop with HOST-resident Dats (pinned buffers in, host buffers out):
+        # Parloop._call_host_partitioned -- pipeline for the core cells, NCCL for the ghost rows
+        xh = op2.Dat(dn, xv.copy(), pinned=True)
+        xh.halo_valid = False
+        yh = op2.Dat(dn, pinned=True)
+        yh.zero()
+        gk = op2.GlobalKernel(k, [m0, m1], extruded=True)
+        op2.Parloop(gk, cells, [yh(op2.INC, m0), X(op2.READ, m1), xh(op2.READ, m0)], location="host")()
+        errh = np.abs(yh._data[:no] - ref).max() / np.abs(gy).max()
+        worst = max(worst, errh)
     # global reduction (C3): x.x summed over owned dofs of all ranks
     xo = op2.Dat(op2.Set(no), f(lat)[:no])
     import ctypes as C

@@ -7,9 +7,8 @@ Python side -- argument marshalling, residency / dat_version bookkeeping, lgmap
 swapping, BC handling, the V-cycle and Krylov loops -- not the device code.
 
 Two groups: (1) tests that already PASS on a real B200 (they calibrate the mock: if
-the mock mis-emulated the ABI these would fail), (2) the tests of the code written
-after the GPU budget was spent (tests/test_jit_gpu.py, gated on the GPU until their
-first device run).
+the mock mis-emulated the ABI these would fail), (2) the tests of tests/test_jit_gpu.py
+(generic wrapper path, multigrid, solve front end), which also pass on the GPU since round 2.
 """
 import numpy as np
 import pytest

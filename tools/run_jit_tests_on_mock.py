@@ -1,6 +1,6 @@
-"""Run EVERY gated GPU test of tests/test_jit_gpu.py (all parametrisations) against the mock engine
+"""Run EVERY GPU test of tests/test_jit_gpu.py (all parametrisations) against the mock engine
 (tests/_mock_engine.py) on the CPU.  The CPU suite runs a subset (tests/test_host_logic_mock.py);
-this is the exhaustive version:  python tools/run_gated_on_mock.py"""
+this is the exhaustive version:  python tools/run_jit_tests_on_mock.py"""
 import os, sys, inspect, traceback
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
