@@ -28,8 +28,8 @@ def mock(oracle):
 # ---- (1) calibration: GPU-validated tests must also pass on the mock
 def test_mock_runs_validated_matrix_tests(mock, oracle):
     tm.test_sparsity_matches_reference_semantics(mock, oracle, 2)
-    tm.test_matrix_matches_oracle(mock, oracle, 2, 1.0, 1.0)
-    tm.test_bc_lgmaps_diagonal_and_matvec(mock, oracle)
+    tm.test_matrix_matches_oracle(mock, oracle, -1, 2, 1.0, 1.0)     # matrix_kernel fixture value: auto
+    tm.test_bc_lgmaps_diagonal_and_matvec(mock, oracle, -1)
 
 
 def test_mock_runs_validated_assemble_tests(mock, oracle):
@@ -57,7 +57,7 @@ def test_generic_vs_fast_path_host_logic(mock, oracle):
 
 
 def test_vector_space_assemble_host_logic(mock, oracle):
-    tj.test_vector_space_matrix_fast_path(mock, oracle, 1, 2)
+    tj.test_vector_space_matrix_fast_path(mock, oracle, -1, 1, 2)
     tj.test_mult_transpose(mock)
 
 
