@@ -219,15 +219,22 @@ __global__ void k_node_lgmap(const fdb_int *__restrict__ dof_lg, fdb_int nnodes,
     if (masked != 0 && masked != bs) *mixed = 1;
 }
 
-// blocked = scalar (x) I_bs (the blocked matrix was zero: plain coalesced stores, no read)
-__global__ void k_store_scalar_blocks(long long n, int bs, const double *__restrict__ sv, double *__restrict__ bv)
+// blocked = scalar (x) I_bs (the blocked matrix was zero: plain coalesced stores, no read).
+// 16-byte stores, block size folded at compile time (a 35 GB stream for config 4 at 32^3).
+template <int BS>
+__global__ void __launch_bounds__(256) k_store_scalar_blocks(long long n2, const double *__restrict__ sv,
+                                                             double2 *__restrict__ bv)
 {
-    const int bb = bs * bs;
+    constexpr int BB = BS * BS;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    for (; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const long long k = i / bb;
-        const int e = (int)(i - k * bb);
-        bv[i] = (e / bs == e % bs) ? sv[k] : 0.0;
+    for (; i < n2; i += (long long)gridDim.x * blockDim.x) {
+        const long long e0 = 2 * i, e1 = e0 + 1;
+        const long long k0 = e0 / BB, k1 = e1 / BB;
+        const int r0 = (int)(e0 - k0 * BB), r1 = (int)(e1 - k1 * BB);
+        double2 v;
+        v.x = (r0 % (BS + 1) == 0) ? __ldg(sv + k0) : 0.0;
+        v.y = (r1 % (BS + 1) == 0) ? __ldg(sv + k1) : 0.0;
+        bv[i] = v;
     }
 }
 
@@ -319,7 +326,23 @@ int fdb_mat_scalar_view_end(fdb_mat_t mb, fdb_mat_t view)
     cudaStream_t st = ctx().stream;
     if (mb->zero_pending) {
         const long long n = mb->nnz * mb->bs * mb->bs;
-        k_store_scalar_blocks<<<grid1d(n), 256, 0, st>>>(n, mb->bs, view->d_vals, mb->d_vals);
+        const long long n2 = n / 2;
+        double2 *out2 = reinterpret_cast<double2 *>(mb->d_vals);
+        const int g = grid1d(n2);
+        switch (mb->bs) {
+        case 2: k_store_scalar_blocks<2><<<g, 256, 0, st>>>(n2, view->d_vals, out2); break;
+        case 3: k_store_scalar_blocks<3><<<g, 256, 0, st>>>(n2, view->d_vals, out2); break;
+        case 4: k_store_scalar_blocks<4><<<g, 256, 0, st>>>(n2, view->d_vals, out2); break;
+        default:
+            // other block sizes: zero, then add
+            FDB_CUDA(cudaMemsetAsync(mb->d_vals, 0, sizeof(double) * (size_t)n, st));
+            k_add_scalar_blocks<<<grid1d(mb->nnz), 256, 0, st>>>(mb->nnz, mb->bs, view->d_vals, mb->d_vals);
+        }
+        if (mb->bs >= 2 && mb->bs <= 4 && (n & 1)) {
+            // odd total (bs = 3, odd nnz): the last entry is the (bs-1, bs-1) diagonal of the last block
+            FDB_CUDA(cudaMemcpyAsync(mb->d_vals + (n - 1), view->d_vals + (mb->nnz - 1), sizeof(double),
+                                     cudaMemcpyDeviceToDevice, st));
+        }
         mb->zero_pending = false;
     } else {
         k_add_scalar_blocks<<<grid1d(mb->nnz), 256, 0, st>>>(mb->nnz, mb->bs, view->d_vals, mb->d_vals);
