@@ -144,6 +144,8 @@ SIGNATURES = {
     "fdb_vec_aypx": (C.c_int, [C.c_size_t, C.c_double, C.c_void_p, C.c_void_p]),
     "fdb_vec_scale": (C.c_int, [C.c_size_t, C.c_double, C.c_void_p]),
     "fdb_vec_fill": (C.c_int, [C.c_size_t, C.c_double, C.c_void_p]),
+    "fdb_vec_gather": (C.c_int, [C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fdb_vec_scatter": (C.c_int, [C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fdb_asm_create": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "fdb_asm_destroy": (C.c_int, [C.c_void_p]),
     "fdb_asm_update": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),

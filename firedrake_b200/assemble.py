@@ -618,6 +618,26 @@ class ImplicitMatrixContext:
             bc.set(D, 1.0)
         return D
 
+    def duplicate(self, copy=True):
+        """``MatDuplicate`` of the python-context matrix (matrix_free/operators.py:451-470): a new
+        context on the same form and conditions (nothing is assembled, so nothing is copied)."""
+        if not copy:
+            raise NotImplementedError("cannot duplicate a matrix-free operator without its values (copy=0)")
+        return ImplicitMatrixContext(self.form, self.bcs)
+
+    def createSubMatrix(self, row_is, col_is=None):
+        """``MatCreateSubMatrix`` (matrix_free/operators.py:380-447).  The spaces here have ONE field,
+        so an index set is either the whole dof range -- the reference then rebuilds the context on the
+        extracted sub-form, i.e. on the same form -- or an arbitrary one, for which the reference falls
+        back to PETSc's virtual sub-matrix (``MatCreateSubMatrixVirtual``: scatter the sub-vector into
+        a zero full vector, apply, gather the rows): :class:`SubMatrixContext`."""
+        col_is = row_is if col_is is None else col_is
+        n = self.form.V.node_count * self.form.V.cdim
+        whole = lambda s: len(s) == n and np.array_equal(np.asarray(s), np.arange(n))
+        if whole(row_is) and whole(col_is):
+            return self.duplicate()
+        return SubMatrixContext(self, row_is, col_is)
+
     def multTranspose(self, X: op2.Dat, Y: op2.Dat):
         """``Y = A^T X`` (matrix_free/operators.py:245-330: the action of ``adjoint(a)`` with the
         row and column conditions exchanged).  Every form of the supported family is
@@ -636,6 +656,32 @@ class ImplicitMatrixContext:
         for bc in self.bcs:
             bc.set(Y, X)
         return Y
+
+
+class SubMatrixContext:
+    """Virtual sub-matrix ``A[rows, cols]`` of a matrix-free operator: ``mult(xs, ys)`` with compact
+    sub-vectors (plain device Dats of len(cols) / len(rows) entries; dof indices = node*cdim + comp)."""
+
+    def __init__(self, parent, rows, cols):
+        self.parent = parent
+        self.rows = np.ascontiguousarray(rows, dtype=np.int32)
+        self.cols = np.ascontiguousarray(cols, dtype=np.int32)
+        self._drows = op2.DeviceArray.from_host(self.rows)
+        self._dcols = op2.DeviceArray.from_host(self.cols)
+        V = parent.form.V
+        self._x, self._y = V.dat(), V.dat()
+        self.row_set, self.col_set = op2.Set(len(self.rows)), op2.Set(len(self.cols))
+
+    def mult(self, xs: op2.Dat, ys: op2.Dat):
+        from . import _lib
+        L = _lib.lib()
+        self._x.zero()
+        _lib.check(L.fdb_vec_scatter(len(self.cols), self._dcols.ptr, xs.device_ptr, self._x.device_ptr))
+        self._x._device_written()
+        self.parent.mult(self._x, self._y)
+        _lib.check(L.fdb_vec_gather(len(self.rows), self._drows.ptr, self._y.device_ptr, ys.device_ptr))
+        ys._device_written()
+        return ys
 
 
 def cg(A, b: op2.Dat, x: op2.Dat, rtol=1e-8, atol=0.0, maxit=1000, allreduce=None):

@@ -81,6 +81,21 @@ __global__ void k_fill(size_t n, double a, double *__restrict__ x)
     for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) x[j] = a;
 }
 
+// compact gather / scatter through an index list (virtual sub-matrices of a matrix-free operator)
+__global__ void k_gather(size_t n, const fdb_int *__restrict__ idx, const double *__restrict__ src,
+                         double *__restrict__ dst)
+{
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) dst[j] = src[idx[j]];
+}
+
+__global__ void k_scatter(size_t n, const fdb_int *__restrict__ idx, const double *__restrict__ src,
+                          double *__restrict__ dst)
+{
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) dst[idx[j]] = src[j];
+}
+
 constexpr int DOT_BLOCKS_MAX = 1184;   // 148 SMs x 8
 
 __global__ void __launch_bounds__(256)
@@ -210,6 +225,24 @@ int fdb_vec_fill(size_t n, double a, double *x)
     if (require_init()) return 1;
     if (n == 0) return 0;
     k_fill<<<stream_grid(n), 256, 0, ctx().stream>>>(n, a, x);
+    FDB_LAUNCH_CHECK();
+    return 0;
+}
+
+int fdb_vec_gather(size_t n, const fdb_int *idx, const double *src, double *dst)    /* dst[j] = src[idx[j]] */
+{
+    if (require_init()) return 1;
+    if (n == 0) return 0;
+    k_gather<<<stream_grid(n), 256, 0, ctx().stream>>>(n, idx, src, dst);
+    FDB_LAUNCH_CHECK();
+    return 0;
+}
+
+int fdb_vec_scatter(size_t n, const fdb_int *idx, const double *src, double *dst)   /* dst[idx[j]] = src[j] */
+{
+    if (require_init()) return 1;
+    if (n == 0) return 0;
+    k_scatter<<<stream_grid(n), 256, 0, ctx().stream>>>(n, idx, src, dst);
     FDB_LAUNCH_CHECK();
     return 0;
 }

@@ -369,6 +369,10 @@ int fdb_vec_fill(size_t n, double a, double *x);                              /*
                                                                                  pyop2/types/dat.py:633-636 */
 int fdb_vec_dot(size_t n, const double *x, const double *y, double *out);
 int fdb_vec_pointwise_mult(size_t n, const double *x, const double *y, double *w);
+/* compact gather / scatter through a device index list: the VecScatter of a virtual sub-matrix
+ * (MatCreateSubMatrixVirtual, the fallback of firedrake/matrix_free/operators.py:380-405) */
+int fdb_vec_gather(size_t n, const fdb_int *idx, const double *src, double *dst);   /* dst[j] = src[idx[j]] */
+int fdb_vec_scatter(size_t n, const fdb_int *idx, const double *src, double *dst);  /* dst[idx[j]] = src[j] */
 
 /* ----------------------------------------------------------- interpolation
  * Dual-evaluation parloop with WRITE access (firedrake/interpolation.py:977-1171):

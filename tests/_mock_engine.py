@@ -210,6 +210,18 @@ class MockEngine:
         _view(x, n)[:] *= a
         return 0
 
+    def fdb_vec_gather(self, n, idx, src, dst):
+        if n:
+            i = np.ctypeslib.as_array(C.cast(idx, C.POINTER(C.c_int32)), (n,))
+            _view(dst, n)[:] = np.ctypeslib.as_array(C.cast(src, C.POINTER(C.c_double)), (int(i.max()) + 1,))[i]
+        return 0
+
+    def fdb_vec_scatter(self, n, idx, src, dst):
+        if n:
+            i = np.ctypeslib.as_array(C.cast(idx, C.POINTER(C.c_int32)), (n,))
+            np.ctypeslib.as_array(C.cast(dst, C.POINTER(C.c_double)), (int(i.max()) + 1,))[i] = _view(src, n)
+        return 0
+
     def fdb_vec_fill(self, n, a, x):
         if n:
             _view(x, n)[:] = a

@@ -97,3 +97,36 @@ def test_interpolate_coordinates(engine, p):
     w = op2.Dat(op2.DataSet(V.vertex_set, 1), 2.0 * mesh.coordinates[:, 0] - mesh.coordinates[:, 2])
     wp = interpolate_q1(V, w)
     assert np.abs(wp.data_ro - (2.0 * ref[:, 0] - ref[:, 2])).max() < 1e-14
+
+
+def test_submatrix_and_duplicate_of_matrix_free_context(engine):
+    """createSubMatrix / duplicate of the matrix-free context (firedrake/matrix_free/operators.py:380-470):
+    the virtual sub-matrix applied to a compact vector equals the sub-block of the assembled matrix."""
+    import scipy.sparse as sp
+    from firedrake_b200 import op2
+    from firedrake_b200.assemble import DirichletBC, FunctionSpace, assemble, helmholtz
+    from firedrake_b200.utility_meshes import ExtrudedHexMesh
+    mesh = ExtrudedHexMesh(3, 4, 3, warp=0.05)
+    V = FunctionSpace(mesh, 2)
+    bcs = [DirichletBC(V, 0.0, "top")]
+    ctx = assemble(helmholtz(V), bcs=bcs, mat_type="matfree")
+    A = assemble(helmholtz(V), bcs=bcs)
+    ro, co, va = A.csr()
+    Ad = sp.csr_matrix((va, co, ro), shape=(V.node_count,) * 2).toarray()
+    rng = np.random.default_rng(11)
+    rows = np.sort(rng.choice(V.node_count, 40, replace=False)).astype(np.int32)
+    cols = np.sort(rng.choice(V.node_count, 55, replace=False)).astype(np.int32)
+    sub = ctx.createSubMatrix(rows, cols)
+    xs = op2.Dat(sub.col_set, rng.standard_normal(len(cols)))
+    ys = op2.Dat(sub.row_set)
+    sub.mult(xs, ys)
+    ref = Ad[np.ix_(rows, cols)] @ xs.data_ro
+    assert np.abs(ys.data_ro - ref).max() < 1e-12 * max(np.abs(ref).max(), 1.0)
+    whole = np.arange(V.node_count)
+    dup = ctx.createSubMatrix(whole, whole)
+    assert type(dup) is type(ctx) and dup is not ctx
+    x = V.dat(rng.standard_normal(V.node_count))
+    y1, y2 = V.dat(), V.dat()
+    ctx.mult(x, y1)
+    ctx.duplicate().mult(x, y2)
+    assert np.array_equal(y1.data_ro, y2.data_ro) or np.abs(y1.data_ro - y2.data_ro).max() < 1e-13 * np.abs(y1.data_ro).max()

@@ -37,6 +37,7 @@ def test_mock_runs_validated_assemble_tests(mock, oracle):
     ta.test_poisson_solve_strong_bcs_extrusion(mock)
     ta.test_cg_matches_scipy(mock)
     ta.test_get_diagonal(mock)
+    ta.test_submatrix_and_duplicate_of_matrix_free_context(mock)
 
 
 # ---- (2) the post-budget code paths
