@@ -111,6 +111,10 @@ int fdb_launch_q1_action(fdb_kernel_s *k, fdb_int start, fdb_int end, int nlay, 
                          double *y, const double *coords, const double *x, const fdb_int *map0,
                          const fdb_int *map1);
 
+int fdb_launch_q2_action(fdb_kernel_s *k, fdb_int start, fdb_int end, int nlay, const fdb_int *subset,
+                         double *y, const double *coords, const double *x, const fdb_int *map0,
+                         const fdb_int *map1);
+
 // launchers implemented in the kernel translation units
 int fdb_launch_helmholtz_action(fdb_kernel_s *k, fdb_int start, fdb_int end, int nlay,
                                 const fdb_int *subset, double *y, const double *coords,

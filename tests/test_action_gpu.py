@@ -223,20 +223,21 @@ def test_edge_cases(engine, oracle):
     assert relerr(y1.data_ro, oracle_action(oracle, mesh1, V1, 3, x1.data_ro, beta=1.0)) < TOL
 
 
+@pytest.mark.parametrize("p", [1, 2])
 @pytest.mark.parametrize("alpha,beta", [(1.0, 0.0), (1.0, 1.0), (0.0, 2.0)])
 @pytest.mark.parametrize("nz", [16, 37, 70])
-def test_q1_thread_per_cell_kernel(engine, oracle, alpha, beta, nz):
-    """Degree 1 on columns of >= 16 layers runs the one-thread-per-cell kernel (q1_action.cu):
-    full and partial warps of layers, several warp-items per column, permuted base cells,
-    [start, end) ranges and INC semantics."""
+def test_thread_per_cell_kernels(engine, oracle, p, alpha, beta, nz):
+    """Degrees 1 and 2 on columns of >= 16 layers run the one-thread-per-cell kernels (q1_action.cu,
+    q2_action.cu): full and partial warps of layers, several warp-items per column, permuted base
+    cells, [start, end) ranges and INC semantics."""
     mesh = ExtrudedHexMesh(4, 3, nz, warp=0.05, permute_seed=3)
-    V, cells, m0, m1, x, y, X = build(mesh, 1)
-    k = op2.Kernel("helmholtz", degree=1, alpha=alpha, beta=beta)
+    V, cells, m0, m1, x, y, X = build(mesh, p)
+    k = op2.Kernel("helmholtz", degree=p, alpha=alpha, beta=beta)
     gk = op2.GlobalKernel(k, [m0, m1], extruded=True)
     y.data[:] = 1.0
     for part in ((0, 5), (5, mesh.num_base_cells)):
         op2.Parloop(gk, cells, [y(op2.INC, m0), X(op2.READ, m1), x(op2.READ, m0)])._compute(part)
-    yo = oracle_action(oracle, mesh, V, 1, x.data_ro, alpha=alpha, beta=beta)
+    yo = oracle_action(oracle, mesh, V, p, x.data_ro, alpha=alpha, beta=beta)
     assert relerr(y.data_ro - 1.0, yo) < TOL
     # a subset of the columns
     sub = cells(1, 4, 7, 10)
@@ -245,7 +246,7 @@ def test_q1_thread_per_cell_kernel(engine, oracle, alpha, beta, nz):
     yo2 = np.zeros_like(yo)
     from firedrake_b200.fiat_lite import interval_element
     for c in (1, 4, 7, 10):
-        oracle.action_extruded(interval_element(1), c, c + 1, [0, mesh.layers], yo2, mesh.coordinates,
+        oracle.action_extruded(interval_element(p), c, c + 1, [0, mesh.layers], yo2, mesh.coordinates,
                                np.ascontiguousarray(x.data_ro), V.cell_node_map, V.offset, mesh.coord_map,
                                mesh.coord_offset, cdim=1, alpha=alpha, beta=beta)
     assert relerr(y2.data_ro, yo2) < TOL
