@@ -7,10 +7,7 @@
 // take the three derivatives straight from the collocated values with Dt = D B^{-1} (9 FMAs), apply
 // the metric of the trilinear geometry (recomputed at the point, as TSFC does), and accumulate the
 // transposed derivative into a second 27-value tensor; three transposed contractions bring it back
-// to the dofs.  Two 27-double tensors + the 21 geometry coefficients live in registers (255, with
-// ~85 doubles spilled by the fully unrolled point loop -- parking the collocated values in shared
-// memory instead did not reduce the spills: they come from the scheduler's hoisting of the geometry
-// across the 27 unrolled points); nothing goes through shared memory.  A warp = 32 consecutive layers of one column (strided-coalesced gathers),
+// to the dofs (storage: see the comment above the kernel).  A warp = 32 consecutive layers of one column (strided-coalesced gathers),
 // vertically adjacent cells merge the contributions to their shared face dofs with one shuffle.
 //
 // Work: 2 x 3 x 81 FMAs of contractions + 27 x (18 + ~60) per point = ~2600 fp64 instructions per
@@ -77,9 +74,17 @@ __device__ __forceinline__ void contract3(const double *M, double (&t)[N][N][N])
         }
 }
 
+// Both 27-value tensors live in a thread-private shared-memory scratch ([27 slots][128 threads]:
+// a warp's access to one slot is 32 consecutive doubles, conflict free); the point loops over qy and
+// qx are ROLLED (run-time slot indices are fine in shared memory), only qz is unrolled.  Registers
+// hold the 21 geometry coefficients and 12 accumulators: 3 CTAs per SM instead of 2, no spills
+// (the all-register version spilled ~85 doubles at the 255-register cap: 5.05 ms at 256^3).
 template <bool MASS>
-__global__ void __launch_bounds__(128, 2) q2_action_kernel(const __grid_constant__ Q2Params P)
+__global__ void __launch_bounds__(128, 3) q2_action_kernel(const __grid_constant__ Q2Params P)
 {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *su = reinterpret_cast<double *>(smem_raw) + threadIdx.x;     // collocated values: su[slot * 128]
+    double *sv = su + ND * 128;                                          // accumulator:       sv[slot * 128]
     const int lane = threadIdx.x & 31;
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -91,15 +96,15 @@ __global__ void __launch_bounds__(128, 2) q2_action_kernel(const __grid_constant
         const int layer = l0 + lane;
         const bool valid = layer < P.nlay;
         const int lay = valid ? layer : P.nlay - 1;
-        // ---- gather
-        double U[N][N][N];
-#pragma unroll
-        for (int loc = 0; loc < ND; loc++) {
-            const int g = __ldg(P.map0 + (long long)col * ND + loc) + P.off0[loc] * lay;
-            U[loc / 9][(loc / 3) % 3][loc % 3] = __ldg(P.x + g);
-        }
         double c1[3], c2[3], c3[3], c4[3], c5[3], c6[3], c7[3];
         {
+            // ---- gather, interpolate to the Gauss points in registers, park in shared memory
+            double U[N][N][N];
+#pragma unroll
+            for (int loc = 0; loc < ND; loc++) {
+                const int g = __ldg(P.map0 + (long long)col * ND + loc) + P.off0[loc] * lay;
+                U[loc / 9][(loc / 3) % 3][loc % 3] = __ldg(P.x + g);
+            }
             double X[8][3];
 #pragma unroll
             for (int v = 0; v < 8; v++) {
@@ -117,39 +122,61 @@ __global__ void __launch_bounds__(128, 2) q2_action_kernel(const __grid_constant
                 c6[a] = X[5][a] - X[4][a] - X[1][a] + X[0][a];
                 c7[a] = X[7][a] - X[6][a] - X[5][a] - X[3][a] + X[4][a] + X[2][a] + X[1][a] - X[0][a];
             }
+            contract3<0, false>(P.B, U);
+            contract3<1, false>(P.B, U);
+            contract3<2, false>(P.B, U);
+#pragma unroll
+            for (int i = 0; i < N; i++)
+#pragma unroll
+                for (int j = 0; j < N; j++)
+#pragma unroll
+                    for (int k = 0; k < N; k++) {
+                        su[((i * N + j) * N + k) * 128] = U[i][j][k];
+                        sv[((i * N + j) * N + k) * 128] = 0.0;
+                    }
         }
-        // ---- to the Gauss points (collocated values)
-        contract3<0, false>(P.B, U);
-        contract3<1, false>(P.B, U);
-        contract3<2, false>(P.B, U);
-        double V[N][N][N];
+        // ---- quadrature points: qy, qx rolled; qz unrolled
+#pragma unroll 1
+        for (int qy = 0; qy < N; qy++) {
+            const double eta = P.xq[qy];
+            double A1[3], A3[3], A6[3];
 #pragma unroll
-        for (int i = 0; i < N; i++)
+            for (int a = 0; a < 3; a++) {
+                A1[a] = fma(c4[a], eta, c1[a]);
+                A3[a] = fma(c5[a], eta, c3[a]);
+                A6[a] = fma(c7[a], eta, c6[a]);
+            }
+            double Vx[N][N];                       // x-part of the accumulator for this qy: [t][qz]
 #pragma unroll
-            for (int j = 0; j < N; j++)
+            for (int t = 0; t < N; t++)
 #pragma unroll
-                for (int k = 0; k < N; k++) V[i][j][k] = 0.0;
-        // ---- quadrature points
+                for (int k = 0; k < N; k++) Vx[t][k] = 0.0;
+#pragma unroll 1
+            for (int qx = 0; qx < N; qx++) {
+                const double xi = P.xq[qx];
+                const double dx0 = P.Dt[qx * N], dx1 = P.Dt[qx * N + 1], dx2 = P.Dt[qx * N + 2];
+                const double dy0 = P.Dt[qy * N], dy1 = P.Dt[qy * N + 1], dy2 = P.Dt[qy * N + 2];
+                double jc[3];
 #pragma unroll
-        for (int qx = 0; qx < N; qx++)
+                for (int a = 0; a < 3; a++) jc[a] = fma(A6[a], xi, A3[a]);               // dX/dzeta
+                // the z-line of collocated values through (qx, qy)
+                double uz[N];
 #pragma unroll
-            for (int qy = 0; qy < N; qy++)
+                for (int k = 0; k < N; k++) uz[k] = su[((qx * N + qy) * N + k) * 128];
+                double Vz[N] = {0.0, 0.0, 0.0};
 #pragma unroll
                 for (int qz = 0; qz < N; qz++) {
-                    double gx = 0.0, gy = 0.0, gz = 0.0;
-#pragma unroll
-                    for (int s = 0; s < N; s++) {
-                        gx = fma(P.Dt[qx * N + s], U[s][qy][qz], gx);
-                        gy = fma(P.Dt[qy * N + s], U[qx][s][qz], gy);
-                        gz = fma(P.Dt[qz * N + s], U[qx][qy][s], gz);
-                    }
-                    const double xi = P.xq[qx], eta = P.xq[qy], zeta = P.xq[qz];
-                    double ja[3], jb[3], jc[3];
+                    const double zeta = P.xq[qz];
+                    const double gx = dx0 * su[((0 * N + qy) * N + qz) * 128] + dx1 * su[((1 * N + qy) * N + qz) * 128] +
+                                      dx2 * su[((2 * N + qy) * N + qz) * 128];
+                    const double gy = dy0 * su[((qx * N + 0) * N + qz) * 128] + dy1 * su[((qx * N + 1) * N + qz) * 128] +
+                                      dy2 * su[((qx * N + 2) * N + qz) * 128];
+                    const double gz = P.Dt[qz * N] * uz[0] + P.Dt[qz * N + 1] * uz[1] + P.Dt[qz * N + 2] * uz[2];
+                    double ja[3], jb[3];
 #pragma unroll
                     for (int a = 0; a < 3; a++) {
-                        ja[a] = fma(fma(c7[a], eta, c6[a]), zeta, fma(c4[a], eta, c1[a]));
+                        ja[a] = fma(A6[a], zeta, A1[a]);
                         jb[a] = fma(fma(c7[a], zeta, c4[a]), xi, fma(c5[a], zeta, c2[a]));
-                        jc[a] = fma(fma(c7[a], eta, c6[a]), xi, fma(c5[a], eta, c3[a]));
                     }
                     double r0[3], r1[3], r2[3];
                     r0[0] = jb[1] * jc[2] - jb[2] * jc[1];
@@ -170,15 +197,34 @@ __global__ void __launch_bounds__(128, 2) q2_action_kernel(const __grid_constant
                     const double fx = s * (r0[0] * h[0] + r0[1] * h[1] + r0[2] * h[2]);
                     const double fy = s * (r1[0] * h[0] + r1[1] * h[1] + r1[2] * h[2]);
                     const double fz = s * (r2[0] * h[0] + r2[1] * h[1] + r2[2] * h[2]);
+                    Vx[0][qz] = fma(dx0, fx, Vx[0][qz]);
+                    Vx[1][qz] = fma(dx1, fx, Vx[1][qz]);
+                    Vx[2][qz] = fma(dx2, fx, Vx[2][qz]);
+                    // y-part: V[qx][t][qz] += Dt[qy][t] fy   (run-time qx: shared memory)
+                    sv[((qx * N + 0) * N + qz) * 128] = fma(dy0, fy, sv[((qx * N + 0) * N + qz) * 128]);
+                    sv[((qx * N + 1) * N + qz) * 128] = fma(dy1, fy, sv[((qx * N + 1) * N + qz) * 128]);
+                    sv[((qx * N + 2) * N + qz) * 128] = fma(dy2, fy, sv[((qx * N + 2) * N + qz) * 128]);
 #pragma unroll
-                    for (int t = 0; t < N; t++) {
-                        V[t][qy][qz] = fma(P.Dt[qx * N + t], fx, V[t][qy][qz]);
-                        V[qx][t][qz] = fma(P.Dt[qy * N + t], fy, V[qx][t][qz]);
-                        V[qx][qy][t] = fma(P.Dt[qz * N + t], fz, V[qx][qy][t]);
-                    }
-                    if (MASS) V[qx][qy][qz] = fma(P.beta * w * adet, U[qx][qy][qz], V[qx][qy][qz]);
+                    for (int t = 0; t < N; t++) Vz[t] = fma(P.Dt[qz * N + t], fz, Vz[t]);
+                    if (MASS) Vz[qz] = fma(P.beta * w * adet, uz[qz], Vz[qz]);
                 }
+#pragma unroll
+                for (int t = 0; t < N; t++)
+                    sv[((qx * N + qy) * N + t) * 128] += Vz[t];
+            }
+#pragma unroll
+            for (int t = 0; t < N; t++)
+#pragma unroll
+                for (int k = 0; k < N; k++) sv[((t * N + qy) * N + k) * 128] += Vx[t][k];
+        }
         // ---- back to the dofs
+        double V[N][N][N];
+#pragma unroll
+        for (int i = 0; i < N; i++)
+#pragma unroll
+            for (int j = 0; j < N; j++)
+#pragma unroll
+                for (int k = 0; k < N; k++) V[i][j][k] = sv[((i * N + j) * N + k) * 128];
         contract3<2, true>(P.B, V);
         contract3<1, true>(P.B, V);
         contract3<0, true>(P.B, V);
@@ -242,10 +288,17 @@ int fdb_launch_q2_action(fdb_kernel_s *k, fdb_int start, fdb_int end, int nlay, 
     long long grid = (nitems + 3) / 4;
     const long long cap = (long long)c.sm_count * 8;
     if (grid > cap) grid = cap;
+    constexpr int SMEM = 2 * ND * 128 * (int)sizeof(double);      // 55 KB: U and V scratch of the 128 threads
+    static bool configured = false;
+    if (!configured) {
+        FDB_CUDA(cudaFuncSetAttribute(q2_action_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        FDB_CUDA(cudaFuncSetAttribute(q2_action_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        configured = true;
+    }
     if (k->desc.beta != 0.0)
-        q2_action_kernel<true><<<(int)grid, 128, 0, c.stream>>>(P);
+        q2_action_kernel<true><<<(int)grid, 128, SMEM, c.stream>>>(P);
     else
-        q2_action_kernel<false><<<(int)grid, 128, 0, c.stream>>>(P);
+        q2_action_kernel<false><<<(int)grid, 128, SMEM, c.stream>>>(P);
     FDB_LAUNCH_CHECK();
     return 0;
 }
