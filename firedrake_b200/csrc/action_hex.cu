@@ -953,12 +953,12 @@ int fdb_launch_helmholtz_action(fdb_kernel_s *k, fdb_int start, fdb_int end, int
     // degree 1 on extruded columns: one thread per cell (q1_action.cu); FDB_Q1_THREAD=0 opts out
     static const bool q1_thread = !(getenv("FDB_Q1_THREAD") && atoi(getenv("FDB_Q1_THREAD")) == 0);
     if (q1_thread && k->n1d == 2 && k->desc.cdim == 1 && k->desc.scatter == FDB_SCATTER_ATOMIC &&
-        k->desc.cell == FDB_CELL_HEX_EXTRUDED && nlay >= 16 && !k->desc.affine_cells)
+        k->desc.cell == FDB_CELL_HEX_EXTRUDED && nlay >= 16)
         return fdb_launch_q1_action(k, start, end, nlay, subset, y, coords, x, map0, map1);
     // degree 2 likewise (q2_action.cu); FDB_Q2_THREAD=0 opts out
     static const bool q2_thread = !(getenv("FDB_Q2_THREAD") && atoi(getenv("FDB_Q2_THREAD")) == 0);
     if (q2_thread && k->n1d == 3 && k->desc.cdim == 1 && k->desc.scatter == FDB_SCATTER_ATOMIC &&
-        k->desc.cell == FDB_CELL_HEX_EXTRUDED && nlay >= 16 && !k->desc.affine_cells)
+        k->desc.cell == FDB_CELL_HEX_EXTRUDED && nlay >= 16)
         return fdb_launch_q2_action(k, start, end, nlay, subset, y, coords, x, map0, map1);
     switch (k->n1d) {
     case 2: return launch_n<2>(k, start, end, nlay, subset, y, coords, x, map0, map1);

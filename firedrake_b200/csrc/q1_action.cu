@@ -70,7 +70,9 @@ __device__ __forceinline__ void contract(const double *M, const double (&in)[2][
             }
 }
 
-template <bool MASS>
+// AFFINE: the caller's promise (fdb_kernel_desc.affine_cells, checked by fdb_cells_are_affine) that
+// every cell is a parallelepiped: c4..c7 vanish, the cofactor rows and det J are formed once per cell.
+template <bool MASS, bool AFFINE>
 __global__ void __launch_bounds__(128, MASS ? 2 : 3) q1_action_kernel(const __grid_constant__ Q1Params P)
 {
     const int lane = threadIdx.x & 31;
@@ -122,6 +124,20 @@ __global__ void __launch_bounds__(128, MASS ? 2 : 3) q1_action_kernel(const __gr
         contract<1, false>(P.B, bx, t0);
         contract<2, false>(P.D, t0, gz);        // B B D
         if (MASS) contract<2, false>(P.B, t0, val);
+        double R0[3], R1[3], R2[3], adet_c = 1.0, rdet_c = 1.0;
+        if (AFFINE) {
+            R0[0] = c2[1] * c3[2] - c2[2] * c3[1];
+            R0[1] = c2[2] * c3[0] - c2[0] * c3[2];
+            R0[2] = c2[0] * c3[1] - c2[1] * c3[0];
+            R1[0] = c3[1] * c1[2] - c3[2] * c1[1];
+            R1[1] = c3[2] * c1[0] - c3[0] * c1[2];
+            R1[2] = c3[0] * c1[1] - c3[1] * c1[0];
+            R2[0] = c1[1] * c2[2] - c1[2] * c2[1];
+            R2[1] = c1[2] * c2[0] - c1[0] * c2[2];
+            R2[2] = c1[0] * c2[1] - c1[1] * c2[0];
+            adet_c = fabs(c1[0] * R0[0] + c1[1] * R0[1] + c1[2] * R0[2]);
+            rdet_c = rcp_nr(adet_c);
+        }
         // ---- fluxes at the points (in place)
 #pragma unroll
         for (int qx = 0; qx < 2; qx++)
@@ -130,26 +146,34 @@ __global__ void __launch_bounds__(128, MASS ? 2 : 3) q1_action_kernel(const __gr
 #pragma unroll
                 for (int qz = 0; qz < 2; qz++) {
                     const double xi = P.xq[qx], eta = P.xq[qy], zeta = P.xq[qz];
-                    double ja[3], jb[3], jc[3];
+                    double r0[3], r1[3], r2[3], adet, rdet;
+                    if (AFFINE) {
 #pragma unroll
-                    for (int a = 0; a < 3; a++) {
-                        ja[a] = fma(fma(c7[a], eta, c6[a]), zeta, fma(c4[a], eta, c1[a]));
-                        jb[a] = fma(fma(c7[a], zeta, c4[a]), xi, fma(c5[a], zeta, c2[a]));
-                        jc[a] = fma(fma(c7[a], eta, c6[a]), xi, fma(c5[a], eta, c3[a]));
+                        for (int a = 0; a < 3; a++) { r0[a] = R0[a]; r1[a] = R1[a]; r2[a] = R2[a]; }
+                        adet = adet_c;
+                        rdet = rdet_c;
+                    } else {
+                        double ja[3], jb[3], jc[3];
+#pragma unroll
+                        for (int a = 0; a < 3; a++) {
+                            ja[a] = fma(fma(c7[a], eta, c6[a]), zeta, fma(c4[a], eta, c1[a]));
+                            jb[a] = fma(fma(c7[a], zeta, c4[a]), xi, fma(c5[a], zeta, c2[a]));
+                            jc[a] = fma(fma(c7[a], eta, c6[a]), xi, fma(c5[a], eta, c3[a]));
+                        }
+                        r0[0] = jb[1] * jc[2] - jb[2] * jc[1];
+                        r0[1] = jb[2] * jc[0] - jb[0] * jc[2];
+                        r0[2] = jb[0] * jc[1] - jb[1] * jc[0];
+                        r1[0] = jc[1] * ja[2] - jc[2] * ja[1];
+                        r1[1] = jc[2] * ja[0] - jc[0] * ja[2];
+                        r1[2] = jc[0] * ja[1] - jc[1] * ja[0];
+                        r2[0] = ja[1] * jb[2] - ja[2] * jb[1];
+                        r2[1] = ja[2] * jb[0] - ja[0] * jb[2];
+                        r2[2] = ja[0] * jb[1] - ja[1] * jb[0];
+                        adet = fabs(ja[0] * r0[0] + ja[1] * r0[1] + ja[2] * r0[2]);
+                        rdet = rcp_nr(adet);
                     }
-                    double r0[3], r1[3], r2[3];
-                    r0[0] = jb[1] * jc[2] - jb[2] * jc[1];
-                    r0[1] = jb[2] * jc[0] - jb[0] * jc[2];
-                    r0[2] = jb[0] * jc[1] - jb[1] * jc[0];
-                    r1[0] = jc[1] * ja[2] - jc[2] * ja[1];
-                    r1[1] = jc[2] * ja[0] - jc[0] * ja[2];
-                    r1[2] = jc[0] * ja[1] - jc[1] * ja[0];
-                    r2[0] = ja[1] * jb[2] - ja[2] * jb[1];
-                    r2[1] = ja[2] * jb[0] - ja[0] * jb[2];
-                    r2[2] = ja[0] * jb[1] - ja[1] * jb[0];
-                    const double adet = fabs(ja[0] * r0[0] + ja[1] * r0[1] + ja[2] * r0[2]);
                     const double w = P.wq[qx] * P.wq[qy] * P.wq[qz];
-                    const double s = P.alpha * w * rcp_nr(adet);
+                    const double s = P.alpha * w * rdet;
                     const double a0 = gx[qx][qy][qz], a1 = gy[qx][qy][qz], a2 = gz[qx][qy][qz];
                     double h[3];
 #pragma unroll
@@ -251,10 +275,11 @@ int fdb_launch_q1_action(fdb_kernel_s *k, fdb_int start, fdb_int end, int nlay, 
     long long grid = (nitems + 3) / 4;                       // 4 warps per CTA
     const long long cap = (long long)c.sm_count * 12;        // a few waves of resident CTAs
     if (grid > cap) grid = cap;
-    if (k->desc.beta != 0.0)
-        q1_action_kernel<true><<<(int)grid, 128, 0, c.stream>>>(P);
-    else
-        q1_action_kernel<false><<<(int)grid, 128, 0, c.stream>>>(P);
+    const bool mass = k->desc.beta != 0.0, aff = k->desc.affine_cells != 0;
+    if (mass && aff) q1_action_kernel<true, true><<<(int)grid, 128, 0, c.stream>>>(P);
+    else if (mass) q1_action_kernel<true, false><<<(int)grid, 128, 0, c.stream>>>(P);
+    else if (aff) q1_action_kernel<false, true><<<(int)grid, 128, 0, c.stream>>>(P);
+    else q1_action_kernel<false, false><<<(int)grid, 128, 0, c.stream>>>(P);
     FDB_LAUNCH_CHECK();
     return 0;
 }

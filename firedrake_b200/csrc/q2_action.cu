@@ -79,7 +79,8 @@ __device__ __forceinline__ void contract3(const double *M, double (&t)[N][N][N])
 // qx are ROLLED (run-time slot indices are fine in shared memory), only qz is unrolled.  Registers
 // hold the 21 geometry coefficients and 12 accumulators: 3 CTAs per SM instead of 2, no spills
 // (the all-register version spilled ~85 doubles at the 255-register cap: 5.05 ms at 256^3).
-template <bool MASS>
+// AFFINE: all cells are parallelepipeds (fdb_kernel_desc.affine_cells): cofactor rows and det J once per cell.
+template <bool MASS, bool AFFINE>
 __global__ void __launch_bounds__(128, 3) q2_action_kernel(const __grid_constant__ Q2Params P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -135,6 +136,20 @@ __global__ void __launch_bounds__(128, 3) q2_action_kernel(const __grid_constant
                         sv[((i * N + j) * N + k) * 128] = 0.0;
                     }
         }
+        double R0[3], R1[3], R2[3], adet_c = 1.0, rdet_c = 1.0;
+        if (AFFINE) {
+            R0[0] = c2[1] * c3[2] - c2[2] * c3[1];
+            R0[1] = c2[2] * c3[0] - c2[0] * c3[2];
+            R0[2] = c2[0] * c3[1] - c2[1] * c3[0];
+            R1[0] = c3[1] * c1[2] - c3[2] * c1[1];
+            R1[1] = c3[2] * c1[0] - c3[0] * c1[2];
+            R1[2] = c3[0] * c1[1] - c3[1] * c1[0];
+            R2[0] = c1[1] * c2[2] - c1[2] * c2[1];
+            R2[1] = c1[2] * c2[0] - c1[0] * c2[2];
+            R2[2] = c1[0] * c2[1] - c1[1] * c2[0];
+            adet_c = fabs(c1[0] * R0[0] + c1[1] * R0[1] + c1[2] * R0[2]);
+            rdet_c = rcp_nr2(adet_c);
+        }
         // ---- quadrature points: qy, qx rolled; qz unrolled
 #pragma unroll 1
         for (int qy = 0; qy < N; qy++) {
@@ -172,25 +187,33 @@ __global__ void __launch_bounds__(128, 3) q2_action_kernel(const __grid_constant
                     const double gy = dy0 * su[((qx * N + 0) * N + qz) * 128] + dy1 * su[((qx * N + 1) * N + qz) * 128] +
                                       dy2 * su[((qx * N + 2) * N + qz) * 128];
                     const double gz = P.Dt[qz * N] * uz[0] + P.Dt[qz * N + 1] * uz[1] + P.Dt[qz * N + 2] * uz[2];
-                    double ja[3], jb[3];
+                    double r0[3], r1[3], r2[3], adet, rdet;
+                    if (AFFINE) {
 #pragma unroll
-                    for (int a = 0; a < 3; a++) {
-                        ja[a] = fma(A6[a], zeta, A1[a]);
-                        jb[a] = fma(fma(c7[a], zeta, c4[a]), xi, fma(c5[a], zeta, c2[a]));
+                        for (int a = 0; a < 3; a++) { r0[a] = R0[a]; r1[a] = R1[a]; r2[a] = R2[a]; }
+                        adet = adet_c;
+                        rdet = rdet_c;
+                    } else {
+                        double ja[3], jb[3];
+#pragma unroll
+                        for (int a = 0; a < 3; a++) {
+                            ja[a] = fma(A6[a], zeta, A1[a]);
+                            jb[a] = fma(fma(c7[a], zeta, c4[a]), xi, fma(c5[a], zeta, c2[a]));
+                        }
+                        r0[0] = jb[1] * jc[2] - jb[2] * jc[1];
+                        r0[1] = jb[2] * jc[0] - jb[0] * jc[2];
+                        r0[2] = jb[0] * jc[1] - jb[1] * jc[0];
+                        r1[0] = jc[1] * ja[2] - jc[2] * ja[1];
+                        r1[1] = jc[2] * ja[0] - jc[0] * ja[2];
+                        r1[2] = jc[0] * ja[1] - jc[1] * ja[0];
+                        r2[0] = ja[1] * jb[2] - ja[2] * jb[1];
+                        r2[1] = ja[2] * jb[0] - ja[0] * jb[2];
+                        r2[2] = ja[0] * jb[1] - ja[1] * jb[0];
+                        adet = fabs(ja[0] * r0[0] + ja[1] * r0[1] + ja[2] * r0[2]);
+                        rdet = rcp_nr2(adet);
                     }
-                    double r0[3], r1[3], r2[3];
-                    r0[0] = jb[1] * jc[2] - jb[2] * jc[1];
-                    r0[1] = jb[2] * jc[0] - jb[0] * jc[2];
-                    r0[2] = jb[0] * jc[1] - jb[1] * jc[0];
-                    r1[0] = jc[1] * ja[2] - jc[2] * ja[1];
-                    r1[1] = jc[2] * ja[0] - jc[0] * ja[2];
-                    r1[2] = jc[0] * ja[1] - jc[1] * ja[0];
-                    r2[0] = ja[1] * jb[2] - ja[2] * jb[1];
-                    r2[1] = ja[2] * jb[0] - ja[0] * jb[2];
-                    r2[2] = ja[0] * jb[1] - ja[1] * jb[0];
-                    const double adet = fabs(ja[0] * r0[0] + ja[1] * r0[1] + ja[2] * r0[2]);
                     const double w = P.wq[qx] * P.wq[qy] * P.wq[qz];
-                    const double s = P.alpha * w * rcp_nr2(adet);
+                    const double s = P.alpha * w * rdet;
                     double h[3];
 #pragma unroll
                     for (int a = 0; a < 3; a++) h[a] = r0[a] * gx + r1[a] * gy + r2[a] * gz;
@@ -291,14 +314,17 @@ int fdb_launch_q2_action(fdb_kernel_s *k, fdb_int start, fdb_int end, int nlay, 
     constexpr int SMEM = 2 * ND * 128 * (int)sizeof(double);      // 55 KB: U and V scratch of the 128 threads
     static bool configured = false;
     if (!configured) {
-        FDB_CUDA(cudaFuncSetAttribute(q2_action_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-        FDB_CUDA(cudaFuncSetAttribute(q2_action_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        FDB_CUDA(cudaFuncSetAttribute(q2_action_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        FDB_CUDA(cudaFuncSetAttribute(q2_action_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        FDB_CUDA(cudaFuncSetAttribute(q2_action_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        FDB_CUDA(cudaFuncSetAttribute(q2_action_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         configured = true;
     }
-    if (k->desc.beta != 0.0)
-        q2_action_kernel<true><<<(int)grid, 128, SMEM, c.stream>>>(P);
-    else
-        q2_action_kernel<false><<<(int)grid, 128, SMEM, c.stream>>>(P);
+    const bool mass = k->desc.beta != 0.0, aff = k->desc.affine_cells != 0;
+    if (mass && aff) q2_action_kernel<true, true><<<(int)grid, 128, SMEM, c.stream>>>(P);
+    else if (mass) q2_action_kernel<true, false><<<(int)grid, 128, SMEM, c.stream>>>(P);
+    else if (aff) q2_action_kernel<false, true><<<(int)grid, 128, SMEM, c.stream>>>(P);
+    else q2_action_kernel<false, false><<<(int)grid, 128, SMEM, c.stream>>>(P);
     FDB_LAUNCH_CHECK();
     return 0;
 }

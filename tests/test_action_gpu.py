@@ -223,16 +223,19 @@ def test_edge_cases(engine, oracle):
     assert relerr(y1.data_ro, oracle_action(oracle, mesh1, V1, 3, x1.data_ro, beta=1.0)) < TOL
 
 
+@pytest.mark.parametrize("affine", [False, True])
 @pytest.mark.parametrize("p", [1, 2])
 @pytest.mark.parametrize("alpha,beta", [(1.0, 0.0), (1.0, 1.0), (0.0, 2.0)])
 @pytest.mark.parametrize("nz", [16, 37, 70])
-def test_thread_per_cell_kernels(engine, oracle, p, alpha, beta, nz):
+def test_thread_per_cell_kernels(engine, oracle, p, alpha, beta, nz, affine):
     """Degrees 1 and 2 on columns of >= 16 layers run the one-thread-per-cell kernels (q1_action.cu,
     q2_action.cu): full and partial warps of layers, several warp-items per column, permuted base
     cells, [start, end) ranges and INC semantics."""
-    mesh = ExtrudedHexMesh(4, 3, nz, warp=0.05, permute_seed=3)
+    # affine: a box mesh of parallelepipeds and the per-cell-metric variant (desc.affine_cells)
+    mesh = (ExtrudedHexMesh(4, 3, nz, Lx=2.0, Ly=0.75, Lz=1.5, permute_seed=3) if affine
+            else ExtrudedHexMesh(4, 3, nz, warp=0.05, permute_seed=3))
     V, cells, m0, m1, x, y, X = build(mesh, p)
-    k = op2.Kernel("helmholtz", degree=p, alpha=alpha, beta=beta)
+    k = op2.Kernel("helmholtz", degree=p, alpha=alpha, beta=beta, affine=affine)
     gk = op2.GlobalKernel(k, [m0, m1], extruded=True)
     y.data[:] = 1.0
     for part in ((0, 5), (5, mesh.num_base_cells)):
