@@ -75,6 +75,27 @@ for p, (nx, ny, nz), exec_halo in [(1, (6, 4, 5), False), (3, (7, 5, 9), False),
     _lib.check(L.fdb_allreduce(d.ptr, 1, 0))
     tot = d.to_host(np.zeros(1))[0]
     assert abs(tot - (f(glat) ** 2).sum()) < 1e-9 * abs(tot), (tot, (f(glat) ** 2).sum())
+if world >= 3:
+    # Advisor (round 1): an owned dof that is a ghost on TWO neighbours appears in two neighbour
+    # lists of the SUM unpack (partition corners in the reference's DMPlex partitions; the slab
+    # partition never produces one).  Ring: my dof 0 is ghost row 4 on my right neighbour and ghost
+    # row 5 on my left neighbour; local->global must add both contributions.
+    left, right = (rank - 1) % world, (rank + 1) % world
+    ring = Halo([(left, np.array([0], dtype=np.int32), np.array([4], dtype=np.int32)),
+                 (right, np.array([0], dtype=np.int32), np.array([5], dtype=np.int32))])
+    rs = op2.Set((4, 4, 6))
+    d = op2.Dat(op2.DataSet(rs, 1, halo=ring), np.array([1.0 + rank, 0, 0, 0, 10.0 * (rank + 1), 100.0 * (rank + 1)]))
+    d.device_ptr
+    ring.local_to_global_begin(d)
+    ring.local_to_global_end(d)
+    # my ghost row 4 is LEFT's dof 0, row 5 is RIGHT's dof 0: my dof 0 receives right's row 4 and left's row 5
+    expect = 1.0 + rank + 10.0 * (right + 1) + 100.0 * (left + 1)
+    assert abs(d.data_ro[0] - expect) < 1e-12, (rank, d.data_ro[0], expect)
+    ring.global_to_local_begin(d)
+    ring.global_to_local_end(d)
+    got = d.data_ro_with_halos
+    exp_l = 1.0 + left + 10.0 * (rank + 1) + 100.0 * ((left - 1) % world + 1)
+    assert abs(got[4] - exp_l) < 1e-12, (rank, got[4], exp_l)
 print(f"rank {rank}/{world}: worst rel err {worst:.2e}")
 assert worst < 1e-12
 if dist is not None:

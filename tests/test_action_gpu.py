@@ -108,6 +108,34 @@ def test_host_pointer_mode(engine, oracle):
     assert relerr(y.data_ro, 3.0 * yo) < TOL
 
 
+def test_map_generation_defeats_a_recycled_address(engine, oracle):
+    """Advisor (round 1): the engine mirrors host map buffers by ADDRESS.  A new Map whose buffer
+    lands on a freed Map's address must not hit the old mirror: maps carry a generation id
+    (fdb_call_args.map_versions).  Emulated by rewriting the buffer in place under a fresh id."""
+    p = 2
+    mesh = ExtrudedHexMesh(4, 3, 5, warp=0.05)
+    V, cells, m0, m1, x, y, X = build(mesh, p)
+    k = op2.Kernel("helmholtz", degree=p)
+    gk = op2.GlobalKernel(k, [m0, m1], extruded=True)
+    op2.Parloop(gk, cells, [y(op2.INC, m0), X(op2.READ, m1), x(op2.READ, m0)], location="host")()
+    yo = oracle_action(oracle, mesh, V, p, x.data_ro)
+    assert relerr(y.data_ro, yo) < TOL
+    # "another mesh at the same address": the same cells in a different order, same buffers
+    perm = np.random.default_rng(0).permutation(mesh.num_base_cells)
+    m0.values_with_halo[:] = m0.values_with_halo[perm]
+    m1.values_with_halo[:] = m1.values_with_halo[perm]
+    m0._generation, m1._generation = next(op2._generations), next(op2._generations)
+    y2 = op2.Dat(y.dataset)
+    # only the first two columns: the result depends on WHICH cells they now are
+    op2.Parloop(gk, cells, [y2(op2.INC, m0), X(op2.READ, m1), x(op2.READ, m0)], location="host")._compute((0, 2))
+    yo2 = np.zeros_like(yo)
+    from firedrake_b200.fiat_lite import interval_element
+    oracle.action_extruded(interval_element(p), 0, 2, [0, mesh.layers], yo2, mesh.coordinates,
+                           np.ascontiguousarray(x.data_ro), np.ascontiguousarray(m0.values_with_halo), V.offset,
+                           np.ascontiguousarray(m1.values_with_halo), mesh.coord_offset)
+    assert relerr(y2.data_ro, yo2) < TOL
+
+
 def test_vector_space_aos(engine, oracle):
     """cdim = 3, node-major / component-fastest (vector Helmholtz, config 4)."""
     p = 2
