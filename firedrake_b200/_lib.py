@@ -76,6 +76,7 @@ class WrapperArg(C.Structure):
         ("offset", C.POINTER(C.c_int32)), ("offset2", C.POINTER(C.c_int32)),
         ("permutation", C.POINTER(C.c_int32)),
         ("interior_horizontal", C.c_int32),
+        ("offset_quotient", C.POINTER(C.c_int32)), ("offset_quotient2", C.POINTER(C.c_int32)),
     ]
 
 
@@ -84,7 +85,7 @@ class WrapperDesc(C.Structure):
         ("kernel_source", C.c_char_p), ("kernel_name", C.c_char_p),
         ("nargs", C.c_int32), ("args", C.POINTER(WrapperArg)),
         ("extruded", C.c_int32), ("subset", C.c_int32), ("iteration_region", C.c_int32),
-        ("pass_layer_arg", C.c_int32),
+        ("pass_layer_arg", C.c_int32), ("extruded_periodic", C.c_int32),
     ]
 
 

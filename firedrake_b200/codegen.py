@@ -66,6 +66,11 @@ class PermutedMap:
     def offset(self):
         return None if self.map_.offset is None else np.asarray(self.map_.offset)[self.permutation]
 
+    @property
+    def offset_quotient(self):
+        oq = getattr(self.map_, "offset_quotient", None)
+        return None if oq is None else np.asarray(oq)[self.permutation]
+
 
 def _base(map_):
     return map_.map_ if isinstance(map_, PermutedMap) else map_
@@ -86,7 +91,8 @@ class WrapperSpec:
     """The compile-time description of one generic parloop."""
 
     def __init__(self, kernel: CStringKernel, args, *, extruded=False, subset=False,
-                 iteration_region="ALL", interior_horizontal=None, pass_layer_arg=False):
+                 iteration_region="ALL", interior_horizontal=None, pass_layer_arg=False,
+                 extruded_periodic=False):
         from . import op2
         if interior_horizontal is None:
             # every indirect argument of an interior-horizontal-facet loop packs the cells
@@ -99,7 +105,7 @@ class WrapperSpec:
         self._keep = []
         arr = (_lib.WrapperArg * len(args))()
         key = [kernel.code, kernel.name, bool(extruded), bool(subset), iteration_region,
-               bool(interior_horizontal), bool(pass_layer_arg)]
+               bool(interior_horizontal), bool(pass_layer_arg), bool(extruded_periodic)]
         for i, a in enumerate(args):
             w = arr[i]
             w.access = int(a.access)
@@ -113,8 +119,10 @@ class WrapperSpec:
                 w.map, w.map2 = self._slot(rmap), self._slot(cmap)
                 w.arity, w.arity2 = rmap.arity, cmap.arity
                 w.offset, w.offset2 = self._ints(rmap.offset), self._ints(cmap.offset)
+                roq, coq = getattr(rmap, "offset_quotient", None), getattr(cmap, "offset_quotient", None)
+                w.offset_quotient, w.offset_quotient2 = self._ints(roq), self._ints(coq)
                 key.append(("mat", w.access, data.bs, w.map, w.map2, w.arity, w.arity2,
-                            self._tup(rmap.offset), self._tup(cmap.offset)))
+                            self._tup(rmap.offset), self._tup(cmap.offset), self._tup(roq), self._tup(coq)))
             elif isinstance(data, op2.Global):
                 w.kind = _lib.ARG_GLOBAL
                 w.dtype = _DTYPE_CODE[np.dtype(data._data.dtype)]
@@ -128,10 +136,12 @@ class WrapperSpec:
                 if m is not None:
                     w.map, w.arity = self._slot(m), m.arity
                     w.offset = self._ints(m.offset)
+                    oq = getattr(m, "offset_quotient", None)
+                    w.offset_quotient = self._ints(oq)
                     perm = m.permutation if isinstance(m, PermutedMap) else None
                     w.permutation = self._ints(perm)
                     key.append(("dat", w.access, w.dtype, w.dim, w.map, w.arity, self._tup(m.offset),
-                                self._tup(perm)))
+                                self._tup(perm), self._tup(oq)))
                 else:
                     key.append(("dat", w.access, w.dtype, w.dim, -1))
         self.cache_key = tuple(key)
@@ -142,6 +152,7 @@ class WrapperSpec:
         d.extruded, d.subset = int(bool(extruded)), int(bool(subset))
         d.iteration_region = _REGIONS[iteration_region]
         d.pass_layer_arg = int(bool(pass_layer_arg))
+        d.extruded_periodic = int(bool(extruded_periodic))
         self._keep.append(arr)
         self.desc = d
 
@@ -225,7 +236,8 @@ def par_loop(kernel: CStringKernel, iterset, *args, iteration_region="ALL", loca
             raise op2.MapValueError(f"direct argument {a.data.name} is not defined on the iteration set")
     spec = WrapperSpec(kernel, args, extruded=base._extruded, subset=isinstance(iterset, op2.Subset),
                        iteration_region=iteration_region, interior_horizontal=interior_horizontal,
-                       pass_layer_arg=pass_layer_arg)
+                       pass_layer_arg=pass_layer_arg,
+                       extruded_periodic=getattr(base, "extruded_periodic", False))
     h = _handle(spec)
     ca = _lib.CallArgs()
     lgmat = []
@@ -326,7 +338,8 @@ def _par_loop_host(kernel, iterset, args, iteration_region, interior_horizontal=
         raise NotImplementedError("host-pointer mode takes Dats and Globals (Mats live on the device)")
     spec = WrapperSpec(kernel, args, extruded=base._extruded, subset=isinstance(iterset, op2.Subset),
                        iteration_region=iteration_region, interior_horizontal=interior_horizontal,
-                       pass_layer_arg=pass_layer_arg)
+                       pass_layer_arg=pass_layer_arg,
+                       extruded_periodic=getattr(base, "extruded_periodic", False))
     h = _handle(spec)
     for a in args:
         if isinstance(a.data, op2.Dat):

@@ -49,7 +49,7 @@ struct FdbWrapParams {
     int start, end;        // iteration range
     int layer_lo, layer_hi;  // cell layers iterated: [layer_lo, layer_hi)
     int bottom;            // layers[0]
-    int pad_;
+    int ncl;               // cell layers per column (the modulus of periodic extrusion)
     const int *subset;
     void *arg[FDB_WRAP_MAX_ARGS];
     const int *map[FDB_WRAP_MAX_MAPS];
@@ -94,7 +94,7 @@ struct FdbWrapParams {
     int start, end;
     int layer_lo, layer_hi;
     int bottom;
-    int pad_;
+    int ncl;
     const int *subset;
     void *arg[16];
     const int *map[8];
@@ -327,10 +327,10 @@ struct ArgInfo {
 
 struct IndexSet {     // one materialised index array: map slot + offsets + permutation + f extent
     int map, arity, F;
-    std::vector<int> off, perm;
+    std::vector<int> off, perm, oq;     // oq: offset_quotient (periodic extrusion), empty = zeros
     bool same(const IndexSet &o) const
     {
-        return map == o.map && arity == o.arity && F == o.F && off == o.off && perm == o.perm;
+        return map == o.map && arity == o.arity && F == o.F && off == o.off && perm == o.perm && oq == o.oq;
     }
 };
 
@@ -338,7 +338,7 @@ struct Plan {
     std::string name;
     std::vector<ArgInfo> args;
     std::vector<IndexSet> idx;
-    int extruded = 0, subset = 0, region = 0, nmaps = 0, nmats = 0, pass_layer = 0;
+    int extruded = 0, subset = 0, region = 0, nmaps = 0, nmats = 0, pass_layer = 0, periodic = 0;
     // a direct Dat that is written from an extruded loop goes through a private copy
     bool private_direct(const fdb_wrapper_arg &a) const
     {
@@ -373,16 +373,19 @@ int validate(const fdb_wrapper_desc *d, Plan &pl)
     pl.subset = d->subset ? 1 : 0;
     pl.region = d->iteration_region;
     pl.pass_layer = d->pass_layer_arg ? 1 : 0;
+    pl.periodic = (d->extruded && d->extruded_periodic) ? 1 : 0;
     if (pl.pass_layer && !pl.extruded) {
         set_error("fdb_wrapper: pass_layer_arg needs an extruded set (pyop2/global_kernel.py:299-302)");
         return 1;
     }
-    auto add_index = [&](int map, int arity, int F, const fdb_int *off, const fdb_int *perm) -> int {
+    auto add_index = [&](int map, int arity, int F, const fdb_int *off, const fdb_int *perm,
+                         const fdb_int *oq) -> int {
         IndexSet s;
         s.map = map;
         s.arity = arity;
         s.F = F;
         if (off && pl.extruded) s.off.assign(off, off + arity);
+        if (oq && pl.extruded && pl.periodic) s.oq.assign(oq, oq + arity);
         if (perm) s.perm.assign(perm, perm + arity);
         for (size_t i = 0; i < pl.idx.size(); i++)
             if (pl.idx[i].same(s)) return (int)i;
@@ -423,7 +426,7 @@ int validate(const fdb_wrapper_desc *d, Plan &pl)
                             return 1;
                         }
                 pl.nmaps = std::max(pl.nmaps, a.map + 1);
-                ai.idx_r = add_index(a.map, a.arity, F, a.offset, a.permutation);
+                ai.idx_r = add_index(a.map, a.arity, F, a.offset, a.permutation, a.offset_quotient);
             } else {
                 // a direct Dat on an extruded set is indexed by the column only
                 // (pyop2/codegen/builder.py:386-397): every layer of a column sees the same
@@ -469,8 +472,8 @@ int validate(const fdb_wrapper_desc *d, Plan &pl)
             }
             ai.mat_slot = pl.nmats++;
             pl.nmaps = std::max(pl.nmaps, std::max(a.map, a.map2) + 1);
-            ai.idx_r = add_index(a.map, a.arity, F, a.offset, nullptr);
-            ai.idx_c = add_index(a.map2, a.arity2, F, a.offset2, nullptr);
+            ai.idx_r = add_index(a.map, a.arity, F, a.offset, nullptr, a.offset_quotient);
+            ai.idx_c = add_index(a.map2, a.arity2, F, a.offset2, nullptr, a.offset_quotient2);
         } else {
             set_error("fdb_wrapper: arg %d: unknown kind %d", i, a.kind);
             return 1;
@@ -479,6 +482,7 @@ int validate(const fdb_wrapper_desc *d, Plan &pl)
         if (a.offset2 && a.arity2 > 0) ai.off2.assign(a.offset2, a.offset2 + a.arity2);
         if (a.permutation && a.arity > 0) ai.perm.assign(a.permutation, a.permutation + a.arity);
         ai.a.offset = ai.a.offset2 = ai.a.permutation = nullptr;   // the copies above are the owners
+        ai.a.offset_quotient = ai.a.offset_quotient2 = nullptr;     // (copied into the index sets)
         pl.args.push_back(ai);
     }
     return 0;
@@ -525,6 +529,7 @@ std::string generate(const fdb_wrapper_desc *d, const Plan &pl)
     for (size_t s = 0; s < pl.idx.size(); s++) {
         const IndexSet &is = pl.idx[s];
         if (!is.off.empty()) emit_int_table(o, "fdb_off" + std::to_string(s), is.off);
+        if (!is.oq.empty()) emit_int_table(o, "fdb_oq" + std::to_string(s), is.oq);
         if (!is.perm.empty()) emit_int_table(o, "fdb_perm" + std::to_string(s), is.perm);
     }
     o << "FDB_DEVICE void wrap_" << pl.name << "_body(const FdbWrapParams &p, long long tid)\n{\n";
@@ -577,7 +582,15 @@ std::string generate(const fdb_wrapper_desc *d, const Plan &pl)
           << "][(long long)n * " << is.arity << " + ";
         if (!is.perm.empty()) o << "fdb_perm" << s << "[i]"; else o << "i";
         o << "]";
-        if (!is.off.empty()) o << " + fdb_off" << s << "[i] * (lrel + f)";
+        if (!is.off.empty()) {
+            if (!pl.periodic)
+                o << " + fdb_off" << s << "[i] * (lrel + f)";
+            else if (is.oq.empty())      // periodic, offset_quotient == 0 (builder.py:108-111)
+                o << " + fdb_off" << s << "[i] * ((lrel + f) % p.ncl)";
+            else                         // builder.py:112-119
+                o << " + fdb_off" << s << "[i] * ((lrel + f + fdb_oq" << s << "[i]) % p.ncl - fdb_oq" << s
+                  << "[i] % p.ncl)";
+        }
         o << ";\n";
     }
     // packs
@@ -816,6 +829,7 @@ int fdb_jit_call(fdb_kernel_s *k, const fdb_call_args *a)
         // NODE layers, so cells are [layers[0], layers[1]-1)
         const int cs = a->layers[0], ce = a->layers[1] - 1;
         p.bottom = cs;
+        p.ncl = ce - cs > 0 ? ce - cs : 1;
         switch (pl.region) {
         case FDB_REGION_ON_BOTTOM: p.layer_lo = cs; p.layer_hi = cs + 1; break;
         case FDB_REGION_ON_TOP: p.layer_lo = ce - 1; p.layer_hi = ce; break;

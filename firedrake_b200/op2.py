@@ -127,12 +127,15 @@ class ExtrudedSet(Set):
     _extruded = True
     constant_layers = True
 
-    def __init__(self, parent: Set, layers: int):
+    def __init__(self, parent: Set, layers: int, extruded_periodic: bool = False):
         super().__init__(parent.sizes, name=parent.name + "_extruded")
         if layers < 2:
             raise ValueError("an extruded set needs at least 2 node layers")
         self.parent = parent
         self.layers = int(layers)
+        # periodic in the extruded direction (pyop2/types/set.py ExtrudedSet(extruded_periodic=...)):
+        # the top layer's top dofs ARE the bottom layer's bottom dofs; maps carry offset_quotient
+        self.extruded_periodic = bool(extruded_periodic)
         self.layers_array = np.array([[0, self.layers]], dtype=IntType)
 
 
@@ -179,7 +182,7 @@ class Map:
     added per layer (pyop2/types/map.py:36-56)."""
     _ids = itertools.count()
 
-    def __init__(self, iterset, toset, arity, values, name=None, offset=None):
+    def __init__(self, iterset, toset, arity, values, name=None, offset=None, offset_quotient=None):
         self.iterset, self.toset, self.arity = iterset, toset, int(arity)
         v = np.ascontiguousarray(np.asarray(values, dtype=IntType).reshape(-1, self.arity))
         if v.shape[0] != iterset.total_size:
@@ -190,6 +193,11 @@ class Map:
         self.offset = None if offset is None else np.ascontiguousarray(offset, dtype=IntType)
         if self.offset is not None and self.offset.shape != (self.arity,):
             raise MapValueError("offset must have one entry per arity index")
+        # periodic extrusion (pyop2/types/map.py: offset_quotient): 1 for dofs on the top of the cell
+        self.offset_quotient = (None if offset_quotient is None
+                                else np.ascontiguousarray(offset_quotient, dtype=IntType))
+        if self.offset_quotient is not None and self.offset_quotient.shape != (self.arity,):
+            raise MapValueError("offset_quotient must have one entry per arity index")
         self.name = name or f"map_{next(Map._ids)}"
         self._dev = None
         self._generation = next(_generations)
@@ -903,6 +911,10 @@ class Parloop:
         self._check()
 
     def _check(self):
+        base = self.iterset.superset if isinstance(self.iterset, Subset) else self.iterset
+        if getattr(base, "extruded_periodic", False):
+            raise NotImplementedError("periodic extrusion (offset_quotient) runs on the generic wrapper path: "
+                                      "pass the local kernel as C source (op2.Kernel(code, name))")
         lk = self.global_kernel.local_kernel
         if len(self.args) != len(lk.accesses):
             raise ValueError(f"kernel takes {len(lk.accesses)} arguments, got {len(self.args)}")

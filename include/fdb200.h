@@ -271,6 +271,13 @@ typedef struct fdb_wrapper_arg {
     const fdb_int *offset2;     /* Mat column map                                            */
     const fdb_int *permutation; /* PermutedMap (pyop2/types/map.py:232-290): `arity` entries or NULL */
     int32_t interior_horizontal;/* 1: pack layer and layer+1                                  */
+    /* periodic extrusion (fdb_wrapper_desc.extruded_periodic; pyop2/codegen/builder.py:34-61,
+     * 100-123): `arity` entries, 1 where the dof sits on the TOP of the cell so that the top
+     * layer wraps onto the bottom one:
+     *   index = map[n][i] + offset[i] * ( (layer - bottom + f + oq[i]) mod L  -  oq[i] mod L ),
+     * L = cell layers per column.  NULL = all zero. */
+    const fdb_int *offset_quotient;
+    const fdb_int *offset_quotient2;   /* Mat column map */
 } fdb_wrapper_arg;
 
 typedef struct fdb_wrapper_desc {
@@ -285,6 +292,8 @@ typedef struct fdb_wrapper_desc {
     int32_t iteration_region;   /* enum fdb_region                                           */
     int32_t pass_layer_arg;     /* extruded: append the current layer (int, by value) to the
                                    local kernel's arguments (pyop2/global_kernel.py:277-279)  */
+    int32_t extruded_periodic;  /* the columns are periodic in the extruded direction
+                                   (ExtrudedSet(..., extruded_periodic=True), pyop2/types/set.py) */
 } fdb_wrapper_desc;
 
 /* The generated CUDA source (no GPU needed).  Writes at most `cap` bytes incl.

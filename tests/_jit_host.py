@@ -27,7 +27,7 @@ class MatView(C.Structure):
 
 class WrapParams(C.Structure):
     _fields_ = [("start", C.c_int), ("end", C.c_int), ("layer_lo", C.c_int), ("layer_hi", C.c_int),
-                ("bottom", C.c_int), ("pad_", C.c_int), ("subset", C.c_void_p),
+                ("bottom", C.c_int), ("ncl", C.c_int), ("subset", C.c_void_p),
                 ("arg", C.c_void_p * 16), ("map", C.c_void_p * 8), ("mat", MatView * 4)]
 
 
@@ -91,6 +91,7 @@ def run(spec, start, end, args, maps, layers=None, subset=None, region="ALL"):
     if layers is not None:
         cs, ce = int(layers[0]), int(layers[1]) - 1
         p.bottom = cs
+        p.ncl = max(ce - cs, 1)
         lo, hi = {"ALL": (cs, ce), "ON_BOTTOM": (cs, cs + 1), "ON_TOP": (ce - 1, ce),
                   "ON_INTERIOR_FACETS": (cs, ce - 1)}[region]
         p.layer_lo, p.layer_hi = lo, hi

@@ -383,6 +383,7 @@ class MockEngine:
         if k["extruded"]:
             cs, ce = a.layers[0], a.layers[1] - 1
             p.bottom = cs
+            p.ncl = max(ce - cs, 1)
             lo, hi = {0: (cs, ce), 1: (cs, cs + 1), 2: (ce - 1, ce), 3: (cs, ce - 1)}[k["region"]]
             p.layer_lo, p.layer_hi = lo, hi
             nl = max(hi - lo, 0)

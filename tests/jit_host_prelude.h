@@ -30,7 +30,7 @@ struct FdbWrapParams {
     int start, end;
     int layer_lo, layer_hi;
     int bottom;
-    int pad_;
+    int ncl;
     const int *subset;
     void *arg[16];
     const int *map[8];

@@ -52,6 +52,10 @@ def test_access_modes_host_logic(mock):
     tj.test_access_modes(mock)
 
 
+def test_periodic_extrusion_host_logic(mock, oracle):
+    tj.test_periodic_extrusion_on_device(mock, oracle)
+
+
 def test_generic_vs_fast_path_host_logic(mock, oracle):
     tj.test_generic_extruded_action_equals_fast_path_and_oracle(mock, oracle)
     tj.test_expression_interpolation(mock)

@@ -417,3 +417,45 @@ def test_variable_coefficient_form(engine, oracle):
     yx = assemble_variable_coefficient(V, xk, u)
     yk = assemble_variable_coefficient(V, kap, u)
     assert np.abs(yk.data_ro - (2 * y1.data_ro + yx.data_ro)).max() < 1e-12 * scale
+
+
+def test_periodic_extrusion_on_device(engine, oracle):
+    """Periodic extrusion on the GPU (generic wrapper path): Q1 Poisson action on columns that are
+    periodic in z -- nz dofs per vertex column, the top cell's top dofs are the bottom cell's bottom
+    ones (Map.offset_quotient, pyop2/codegen/builder.py:100-123) -- against a cell-by-cell NumPy
+    assembly of the oracle's element actions with wrapped indices."""
+    from oracle import oracle as orc
+    nx, ny, nz = 3, 2, 6
+    mesh = ExtrudedHexMesh(nx, ny, nz, warp=0.0)
+    V1 = mesh.coord_space
+    NV = (nx + 1) * (ny + 1)
+    cols = op2.ExtrudedSet(op2.Set(mesh.num_base_cells), mesh.layers, extruded_periodic=True)
+    pnodes = op2.Set(NV * nz)
+    vnodes = op2.Set(V1.node_count)
+    # periodic numbering: vertex column v holds dofs v*nz .. v*nz + nz-1
+    vcol = (V1.cell_node_map[:, ::2] // (nz + 1))            # (ncols, 4): vertex column of each (ax, ay)
+    assert np.array_equal(V1.cell_node_map[:, ::2] % (nz + 1), 0 * vcol)
+    pm = np.empty((mesh.num_base_cells, 8), dtype=np.int32)
+    pm[:, 0::2] = vcol * nz
+    pm[:, 1::2] = vcol * nz + 1
+    m0 = op2.Map(cols, pnodes, 8, pm, offset=[1] * 8, offset_quotient=[0, 1] * 4)
+    m1 = op2.Map(cols, vnodes, 8, mesh.coord_map, offset=mesh.coord_offset)
+    rng = np.random.default_rng(5)
+    u = op2.Dat(pnodes, rng.standard_normal(NV * nz))
+    y = op2.Dat(pnodes)
+    X = op2.Dat(op2.DataSet(vnodes, 3), mesh.coordinates)
+    op2.par_loop(op2.Kernel(tc.Q1_POISSON, "q1_poisson"), cols, y(op2.INC, m0), X(op2.READ, m1), u(op2.READ, m0))
+    el = interval_element(1)
+    ref = np.zeros(NV * nz)
+    uh = u.data_ro
+    for c in range(mesh.num_base_cells):
+        for l in range(nz):
+            idx = pm[c] + np.array([(l + q) % nz - q for q in (0, 1)] * 4)
+            cidx = mesh.coord_map[c] + mesh.coord_offset * l
+            ref[idx] += orc.cell_action(el, mesh.coordinates[cidx].ravel(), uh[idx].copy())
+    assert np.abs(y.data_ro - ref).max() < 1e-12 * np.abs(ref).max()
+    # constants are in the null space of the periodic operator as well
+    one = op2.Dat(pnodes, np.ones(NV * nz))
+    z = op2.Dat(pnodes)
+    op2.par_loop(op2.Kernel(tc.Q1_POISSON, "q1_poisson"), cols, z(op2.INC, m0), X(op2.READ, m1), one(op2.READ, m0))
+    assert np.abs(z.data_ro).max() < 1e-12
