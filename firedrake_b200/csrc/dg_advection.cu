@@ -517,6 +517,214 @@ __global__ void __launch_bounds__(128) dg_fused_nq_kernel(const __grid_constant_
     }
 }
 
+// ---- round 2: the three reference-ABI kernels specialised on NQ with the same algebra as
+// dg_fused_nq_kernel (no division in the cell term, scaled facet normal = cof(J) n_ref, constant
+// along a straight edge: no sqrt / rsqrt).  These are what a real Firedrake calls through the
+// hook (one parloop per integral type, firedrake/assemble.py:1069-1096).
+struct DgCellX {            // bilinear expansions f = F0 + F1 x + F2 y + F3 xy of geometry and velocity
+    double C1[2], C2[2], C3[2], U0[2], U1[2], U2[2], U3[2], sg;
+};
+
+__device__ __forceinline__ void dg_expand(const Q1Cell &K, DgCellX &G)
+{
+#pragma unroll
+    for (int a = 0; a < 2; a++) {
+        G.C1[a] = K.c[4 + a] - K.c[a];
+        G.C2[a] = K.c[2 + a] - K.c[a];
+        G.C3[a] = K.c[6 + a] - K.c[4 + a] - K.c[2 + a] + K.c[a];
+        G.U0[a] = K.u[a];
+        G.U1[a] = K.u[4 + a] - K.u[a];
+        G.U2[a] = K.u[2 + a] - K.u[a];
+        G.U3[a] = K.u[6 + a] - K.u[4 + a] - K.u[2 + a] + K.u[a];
+    }
+    const double detc = (G.C1[0] + 0.5 * G.C3[0]) * (G.C2[1] + 0.5 * G.C3[1]) -
+                        (G.C2[0] + 0.5 * G.C3[0]) * (G.C1[1] + 0.5 * G.C3[1]);
+    G.sg = detc < 0.0 ? -1.0 : 1.0;
+}
+
+// E[j] = sum_k dt w_k phi_j(s_k) flux_k on local facet f (run-time) of the cell G; q(s) = ta phi_0 + tb phi_1
+// is the cell's own trace, (na, nb) the neighbour's (interior) -- flux as in dg_fused_nq_kernel
+template <int NQ>
+__device__ __forceinline__ void dg_facet_E(const DgParams &P, const double (&Phi)[2][NQ], const DgCellX &G, int f,
+                                           double ta, double tb, bool interior, double na, double nbv,
+                                           double (&E)[2])
+{
+    const int e = f & 1;
+    const double xe = (double)e, sgn = e ? 1.0 : -1.0;
+    const bool vert = f < 2;
+    const double nn0 = vert ? G.sg * sgn * fma(G.C3[1], xe, G.C2[1]) : -G.sg * sgn * fma(G.C3[1], xe, G.C1[1]);
+    const double nn1 = vert ? -G.sg * sgn * fma(G.C3[0], xe, G.C2[0]) : G.sg * sgn * fma(G.C3[0], xe, G.C1[0]);
+    const double ue0 = vert ? fma(G.U1[0], xe, G.U0[0]) : fma(G.U2[0], xe, G.U0[0]);
+    const double ue1 = vert ? fma(G.U1[1], xe, G.U0[1]) : fma(G.U2[1], xe, G.U0[1]);
+    const double us0 = vert ? fma(G.U3[0], xe, G.U2[0]) : fma(G.U3[0], xe, G.U1[0]);
+    const double us1 = vert ? fma(G.U3[1], xe, G.U2[1]) : fma(G.U3[1], xe, G.U1[1]);
+    const double un_e = ue0 * nn0 + ue1 * nn1, un_s = us0 * nn0 + us1 * nn1;
+    E[0] = E[1] = 0.0;
+#pragma unroll
+    for (int k = 0; k < NQ; k++) {
+        const double uds = fma(un_s, P.xq[k], un_e);
+        const double qv = ta * Phi[0][k] + tb * Phi[1][k];
+        double flux;
+        if (!interior) {
+            flux = (uds < 0.0 ? uds * P.q_in : 0.0) + (uds > 0.0 ? uds * qv : 0.0);
+        } else {
+            const double qnv = na * Phi[0][k] + nbv * Phi[1][k];
+            flux = fmax(uds, 0.0) * qv - fmax(-uds, 0.0) * qnv;
+        }
+        const double wf = P.dt * P.wq[k] * flux;
+        E[0] = fma(wf, Phi[0][k], E[0]);
+        E[1] = fma(wf, Phi[1][k], E[1]);
+    }
+}
+
+// the two edge coefficients of q (4 dofs, index ax*2+ay) on local facet f
+__device__ __forceinline__ void dg_trace(const DgParams &P, const double *q, int f, double &ta, double &tb)
+{
+    const int e = f & 1;
+    const double b0 = P.Bend[e * 2], b1 = P.Bend[e * 2 + 1];
+    if (f < 2) { ta = q[0] * b0 + q[2] * b1; tb = q[1] * b0 + q[3] * b1; }
+    else       { ta = q[0] * b0 + q[1] * b1; tb = q[2] * b0 + q[3] * b1; }
+}
+
+// A[ax*2+ay] += sign * phi_(normal index)(x_e) * E[(tangential index)]
+__device__ __forceinline__ void dg_facet_add(const DgParams &P, int f, const double (&E)[2], double sign, double *A)
+{
+    const int e = f & 1;
+#pragma unroll
+    for (int ax = 0; ax < 2; ax++)
+#pragma unroll
+        for (int ay = 0; ay < 2; ay++)
+            A[ax * 2 + ay] += sign * (f < 2 ? P.Bend[e * 2 + ax] * E[ay] : P.Bend[e * 2 + ay] * E[ax]);
+}
+
+template <int NQ>
+__device__ __forceinline__ void dg_tab(const DgParams &P, double (&Phi)[2][NQ])
+{
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int k = 0; k < NQ; k++) Phi[i][k] = P.Bend[i] * (1.0 - P.xq[k]) + P.Bend[2 + i] * P.xq[k];
+}
+
+template <int NQ>
+__global__ void __launch_bounds__(128) dg_cell_nq_kernel(const __grid_constant__ DgParams P)
+{
+    double Phi[2][NQ];
+    dg_tab<NQ>(P, Phi);
+    const double dPhi[2] = {P.Bend[2] - P.Bend[0], P.Bend[3] - P.Bend[1]};
+    for (int i = P.start + blockIdx.x * blockDim.x + threadIdx.x; i < P.end; i += gridDim.x * blockDim.x) {
+        const int n = P.subset ? P.subset[i] : i;
+        const int4 dg = *reinterpret_cast<const int4 *>(P.dgmap + 4 * (long long)n);
+        const int4 cg = *reinterpret_cast<const int4 *>(P.cgmap + 4 * (long long)n);
+        const int dgi[4] = {dg.x, dg.y, dg.z, dg.w}, cgi[4] = {cg.x, cg.y, cg.z, cg.w};
+        Q1Cell K;
+        load_cell(P, cgi, K);
+        double ql[2][2], A[2][2] = {{0, 0}, {0, 0}};
+#pragma unroll
+        for (int k = 0; k < 4; k++) ql[k >> 1][k & 1] = P.q[dgi[k]];
+        DgCellX G;
+        dg_expand(K, G);
+#pragma unroll
+        for (int qx = 0; qx < NQ; qx++) {
+            const double x = P.xq[qx];
+            const double J01 = fma(G.C3[0], x, G.C2[0]), J11 = fma(G.C3[1], x, G.C2[1]);
+            const double uy0 = fma(G.U3[0], x, G.U2[0]), uy1 = fma(G.U3[1], x, G.U2[1]);
+            const double ub0 = fma(G.U1[0], x, G.U0[0]), ub1 = fma(G.U1[1], x, G.U0[1]);
+            const double qa = ql[0][0] * Phi[0][qx] + ql[1][0] * Phi[1][qx];
+            const double qb = ql[0][1] * Phi[0][qx] + ql[1][1] * Phi[1][qx];
+            double T0[2] = {0, 0}, T1[2] = {0, 0};
+#pragma unroll
+            for (int qy = 0; qy < NQ; qy++) {
+                const double y = P.xq[qy];
+                const double J00 = fma(G.C3[0], y, G.C1[0]), J10 = fma(G.C3[1], y, G.C1[1]);
+                const double ux0 = fma(G.U3[0], y, G.U1[0]), ux1 = fma(G.U3[1], y, G.U1[1]);
+                const double uv0 = fma(uy0, y, ub0), uv1 = fma(uy1, y, ub1);
+                const double qv = qa * Phi[0][qy] + qb * Phi[1][qy];
+                const double sc = P.dt * G.sg * P.wq[qx] * P.wq[qy] * qv;
+                const double a0 = J11 * uv0 - J01 * uv1;
+                const double a1 = J00 * uv1 - J10 * uv0;
+                const double dd = J11 * ux0 - J10 * uy0 - J01 * ux1 + J00 * uy1;
+#pragma unroll
+                for (int ay = 0; ay < 2; ay++) {
+                    T0[ay] = fma(sc * a0, Phi[ay][qy], T0[ay]);
+                    T1[ay] = fma(sc, fma(a1, dPhi[ay], dd * Phi[ay][qy]), T1[ay]);
+                }
+            }
+#pragma unroll
+            for (int ax = 0; ax < 2; ax++)
+#pragma unroll
+                for (int ay = 0; ay < 2; ay++) A[ax][ay] += dPhi[ax] * T0[ay] + Phi[ax][qx] * T1[ay];
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) atomicAdd(P.out + dgi[k], A[k >> 1][k & 1]);
+    }
+}
+
+template <int NQ>
+__global__ void __launch_bounds__(128) dg_exterior_nq_kernel(const __grid_constant__ DgParams P)
+{
+    double Phi[2][NQ];
+    dg_tab<NQ>(P, Phi);
+    for (int i = P.start + blockIdx.x * blockDim.x + threadIdx.x; i < P.end; i += gridDim.x * blockDim.x) {
+        const int f = P.subset ? P.subset[i] : i;
+        const int4 dg = *reinterpret_cast<const int4 *>(P.dgmap + 4 * (long long)f);
+        const int4 cg = *reinterpret_cast<const int4 *>(P.cgmap + 4 * (long long)f);
+        const int dgi[4] = {dg.x, dg.y, dg.z, dg.w}, cgi[4] = {cg.x, cg.y, cg.z, cg.w};
+        Q1Cell K;
+        load_cell(P, cgi, K);
+        double ql[4], A[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < 4; k++) ql[k] = P.q[dgi[k]];
+        const int lf = (int)P.facet[f];
+        DgCellX G;
+        dg_expand(K, G);
+        double ta, tb, E[2];
+        dg_trace(P, ql, lf, ta, tb);
+        dg_facet_E<NQ>(P, Phi, G, lf, ta, tb, false, 0.0, 0.0, E);
+        dg_facet_add(P, lf, E, -1.0, A);
+#pragma unroll
+        for (int k = 0; k < 4; k++) atomicAdd(P.out + dgi[k], A[k]);
+    }
+}
+
+template <int NQ>
+__global__ void __launch_bounds__(128) dg_interior_nq_kernel(const __grid_constant__ DgParams P)
+{
+    double Phi[2][NQ];
+    dg_tab<NQ>(P, Phi);
+    for (int i = P.start + blockIdx.x * blockDim.x + threadIdx.x; i < P.end; i += gridDim.x * blockDim.x) {
+        const int f = P.subset ? P.subset[i] : i;
+        int dgi[8], cgi[4];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int4 a = *reinterpret_cast<const int4 *>(P.dgmap + 8 * (long long)f + 4 * h);
+            dgi[4 * h] = a.x; dgi[4 * h + 1] = a.y; dgi[4 * h + 2] = a.z; dgi[4 * h + 3] = a.w;
+        }
+        {
+            // geometry and velocity of the '+' cell: u is continuous and the mesh conforming, so the '-'
+            // side's u.n is minus this one (what the reference's facet kernel computes from cell '-')
+            const int4 b = *reinterpret_cast<const int4 *>(P.cgmap + 8 * (long long)f);
+            cgi[0] = b.x; cgi[1] = b.y; cgi[2] = b.z; cgi[3] = b.w;
+        }
+        Q1Cell Kp;
+        load_cell(P, cgi, Kp);
+        double ql[8], A[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < 8; k++) ql[k] = P.q[dgi[k]];
+        const int fp = (int)P.facet[2 * (long long)f], fm = (int)P.facet[2 * (long long)f + 1];
+        DgCellX G;
+        dg_expand(Kp, G);
+        double ta, tb, na, nbv, E[2];
+        dg_trace(P, ql, fp, ta, tb);
+        dg_trace(P, ql + 4, fm, na, nbv);
+        dg_facet_E<NQ>(P, Phi, G, fp, ta, tb, true, na, nbv, E);
+        dg_facet_add(P, fp, E, -1.0, A);
+        dg_facet_add(P, fm, E, 1.0, A + 4);
+#pragma unroll
+        for (int k = 0; k < 8; k++) atomicAdd(P.out + dgi[k], A[k]);
+    }
+}
+
 }  // namespace
 
 int fdb_launch_dg_advection(fdb_kernel_s *k, fdb_int start, fdb_int end, const fdb_int *subset,
@@ -550,12 +758,28 @@ int fdb_launch_dg_advection(fdb_kernel_s *k, fdb_int start, fdb_int end, const f
     long long blocks = ((long long)(end - start) + 127) / 128;
     long long cap = (long long)c.sm_count * 16;
     if (blocks > cap) blocks = cap;
+    static const bool dg_generic = getenv("FDB_DG_GENERIC") && atoi(getenv("FDB_DG_GENERIC"));
     switch (k->desc.integral) {
-    case FDB_INTEGRAL_CELL: dg_cell_kernel<<<(int)blocks, 128, 0, c.stream>>>(P); break;
-    case FDB_INTEGRAL_EXTERIOR_FACET: dg_exterior_kernel<<<(int)blocks, 128, 0, c.stream>>>(P); break;
-    case FDB_INTEGRAL_INTERIOR_FACET: dg_interior_kernel<<<(int)blocks, 128, 0, c.stream>>>(P); break;
+    case FDB_INTEGRAL_CELL:
+        if (!dg_generic && P.nq == 2) dg_cell_nq_kernel<2><<<(int)blocks, 128, 0, c.stream>>>(P);
+        else if (!dg_generic && P.nq == 3) dg_cell_nq_kernel<3><<<(int)blocks, 128, 0, c.stream>>>(P);
+        else if (!dg_generic && P.nq == 4) dg_cell_nq_kernel<4><<<(int)blocks, 128, 0, c.stream>>>(P);
+        else dg_cell_kernel<<<(int)blocks, 128, 0, c.stream>>>(P);
+        break;
+    case FDB_INTEGRAL_EXTERIOR_FACET:
+        if (!dg_generic && P.nq == 2) dg_exterior_nq_kernel<2><<<(int)blocks, 128, 0, c.stream>>>(P);
+        else if (!dg_generic && P.nq == 3) dg_exterior_nq_kernel<3><<<(int)blocks, 128, 0, c.stream>>>(P);
+        else if (!dg_generic && P.nq == 4) dg_exterior_nq_kernel<4><<<(int)blocks, 128, 0, c.stream>>>(P);
+        else dg_exterior_kernel<<<(int)blocks, 128, 0, c.stream>>>(P);
+        break;
+    case FDB_INTEGRAL_INTERIOR_FACET:
+        if (!dg_generic && P.nq == 2) dg_interior_nq_kernel<2><<<(int)blocks, 128, 0, c.stream>>>(P);
+        else if (!dg_generic && P.nq == 3) dg_interior_nq_kernel<3><<<(int)blocks, 128, 0, c.stream>>>(P);
+        else if (!dg_generic && P.nq == 4) dg_interior_nq_kernel<4><<<(int)blocks, 128, 0, c.stream>>>(P);
+        else dg_interior_kernel<<<(int)blocks, 128, 0, c.stream>>>(P);
+        break;
     case FDB_INTEGRAL_FUSED: {
-        static const bool generic = getenv("FDB_DG_GENERIC") && atoi(getenv("FDB_DG_GENERIC"));
+        const bool generic = dg_generic;
         if (!generic && P.nq == 2) dg_fused_nq_kernel<2><<<(int)blocks, 128, 0, c.stream>>>(P);
         else if (!generic && P.nq == 3) dg_fused_nq_kernel<3><<<(int)blocks, 128, 0, c.stream>>>(P);
         else if (!generic && P.nq == 4) dg_fused_nq_kernel<4><<<(int)blocks, 128, 0, c.stream>>>(P);
