@@ -77,6 +77,7 @@ class WrapperArg(C.Structure):
         ("permutation", C.POINTER(C.c_int32)),
         ("interior_horizontal", C.c_int32),
         ("offset_quotient", C.POINTER(C.c_int32)), ("offset_quotient2", C.POINTER(C.c_int32)),
+        ("mixed_continuation", C.c_int32),
     ]
 
 

@@ -140,8 +140,9 @@ class WrapperSpec:
                     w.offset_quotient = self._ints(oq)
                     perm = m.permutation if isinstance(m, PermutedMap) else None
                     w.permutation = self._ints(perm)
+                    w.mixed_continuation = int(bool(getattr(a, "mixed_continuation", False)))
                     key.append(("dat", w.access, w.dtype, w.dim, w.map, w.arity, self._tup(m.offset),
-                                self._tup(perm), self._tup(oq)))
+                                self._tup(perm), self._tup(oq), w.mixed_continuation))
                 else:
                     key.append(("dat", w.access, w.dtype, w.dim, -1))
         self.cache_key = tuple(key)
@@ -219,11 +220,15 @@ def par_loop(kernel: CStringKernel, iterset, *args, iteration_region="ALL", loca
     Dat copied back).  Follows pyop2/parloop.py:243-260 without the halo phases
     (generic parloops run unpartitioned for now)."""
     from . import op2
+    if kernel.accesses is not None and tuple(a.access for a in args) != tuple(kernel.accesses):
+        raise ValueError("access descriptors do not match the kernel's")
+    # a MixedDat argument is one local tensor for the kernel and one wrapper argument per block
+    args = tuple(b for a in args for b in (a.split() if isinstance(a, op2.MixedArg) else (a,)))
+    if kernel.accesses is not None and len(args) != len(kernel.accesses):
+        kernel = CStringKernel(kernel.code, kernel.name, None, kernel.flop_count, kernel.opts)
     if location == "host":
         return _par_loop_host(kernel, iterset, args, iteration_region, interior_horizontal, pass_layer_arg)
     base = iterset.superset if isinstance(iterset, op2.Subset) else iterset
-    if kernel.accesses is not None and tuple(a.access for a in args) != tuple(kernel.accesses):
-        raise ValueError("access descriptors do not match the kernel's")
     for a in args:
         for m in (a.map, getattr(a, "cmap", None)):
             if m is None:

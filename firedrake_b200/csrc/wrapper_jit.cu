@@ -401,6 +401,15 @@ int validate(const fdb_wrapper_desc *d, Plan &pl)
             set_error("fdb_wrapper: arg %d: interior_horizontal needs an extruded set", i);
             return 1;
         }
+        if (a.mixed_continuation) {
+            // a MixedDat segment continues the previous wrapper argument's local tensor
+            if (i == 0 || a.kind != FDB_ARG_DAT || a.map < 0 || d->args[i - 1].kind != FDB_ARG_DAT ||
+                d->args[i - 1].map < 0 || d->args[i - 1].access != a.access || d->args[i - 1].dtype != a.dtype) {
+                set_error("fdb_wrapper: arg %d: a MixedDat segment must follow an indirect Dat argument of the "
+                          "same access and dtype", i);
+                return 1;
+            }
+        }
         if (a.access < FDB_READ || a.access > FDB_MAX) {
             set_error("fdb_wrapper: arg %d: bad access %d", i, a.access);
             return 1;
@@ -547,12 +556,26 @@ std::string generate(const fdb_wrapper_desc *d, const Plan &pl)
     }
     o << "    int n = p.start + (int)it;\n";
     if (pl.subset) o << "    if (active) n = p.subset[n];\n";
+    // MixedDat groups: a continuation segment shares the local tensor of its group head
+    std::vector<int> ghead(pl.args.size()), goff(pl.args.size(), 0), gsize(pl.args.size(), 0);
+    for (size_t i = 0; i < pl.args.size(); i++) {
+        const fdb_wrapper_arg &a = pl.args[i].a;
+        const int F = a.interior_horizontal ? 2 : 1;
+        const int sz = (a.kind == FDB_ARG_DAT && a.map >= 0) ? F * a.arity * a.dim : 0;
+        ghead[i] = (a.mixed_continuation && i > 0) ? ghead[i - 1] : (int)i;
+        goff[i] = gsize[ghead[i]];
+        gsize[ghead[i]] += sz;
+    }
+    auto tseg = [&](size_t i) {     // "t<head> + <offset>" of segment i
+        return "(t" + std::to_string(ghead[i]) + " + " + std::to_string(goff[i]) + ")";
+    };
     // declarations (function scope so that the reductions after the guarded block see them)
     for (size_t i = 0; i < pl.args.size(); i++) {
         const fdb_wrapper_arg &a = pl.args[i].a;
         const int F = a.interior_horizontal ? 2 : 1;
-        if (a.kind == FDB_ARG_DAT && a.map >= 0)
-            o << "    " << ctype(a.dtype) << " t" << i << "[" << F * a.arity * a.dim << "];\n";
+        if (a.kind == FDB_ARG_DAT && a.map >= 0) {
+            if (ghead[i] == (int)i) o << "    " << ctype(a.dtype) << " t" << i << "[" << gsize[i] << "];\n";
+        }
         else if (pl.private_direct(a))
             o << "    " << ctype(a.dtype) << " t" << i << "[" << a.dim << "];\n";
         else if (a.kind == FDB_ARG_GLOBAL && a.access != FDB_READ)
@@ -603,7 +626,7 @@ std::string generate(const fdb_wrapper_desc *d, const Plan &pl)
                                a.access == FDB_MAX;
             o << "        for (int k = 0; k < " << F * a.arity << "; ++k)\n"
               << "            for (int c = 0; c < " << a.dim << "; ++c)\n"
-              << "                t" << i << "[k * " << a.dim << " + c] = ";
+              << "                " << tseg(i) << "[k * " << a.dim << " + c] = ";
             if (reads)
                 o << "((const " << ctype(a.dtype) << " *)p.arg[" << i << "])[(long long)ix" << ai.idx_r
                   << "[k] * " << a.dim << " + c];\n";
@@ -618,9 +641,12 @@ std::string generate(const fdb_wrapper_desc *d, const Plan &pl)
     }
     // the local kernel
     o << "        " << pl.name << "(";
+    bool first_kernel_arg = true;
     for (size_t i = 0; i < pl.args.size(); i++) {
         const fdb_wrapper_arg &a = pl.args[i].a;
-        if (i) o << ", ";
+        if (ghead[i] != (int)i) continue;            // continuation segment of a MixedDat: no own pointer
+        if (!first_kernel_arg) o << ", ";
+        first_kernel_arg = false;
         if (a.kind == FDB_ARG_DAT && a.map < 0 && !pl.private_direct(a))
             o << "((" << ctype(a.dtype) << " *)p.arg[" << i << "]) + (long long)n * " << a.dim;
         else if (a.kind == FDB_ARG_GLOBAL && a.access == FDB_READ)
@@ -640,7 +666,7 @@ std::string generate(const fdb_wrapper_desc *d, const Plan &pl)
               << "            for (int c = 0; c < " << a.dim << "; ++c) {\n"
               << "                " << ctype(a.dtype) << " *dst = ((" << ctype(a.dtype) << " *)p.arg[" << i
               << "]) + (long long)ix" << ai.idx_r << "[k] * " << a.dim << " + c;\n"
-              << "                const " << ctype(a.dtype) << " v = t" << i << "[k * " << a.dim << " + c];\n";
+              << "                const " << ctype(a.dtype) << " v = " << tseg(i) << "[k * " << a.dim << " + c];\n";
             switch (a.access) {
             case FDB_INC: o << "                fdb_atomic_add(dst, v);\n"; break;
             case FDB_MIN: o << "                fdb_atomic_min(dst, v);\n"; break;

@@ -93,6 +93,10 @@ class Set:
     _extruded = False
     owner_computes = False     # True: partitioned with exec-halo entries, INC loops need no reduce
 
+    def __pow__(self, dim):
+        """``set ** dim`` is the DataSet of that shape on the set (pyop2/types/set.py Set.__pow__)."""
+        return DataSet(self, dim)
+
     def __init__(self, size, name=None):
         if isinstance(size, (int, np.integer)):
             size = (size, size, size)
@@ -266,6 +270,156 @@ class PinnedArray:
         except Exception:
             pass
         self.ptr = None
+
+
+# ------------------------------------------------------------- mixed carriers
+class MixedSet:
+    """Tuple of Sets (pyop2/types/set.py MixedSet): the node sets of a mixed function space."""
+
+    def __init__(self, sets):
+        self._sets = tuple(sets)
+
+    def split(self):
+        return self._sets
+
+    def __iter__(self):
+        return iter(self._sets)
+
+    def __len__(self):
+        return len(self._sets)
+
+    def __getitem__(self, i):
+        return self._sets[i]
+
+
+class MixedDataSet(MixedSet):
+    """Tuple of DataSets (pyop2/types/dataset.py MixedDataSet)."""
+
+    def __init__(self, dsets):
+        super().__init__(_as_dataset(d) for d in dsets)
+
+
+class MixedMap:
+    """Tuple of Maps from ONE iteration set to the sets of a MixedSet (pyop2/types/map.py MixedMap)."""
+
+    def __init__(self, maps):
+        self._maps = tuple(maps)
+        its = {id(_m.iterset) for _m in self._maps}
+        if len(its) != 1:
+            raise MapValueError("all maps of a MixedMap share the iteration set")
+        self.iterset = self._maps[0].iterset
+        self.arity = sum(m.arity for m in self._maps)
+
+    def split(self):
+        return self._maps
+
+    def __iter__(self):
+        return iter(self._maps)
+
+    def __len__(self):
+        return len(self._maps)
+
+    def __getitem__(self, i):
+        return self._maps[i]
+
+
+@dataclass
+class MixedArg:
+    """``mixed_dat(access, mixed_map)``: expands to one wrapper argument (= one pointer in the
+    arglist, pyop2/parloop.py:203-212) per sub-Dat, packed back to back into ONE local tensor."""
+    data: "MixedDat"
+    access: Access
+    map: MixedMap
+
+    def split(self):
+        if len(self.map) != len(self.data):
+            raise MapValueError("MixedMap and MixedDat have different numbers of blocks")
+        out = [d(self.access, m) for d, m in zip(self.data, self.map)]
+        for a in out[1:]:
+            a.mixed_continuation = True
+        return out
+
+
+class MixedDat:
+    """Tuple of Dats behaving like one vector (pyop2/types/dat.py:861-): ``split`` / indexing /
+    iteration give the blocks; whole-vector operations (zero, copy, axpy, inner, norm, +=, -=, *=)
+    apply block by block; ``dat(access, MixedMap)`` passes all blocks to a parloop."""
+
+    def __init__(self, dats_or_dset):
+        if isinstance(dats_or_dset, MixedDataSet):
+            self._dats = tuple(Dat(ds) for ds in dats_or_dset)
+        else:
+            self._dats = tuple(dats_or_dset)
+        if not all(isinstance(d, Dat) for d in self._dats):
+            raise DataSetTypeError("MixedDat takes Dats or a MixedDataSet")
+        self.dataset = MixedDataSet(d.dataset for d in self._dats)
+        self.name = "mixed_" + "_".join(d.name for d in self._dats)
+
+    def split(self):
+        return self._dats
+
+    def __iter__(self):
+        return iter(self._dats)
+
+    def __len__(self):
+        return len(self._dats)
+
+    def __getitem__(self, i):
+        return self._dats[i]
+
+    def __call__(self, access, map_=None):
+        if not isinstance(map_, MixedMap):
+            raise MapValueError("a MixedDat argument needs a MixedMap")
+        return MixedArg(self, access, map_)
+
+    @property
+    def dat_version(self):
+        return sum(d.dat_version for d in self._dats)
+
+    @property
+    def data(self):
+        return tuple(d.data for d in self._dats)
+
+    @property
+    def data_ro(self):
+        return tuple(d.data_ro for d in self._dats)
+
+    @property
+    def halo_valid(self):
+        return all(d.halo_valid for d in self._dats)
+
+    def zero(self, subset=None):
+        if subset is not None:
+            raise NotImplementedError("zero(subset) on a MixedDat: apply it to the block")
+        for d in self._dats:
+            d.zero()
+
+    def copy(self, other):
+        for a, b in zip(self._dats, other._dats):
+            a.copy(b)
+
+    def axpy(self, alpha, other):
+        for a, b in zip(self._dats, other._dats):
+            a.axpy(alpha, b)
+
+    def inner(self, other):
+        return sum(a.inner(b) for a, b in zip(self._dats, other._dats))
+
+    def norm(self):
+        return float(np.sqrt(self.inner(self)))
+
+    def __iadd__(self, other):
+        self.axpy(1.0, other)
+        return self
+
+    def __isub__(self, other):
+        self.axpy(-1.0, other)
+        return self
+
+    def __imul__(self, scalar):
+        for d in self._dats:
+            d.__imul__(scalar)
+        return self
 
 
 # ----------------------------------------------------------------------- Dats

@@ -278,6 +278,11 @@ typedef struct fdb_wrapper_arg {
      * L = cell layers per column.  NULL = all zero. */
     const fdb_int *offset_quotient;
     const fdb_int *offset_quotient2;   /* Mat column map */
+    /* MixedDat (pyop2/types/dat.py:861-, "one pointer per sub-Dat" in the arglist,
+     * pyop2/parloop.py:203-212): 1 = this wrapper argument is the NEXT SEGMENT of the previous
+     * one -- its pack is appended to the previous argument's local tensor and the local kernel
+     * receives ONE pointer for the whole group (indirect Dats of equal access and dtype only). */
+    int32_t mixed_continuation;
 } fdb_wrapper_arg;
 
 typedef struct fdb_wrapper_desc {

@@ -52,6 +52,10 @@ def test_access_modes_host_logic(mock):
     tj.test_access_modes(mock)
 
 
+def test_mixed_dat_host_logic(mock):
+    tj.test_mixed_dat_parloop_and_vector_operations(mock)
+
+
 def test_periodic_extrusion_host_logic(mock, oracle):
     tj.test_periodic_extrusion_on_device(mock, oracle)
 

@@ -459,3 +459,42 @@ def test_periodic_extrusion_on_device(engine, oracle):
     z = op2.Dat(pnodes)
     op2.par_loop(op2.Kernel(tc.Q1_POISSON, "q1_poisson"), cols, z(op2.INC, m0), X(op2.READ, m1), one(op2.READ, m0))
     assert np.abs(z.data_ro).max() < 1e-12
+
+
+def test_mixed_dat_parloop_and_vector_operations(engine):
+    """op2.MixedDat through op2.par_loop on the device and in host-pointer mode (one local tensor
+    for the kernel, one arglist pointer per block: pyop2/parloop.py:203-212), plus the block-wise
+    whole-vector operations of pyop2/types/dat.py:861-."""
+    from firedrake_b200 import codegen
+    rng = np.random.default_rng(5)
+    ncell, nv, npr = 4000, 2300, 900
+    cells, vset, pset = op2.Set(ncell), op2.Set(nv), op2.Set(npr)
+    mv = op2.Map(cells, vset, 3, rng.integers(0, nv, (ncell, 3)))
+    mp = op2.Map(cells, pset, 2, rng.integers(0, npr, (ncell, 2)))
+    u, p = op2.Dat(vset ** 2, rng.standard_normal((nv, 2))), op2.Dat(pset, rng.standard_normal(npr))
+    w, r = op2.MixedDat([u, p]), op2.MixedDat(op2.MixedDataSet([vset ** 2, pset]))
+    mm = op2.MixedMap([mv, mp])
+    k = op2.Kernel("static void k(double *r, const double *w, const double *s) {"
+                   " for (int i = 0; i < 8; ++i) r[i] += s[0]*w[i] + (i < 7 ? w[i+1] : w[0]); }", "k")
+    s = op2.Global(1, 1.5)
+    eu, ep = np.zeros((nv, 2)), np.zeros(npr)
+    for c in range(ncell):
+        loc = np.concatenate([u.data_ro[mv.values[c]].ravel(), p.data_ro[mp.values[c]].ravel()])
+        out = 1.5 * loc + np.roll(loc, -1)
+        np.add.at(eu, mv.values[c], out[:6].reshape(3, 2))
+        np.add.at(ep, mp.values[c], out[6:])
+    r.zero()
+    op2.par_loop(k, cells, r(op2.INC, mm), w(op2.READ, mm), s(op2.READ))
+    assert np.abs(r[0].data_ro - eu).max() < 1e-12 and np.abs(r[1].data_ro.ravel() - ep).max() < 1e-12
+    r.zero()
+    codegen.par_loop(k, cells, r(op2.INC, mm), w(op2.READ, mm), s(op2.READ), location="host")
+    assert np.abs(r[0]._data - eu).max() < 1e-12 and np.abs(r[1]._data.ravel() - ep).max() < 1e-12
+    # whole-vector operations act block by block
+    w2 = op2.MixedDat(w.dataset)
+    w.copy(w2)
+    w2.axpy(2.0, w)
+    assert abs(w2.inner(w) - 3.0 * w.inner(w)) < 1e-12 * w.inner(w)
+    assert abs(w.norm() - np.sqrt((u.data_ro ** 2).sum() + (p.data_ro ** 2).sum())) < 1e-12
+    w2 -= w
+    w2 *= 0.5
+    assert np.abs(w2[0].data_ro - u.data_ro).max() < 1e-14 and np.abs(w2[1].data_ro - p.data_ro).max() < 1e-14
