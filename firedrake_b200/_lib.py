@@ -57,6 +57,7 @@ class CallArgs(C.Structure):
         ("map_bytes", C.POINTER(C.c_size_t)),
         ("location", C.c_int32), ("writeback", C.c_int32), ("output_is_zero", C.c_int32),
         ("map_versions", C.POINTER(C.c_uint64)), ("subset_version", C.c_uint64),
+        ("layers_count", C.c_int32), ("layers_version", C.c_uint64),
     ]
 
 
@@ -86,7 +87,7 @@ class WrapperDesc(C.Structure):
         ("kernel_source", C.c_char_p), ("kernel_name", C.c_char_p),
         ("nargs", C.c_int32), ("args", C.POINTER(WrapperArg)),
         ("extruded", C.c_int32), ("subset", C.c_int32), ("iteration_region", C.c_int32),
-        ("pass_layer_arg", C.c_int32), ("extruded_periodic", C.c_int32),
+        ("pass_layer_arg", C.c_int32), ("extruded_periodic", C.c_int32), ("variable_layers", C.c_int32),
     ]
 
 

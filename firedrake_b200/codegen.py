@@ -92,7 +92,7 @@ class WrapperSpec:
 
     def __init__(self, kernel: CStringKernel, args, *, extruded=False, subset=False,
                  iteration_region="ALL", interior_horizontal=None, pass_layer_arg=False,
-                 extruded_periodic=False):
+                 extruded_periodic=False, constant_layers=True):
         from . import op2
         if interior_horizontal is None:
             # every indirect argument of an interior-horizontal-facet loop packs the cells
@@ -105,7 +105,7 @@ class WrapperSpec:
         self._keep = []
         arr = (_lib.WrapperArg * len(args))()
         key = [kernel.code, kernel.name, bool(extruded), bool(subset), iteration_region,
-               bool(interior_horizontal), bool(pass_layer_arg), bool(extruded_periodic)]
+               bool(interior_horizontal), bool(pass_layer_arg), bool(extruded_periodic), bool(constant_layers)]
         for i, a in enumerate(args):
             w = arr[i]
             w.access = int(a.access)
@@ -154,6 +154,7 @@ class WrapperSpec:
         d.iteration_region = _REGIONS[iteration_region]
         d.pass_layer_arg = int(bool(pass_layer_arg))
         d.extruded_periodic = int(bool(extruded_periodic))
+        d.variable_layers = int(bool(extruded) and not constant_layers)
         self._keep.append(arr)
         self.desc = d
 
@@ -242,7 +243,8 @@ def par_loop(kernel: CStringKernel, iterset, *args, iteration_region="ALL", loca
     spec = WrapperSpec(kernel, args, extruded=base._extruded, subset=isinstance(iterset, op2.Subset),
                        iteration_region=iteration_region, interior_horizontal=interior_horizontal,
                        pass_layer_arg=pass_layer_arg,
-                       extruded_periodic=getattr(base, "extruded_periodic", False))
+                       extruded_periodic=getattr(base, "extruded_periodic", False),
+                       constant_layers=getattr(base, "constant_layers", True))
     h = _handle(spec)
     ca = _lib.CallArgs()
     lgmat = []
@@ -304,6 +306,8 @@ def par_loop(kernel: CStringKernel, iterset, *args, iteration_region="ALL", loca
             ca.start, ca.end = int(start), int(end)
             if layers is not None:
                 ca.layers = layers.ctypes.data_as(C.POINTER(C.c_int32))
+                if not base.constant_layers:
+                    ca.layers_count, ca.layers_version = len(base.layers_array), base._generation
             ca.subset = subset
             ca.nargs, ca.args = len(ptrs), (C.c_void_p * len(ptrs))(*ptrs)
             mp = [m.device_ptr for m in spec.maps]
@@ -344,7 +348,8 @@ def _par_loop_host(kernel, iterset, args, iteration_region, interior_horizontal=
     spec = WrapperSpec(kernel, args, extruded=base._extruded, subset=isinstance(iterset, op2.Subset),
                        iteration_region=iteration_region, interior_horizontal=interior_horizontal,
                        pass_layer_arg=pass_layer_arg,
-                       extruded_periodic=getattr(base, "extruded_periodic", False))
+                       extruded_periodic=getattr(base, "extruded_periodic", False),
+                       constant_layers=getattr(base, "constant_layers", True))
     h = _handle(spec)
     for a in args:
         if isinstance(a.data, op2.Dat):
@@ -361,6 +366,8 @@ def _par_loop_host(kernel, iterset, args, iteration_region, interior_horizontal=
         ca.start, ca.end = int(start), int(end)
         if layers is not None:
             ca.layers = layers.ctypes.data_as(C.POINTER(C.c_int32))
+            if not base.constant_layers:
+                ca.layers_count, ca.layers_version = len(base.layers_array), base._generation
         ca.subset = iterset.indices.ctypes.data if isinstance(iterset, op2.Subset) else None
         ca.nargs, ca.args = len(ptrs), (C.c_void_p * len(ptrs))(*ptrs)
         ca.arg_bytes = (C.c_size_t * len(ptrs))(*nbytes)

@@ -51,6 +51,7 @@ struct FdbWrapParams {
     int bottom;            // layers[0]
     int ncl;               // cell layers per column (the modulus of periodic extrusion)
     const int *subset;
+    const int *col_layers; // variable layers: int[ncolumns][2] node-layer extents, else NULL
     void *arg[FDB_WRAP_MAX_ARGS];
     const int *map[FDB_WRAP_MAX_MAPS];
     FdbMatView mat[FDB_WRAP_MAX_MATS];
@@ -96,6 +97,7 @@ struct FdbWrapParams {
     int bottom;
     int ncl;
     const int *subset;
+    const int *col_layers; // variable layers: int[ncolumns][2] node-layer extents, else NULL
     void *arg[16];
     const int *map[8];
     FdbMatView mat[4];
@@ -338,7 +340,7 @@ struct Plan {
     std::string name;
     std::vector<ArgInfo> args;
     std::vector<IndexSet> idx;
-    int extruded = 0, subset = 0, region = 0, nmaps = 0, nmats = 0, pass_layer = 0, periodic = 0;
+    int extruded = 0, subset = 0, region = 0, nmaps = 0, nmats = 0, pass_layer = 0, periodic = 0, varlay = 0;
     // a direct Dat that is written from an extruded loop goes through a private copy
     bool private_direct(const fdb_wrapper_arg &a) const
     {
@@ -374,6 +376,15 @@ int validate(const fdb_wrapper_desc *d, Plan &pl)
     pl.region = d->iteration_region;
     pl.pass_layer = d->pass_layer_arg ? 1 : 0;
     pl.periodic = (d->extruded && d->extruded_periodic) ? 1 : 0;
+    pl.varlay = (d->extruded && d->variable_layers) ? 1 : 0;
+    if (d->variable_layers && !d->extruded) {
+        set_error("fdb_wrapper: variable_layers needs an extruded wrapper");
+        return 1;
+    }
+    if (pl.varlay && pl.periodic) {
+        set_error("fdb_wrapper: periodic extrusion has constant layers (pyop2/types/set.py ExtrudedSet)");
+        return 1;
+    }
     if (pl.pass_layer && !pl.extruded) {
         set_error("fdb_wrapper: pass_layer_arg needs an extruded set (pyop2/global_kernel.py:299-302)");
         return 1;
@@ -542,7 +553,27 @@ std::string generate(const fdb_wrapper_desc *d, const Plan &pl)
         if (!is.perm.empty()) emit_int_table(o, "fdb_perm" + std::to_string(s), is.perm);
     }
     o << "FDB_DEVICE void wrap_" << pl.name << "_body(const FdbWrapParams &p, long long tid)\n{\n";
-    if (pl.extruded) {
+    if (pl.varlay) {
+        // every column has its own extent; the grid is (entries) x (tallest column in the region),
+        // threads above a column's top stay idle (pyop2/codegen/builder.py:754-812)
+        o << "    const int nl = p.layer_hi - p.layer_lo;\n"
+          << "    const long long total = (long long)(p.end - p.start) * (nl > 0 ? nl : 0);\n"
+          << "    bool active = tid < total;\n"
+          << "    const long long it = active ? tid / nl : 0;\n"
+          << "    int n = p.start + (int)it;\n";
+        if (pl.subset) o << "    if (active) n = p.subset[n];\n";
+        o << "    const int fdb_cs = active ? p.col_layers[2 * (long long)n] : 0;\n"
+          << "    const int fdb_ce = active ? p.col_layers[2 * (long long)n + 1] - 1 : 0;\n";
+        switch (pl.region) {
+        case FDB_REGION_ON_BOTTOM: o << "    const int fdb_lo = fdb_cs, fdb_hi = fdb_cs + 1;\n"; break;
+        case FDB_REGION_ON_TOP: o << "    const int fdb_lo = fdb_ce - 1, fdb_hi = fdb_ce;\n"; break;
+        case FDB_REGION_ON_INTERIOR_FACETS: o << "    const int fdb_lo = fdb_cs, fdb_hi = fdb_ce - 1;\n"; break;
+        default: o << "    const int fdb_lo = fdb_cs, fdb_hi = fdb_ce;\n"; break;
+        }
+        o << "    const int layer = fdb_lo + (active ? (int)(tid - it * nl) : 0);\n"
+          << "    active = active && layer < fdb_hi && layer >= fdb_cs && layer < fdb_ce;\n"
+          << "    const int lrel = layer - fdb_cs;\n";
+    } else if (pl.extruded) {
         o << "    const int nl = p.layer_hi - p.layer_lo;\n"
           << "    const long long total = (long long)(p.end - p.start) * (nl > 0 ? nl : 0);\n"
           << "    const bool active = tid < total;\n"
@@ -554,8 +585,10 @@ std::string generate(const fdb_wrapper_desc *d, const Plan &pl)
           << "    const bool active = tid < total;\n"
           << "    const long long it = active ? tid : 0;\n";
     }
-    o << "    int n = p.start + (int)it;\n";
-    if (pl.subset) o << "    if (active) n = p.subset[n];\n";
+    if (!pl.varlay) {
+        o << "    int n = p.start + (int)it;\n";
+        if (pl.subset) o << "    if (active) n = p.subset[n];\n";
+    }
     // MixedDat groups: a continuation segment shares the local tensor of its group head
     std::vector<int> ghead(pl.args.size()), goff(pl.args.size(), 0), gsize(pl.args.size(), 0);
     for (size_t i = 0; i < pl.args.size(); i++) {
@@ -806,6 +839,11 @@ struct fdb_jit_s {
     std::vector<size_t> gofs;         // byte offset per arg (Globals only)
     size_t gbytes = 0;
     std::vector<char> h_globals;      // staging
+    // variable layers: tallest column of the last layers array seen
+    const fdb_int *lay_ptr = nullptr;
+    uint64_t lay_ver = 0;
+    fdb_int lay_cnt = 0;
+    int lay_max = 0;
 };
 
 void fdb_jit_destroy(fdb_jit_s *j)
@@ -850,7 +888,35 @@ int fdb_jit_call(fdb_kernel_s *k, const fdb_call_args *a)
     p.start = a->start;
     p.end = a->end;
     int nl = 1;
-    if (pl.extruded) {
+    if (pl.varlay) {
+        if (a->layers_count < a->end && !pl.subset) {
+            set_error("wrap_%s: variable layers: %d rows of layers for an iteration range ending at %d",
+                      pl.name.c_str(), (int)a->layers_count, (int)a->end);
+            return 1;
+        }
+        // tallest column in the iteration region: the layer extent of the launch grid
+        if (j->lay_ptr != a->layers || j->lay_ver != a->layers_version || j->lay_cnt != a->layers_count) {
+            int mx = 0;
+            for (fdb_int c = 0; c < a->layers_count; c++) {
+                const int cs = a->layers[2 * c], ce = a->layers[2 * c + 1] - 1;
+                int ext;
+                switch (pl.region) {
+                case FDB_REGION_ON_BOTTOM: case FDB_REGION_ON_TOP: ext = ce > cs ? 1 : 0; break;
+                case FDB_REGION_ON_INTERIOR_FACETS: ext = ce - 1 - cs; break;
+                default: ext = ce - cs; break;
+                }
+                if (ext > mx) mx = ext;
+            }
+            j->lay_ptr = a->layers; j->lay_ver = a->layers_version; j->lay_cnt = a->layers_count; j->lay_max = mx;
+        }
+        void *q;
+        if (fdb_mirror_acquire(a->layers, sizeof(fdb_int) * 2 * (size_t)a->layers_count, a->layers_version, 1, &q))
+            return 1;
+        p.col_layers = (const int *)q;
+        p.layer_lo = 0;
+        p.layer_hi = nl = j->lay_max;
+        p.ncl = 1;
+    } else if (pl.extruded) {
         // layer extents by iteration region (pyop2/codegen/builder.py:779-800); layers[] counts
         // NODE layers, so cells are [layers[0], layers[1]-1)
         const int cs = a->layers[0], ce = a->layers[1] - 1;

@@ -125,26 +125,50 @@ class Set:
 
 
 class ExtrudedSet(Set):
-    """A set of columns with a constant number of node layers
-    (pyop2/types/set.py:306-394): ``layers`` counts NODE layers, cells per
-    column = layers - 1; ``layers_array`` is the int[1][2] the wrapper gets."""
+    """A set of columns (pyop2/types/set.py:306-394).  ``layers`` is an int -- NODE layers
+    per column, cells per column = layers - 1, ``layers_array`` the int[1][2] the wrapper gets
+    -- or an ``(total_size, 2)`` array of ``[bottom, top)`` node layers per column (variable
+    layers: every column's map row points at ITS bottom cell; generic wrapper path only)."""
     _extruded = True
     constant_layers = True
 
-    def __init__(self, parent: Set, layers: int, extruded_periodic: bool = False):
+    def __init__(self, parent: Set, layers, extruded_periodic: bool = False):
         super().__init__(parent.sizes, name=parent.name + "_extruded")
-        if layers < 2:
-            raise ValueError("an extruded set needs at least 2 node layers")
         self.parent = parent
-        self.layers = int(layers)
+        layers = np.asarray(layers, dtype=IntType)
+        if layers.shape:
+            if layers.shape != (parent.total_size, 2):
+                raise ValueError(f"specifying layers per entity, but provided {layers.shape}, "
+                                 f"needed ({parent.total_size}, 2)")
+            if extruded_periodic:
+                raise ValueError("periodic extrusion needs constant layers")
+            if (layers[:, 1] - layers[:, 0] < 1).any():
+                raise ValueError("every column needs at least one node layer")
+            self.constant_layers = False
+            self.layers_array = np.ascontiguousarray(layers)
+            self._generation = next(_generations)
+            weakref.finalize(self, _drop_host_mirror, self.layers_array.ctypes.data)
+        else:
+            if layers < 2:
+                raise ValueError("an extruded set needs at least 2 node layers")
+            self.layers_array = np.array([[0, int(layers)]], dtype=IntType)
         # periodic in the extruded direction (pyop2/types/set.py ExtrudedSet(extruded_periodic=...)):
         # the top layer's top dofs ARE the bottom layer's bottom dofs; maps carry offset_quotient
         self.extruded_periodic = bool(extruded_periodic)
-        self.layers_array = np.array([[0, self.layers]], dtype=IntType)
+
+    @property
+    def layers(self):
+        if not self.constant_layers:
+            raise ValueError("no single layer count: use layers_array")
+        return int(self.layers_array[0, 1])
 
 
 class Subset(Set):
     _extruded = False
+
+    @property
+    def layers(self):
+        return self.superset.layers
 
     def __init__(self, superset: Set, indices):
         idx = np.unique(np.asarray(indices, dtype=IntType))
@@ -159,7 +183,7 @@ class Subset(Set):
         Set.__init__(self, (core, owned, len(idx)), name=superset.name + "_subset")
         self._extruded = superset._extruded
         if self._extruded:
-            self.layers = superset.layers
+            self.constant_layers = superset.constant_layers
             self.layers_array = superset.layers_array
 
 
@@ -892,8 +916,8 @@ class GlobalKernel:
         self.scatter = scatter
         self._handle = None
         if extruded and not constant_layers:
-            raise NotImplementedError("variable layers are deprecated in the reference "
-                                      "(firedrake/mesh.py:3540-3546) and not supported")
+            raise NotImplementedError("the hand-written kernels take constant layers; variable layers run "
+                                      "on the generic wrapper path (op2.Kernel(code, name))")
 
     @property
     def name(self):
@@ -1068,6 +1092,9 @@ class Parloop:
         base = self.iterset.superset if isinstance(self.iterset, Subset) else self.iterset
         if getattr(base, "extruded_periodic", False):
             raise NotImplementedError("periodic extrusion (offset_quotient) runs on the generic wrapper path: "
+                                      "pass the local kernel as C source (op2.Kernel(code, name))")
+        if not getattr(base, "constant_layers", True):
+            raise NotImplementedError("variable layers run on the generic wrapper path: "
                                       "pass the local kernel as C source (op2.Kernel(code, name))")
         lk = self.global_kernel.local_kernel
         if len(self.args) != len(lk.accesses):

@@ -189,6 +189,8 @@ typedef struct fdb_call_args {
     fdb_int start, end;         /* half-open range into the iteration set          */
     const fdb_int *layers;      /* HOST int[2] {bottom, top node layer}, extruded
                                    constant layers (pyop2/types/set.py:336-345);
+                                   variable layers (fdb_wrapper_desc.variable_layers):
+                                   HOST int[layers_count][2], one row per column;
                                    NULL otherwise                                   */
     const fdb_int *subset;      /* subset indices (same location as args) or NULL  */
     int32_t nargs;              /* TSFC argument order: output, coords, coefficients */
@@ -211,6 +213,9 @@ typedef struct fdb_call_args {
                                    Map's address misses the mirror / colouring / pipeline
                                    caches.  NULL = 0 for every map (address-keyed only)      */
     uint64_t subset_version;    /* same for the subset index array                            */
+    fdb_int layers_count;       /* variable layers: rows of `layers` (= columns of the set incl.
+                                   ghosts); 0 for constant layers                              */
+    uint64_t layers_version;    /* generation id of the layers array (mirror key), like map_versions */
 } fdb_call_args;
 
 /* Replaces the ctypes call fn(start, end, *arglist) of
@@ -292,13 +297,17 @@ typedef struct fdb_wrapper_desc {
                                    (pyop2/global_kernel.py:344-346)                           */
     int32_t nargs;              /* local-kernel argument order                                */
     const fdb_wrapper_arg *args;
-    int32_t extruded;           /* iterate layers (constant layers only)                     */
+    int32_t extruded;           /* iterate layers                                            */
     int32_t subset;             /* n = subset[n]                                             */
     int32_t iteration_region;   /* enum fdb_region                                           */
     int32_t pass_layer_arg;     /* extruded: append the current layer (int, by value) to the
                                    local kernel's arguments (pyop2/global_kernel.py:277-279)  */
     int32_t extruded_periodic;  /* the columns are periodic in the extruded direction
                                    (ExtrudedSet(..., extruded_periodic=True), pyop2/types/set.py) */
+    int32_t variable_layers;    /* 1: `layers` is int[ncolumns][2], every column has its own
+                                   [bottom, top) node layers and its map row points at ITS bottom
+                                   cell (constant_layers == False: pyop2/codegen/builder.py:754-812,
+                                   pyop2/types/set.py:336-345)                                  */
 } fdb_wrapper_desc;
 
 /* The generated CUDA source (no GPU needed).  Writes at most `cap` bytes incl.

@@ -27,7 +27,7 @@ class MatView(C.Structure):
 
 class WrapParams(C.Structure):
     _fields_ = [("start", C.c_int), ("end", C.c_int), ("layer_lo", C.c_int), ("layer_hi", C.c_int),
-                ("bottom", C.c_int), ("ncl", C.c_int), ("subset", C.c_void_p),
+                ("bottom", C.c_int), ("ncl", C.c_int), ("subset", C.c_void_p), ("col_layers", C.c_void_p),
                 ("arg", C.c_void_p * 16), ("map", C.c_void_p * 8), ("mat", MatView * 4)]
 
 
@@ -80,6 +80,16 @@ class HostCSR:
         return A
 
 
+def tallest(layers, region):
+    """Layer extent of the launch grid for variable layers (fdb_jit_call)."""
+    cells = layers[:, 1] - 1 - layers[:, 0]
+    if region in ("ON_BOTTOM", "ON_TOP", 1, 2):
+        return int((cells > 0).any())
+    if region in ("ON_INTERIOR_FACETS", 3):
+        return int(max(cells.max() - 1, 0))
+    return int(max(cells.max(), 0))
+
+
 def run(spec, start, end, args, maps, layers=None, subset=None, region="ALL"):
     """Execute the generated wrapper on host arrays.  ``args``: one entry per
     kernel argument -- numpy array (Dat / Global) or HostCSR (Mat); ``maps``: the
@@ -88,7 +98,13 @@ def run(spec, start, end, args, maps, layers=None, subset=None, region="ALL"):
     p = WrapParams()
     p.start, p.end = start, end
     nl = 1
-    if layers is not None:
+    if layers is not None and np.ndim(layers) == 2:
+        lay = np.ascontiguousarray(layers, dtype=np.int32)
+        keep_lay = lay
+        p.col_layers = lay.ctypes.data
+        p.layer_lo, p.layer_hi, p.ncl = 0, tallest(lay, region), 1
+        nl = p.layer_hi
+    elif layers is not None:
         cs, ce = int(layers[0]), int(layers[1]) - 1
         p.bottom = cs
         p.ncl = max(ce - cs, 1)

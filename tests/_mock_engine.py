@@ -358,7 +358,8 @@ class MockEngine:
         args = [(d.args[i].kind, d.args[i].access, d.args[i].dtype, d.args[i].dim) for i in range(d.nargs)]
         self._next += 1
         self.kernels[self._next] = dict(kind="jit", fn=fn, keep=keep, args=args, extruded=d.extruded,
-                                        subset=d.subset, region=d.iteration_region, name=name)
+                                        subset=d.subset, region=d.iteration_region, name=name,
+                                        varlay=d.variable_layers)
         _obj(out).value = self._next
         return 0
 
@@ -380,7 +381,12 @@ class MockEngine:
         p = jh.WrapParams()
         p.start, p.end = a.start, a.end
         nl = 1
-        if k["extruded"]:
+        if k["extruded"] and k["varlay"]:
+            lay = _view(C.cast(a.layers, C.c_void_p).value, 2 * a.layers_count, np.int32).reshape(-1, 2)
+            p.col_layers = lay.ctypes.data
+            p.layer_lo, p.layer_hi, p.ncl = 0, jh.tallest(lay, k["region"]), 1
+            nl = p.layer_hi
+        elif k["extruded"]:
             cs, ce = a.layers[0], a.layers[1] - 1
             p.bottom = cs
             p.ncl = max(ce - cs, 1)

@@ -32,6 +32,7 @@ struct FdbWrapParams {
     int bottom;
     int ncl;
     const int *subset;
+    const int *col_layers;
     void *arg[16];
     const int *map[8];
     FdbMatView mat[4];

@@ -56,6 +56,11 @@ def test_mixed_dat_host_logic(mock):
     tj.test_mixed_dat_parloop_and_vector_operations(mock)
 
 
+@pytest.mark.parametrize("region", ["ALL", "ON_TOP", "ON_INTERIOR_FACETS"])
+def test_variable_layers_host_logic(mock, region):
+    tj.test_variable_layers_on_device(mock, region)
+
+
 def test_periodic_extrusion_host_logic(mock, oracle):
     tj.test_periodic_extrusion_on_device(mock, oracle)
 

@@ -498,3 +498,40 @@ def test_mixed_dat_parloop_and_vector_operations(engine):
     w2 -= w
     w2 *= 0.5
     assert np.abs(w2[0].data_ro - u.data_ro).max() < 1e-14 and np.abs(w2[1].data_ro - p.data_ro).max() < 1e-14
+
+
+@pytest.mark.parametrize("region", ["ALL", "ON_TOP", "ON_INTERIOR_FACETS"])
+def test_variable_layers_on_device(engine, region):
+    """Variable layers through op2.par_loop, device-resident and host-pointer mode, against the
+    NumPy loop of tests/test_codegen.py::test_variable_layers at a size with uneven columns."""
+    from firedrake_b200 import codegen
+    lay, colstart, nnode = tc._variable_columns(seed=3, ncol=700)
+    ncol = len(lay)
+    cols = op2.ExtrudedSet(op2.Set(ncol), lay)
+    nodes = op2.Set(nnode)
+    m = op2.Map(cols, nodes, 2, colstart[:, None] + np.array([0, 1])[None, :], offset=[1, 1])
+    xh = np.random.default_rng(0).standard_normal(nnode)
+    x, y = op2.Dat(nodes, xh), op2.Dat(nodes)
+    if region == "ON_INTERIOR_FACETS":
+        k = op2.Kernel("static void k(double *y, const double *x, int layer) { for (int i = 0; i < 4; ++i) "
+                       "y[i] += (i + 1) * x[3 - i] + layer; }", "k")
+    else:
+        k = op2.Kernel("static void k(double *y, const double *x, int layer) "
+                       "{ y[0] += 2.0*x[0] + x[1] + layer; y[1] += x[0] - 3.0*x[1]; }", "k")
+    ref = np.zeros(nnode)
+    for c in range(ncol):
+        cs, ce = lay[c, 0], lay[c, 1] - 1
+        lo, hi = {"ALL": (cs, ce), "ON_TOP": (max(ce - 1, cs), ce), "ON_INTERIOR_FACETS": (cs, ce - 1)}[region]
+        for l in range(lo, hi):
+            b = colstart[c] + (l - cs)
+            if region == "ON_INTERIOR_FACETS":
+                idx = np.array([b, b + 1, b + 1, b + 2])
+                np.add.at(ref, idx, np.array([(i + 1) * xh[idx[3 - i]] + l for i in range(4)]))
+            else:
+                ref[b] += 2 * xh[b] + xh[b + 1] + l
+                ref[b + 1] += xh[b] - 3 * xh[b + 1]
+    for location in ("device", "host"):
+        y.zero()
+        codegen.par_loop(k, cols, y(op2.INC, m), x(op2.READ, m), iteration_region=region, pass_layer_arg=True,
+                         location=location)
+        assert np.abs(y.data_ro - ref).max() < 1e-12
