@@ -185,6 +185,22 @@ struct Tile {
 #ifndef FDB_WARPS
 #define FDB_WARPS 4
 #endif
+// timing-only experiment switches (tools/build_variant.sh; results are garbage, never shipped)
+#ifdef FDB_EXP_NOGATHER
+constexpr bool EXP_NOGATHER = true;
+#else
+constexpr bool EXP_NOGATHER = false;
+#endif
+#if defined(FDB_EXP_NOSCATTER) || defined(FDB_EXP_NOGATHER)
+constexpr bool EXP_NOSCATTER = true;
+#else
+constexpr bool EXP_NOSCATTER = false;
+#endif
+#ifdef FDB_EXP_NOCOMPUTE
+constexpr bool EXP_NOCOMPUTE = true;
+#else
+constexpr bool EXP_NOCOMPUTE = false;
+#endif
 // warps per CTA: 4 everywhere except degree 5 (N = 6), whose per-warp staging is 38 KB:
 // one CTA of 5 warps fills the 227 KB of shared memory better than one of 4
 template <int N, bool SLIM = false>
@@ -369,6 +385,7 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
     // s_coord are shared by the N lanes of a cell and are read after the
     // wait + __syncwarp at the top of the loop.
     auto stageA = [&](const Unit &u) {
+        if (EXP_NOGATHER) return;
         if (u.valid && u.comp == 0 && u.lead) {
             const int *mrow = P.map0 + (long long)u.col * ND;
             int *sm = row_of(u);
@@ -384,6 +401,7 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
         }
     };
     auto stageB_coords = [&](const Unit &u) {
+        if (EXP_NOGATHER) return;
         if (u.valid && u.comp == 0) {
             const int *sv = vrow_of(u);
             double *scd = s_coord + cw * CS;
@@ -395,6 +413,7 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
         }
     };
     auto stageB_part = [&](const Unit &u, int ubuf, int part) {
+        if (EXP_NOGATHER) return;
         if (u.valid) {
             double *su = s_u + cw * US;
             int *si = s_idx + (u.ib * CWS + cw) * US;
@@ -509,8 +528,10 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
                     if (MATRIX) u[x][yy] = ((x * N + yy) * N + t == comp) ? 1.0 : 0.0;
                     else u[x][yy] = valid ? su[(x * N + yy) * N + t] : 0.0;
                 }
-            // ---- forward: interpolate to the quadrature points
             double tmp[N][N], U[N][N];
+            double Vp[N][N];
+            if (!EXP_NOCOMPUTE) {
+            // ---- forward: interpolate to the quadrature points
             apply_first<N, false>(P.B, u, tmp);          // a_x -> q_x
             apply_second<N, false>(P.B, tmp, u);         // a_y -> q_y     u = w[qx][qy] @ a_z
             __syncwarp();
@@ -532,7 +553,6 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
 
             // ---- quadrature points (layout Y), fused with the x/z derivative
             //      and its transpose so only U, Gy and Vp stay live
-            double Vp[N][N];
 #pragma unroll
             for (int i = 0; i < N; i++)
 #pragma unroll
@@ -640,10 +660,16 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
                 }
             }
 
+            } else {
+                stageB_coords(nxt);
+#pragma unroll
+                for (int part = 0; part < N; part++) stageB_part(nxt, ubuf ^ 1, part);
+            }
             __syncwarp();            // all lanes are done reading the staged rows of `nxt`
             stageA(nn);
             cp_async_commit();
 
+            if (!EXP_NOCOMPUTE) {
             // ---- backward (the tile holds Fy[qx][qz] @ q_y)
             __syncwarp();
             tile.load_Z(tmp);                            // Fy[qx][qy] @ q_z
@@ -664,6 +690,7 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
             apply_first<N, true>(P.B, u, tmp);           // q_x -> a_x
             apply_second<N, true>(P.B, tmp, u);          // q_y -> a_y     R[ax][ay] @ a_z
 
+            }
             // ---- scatter-add, layout Z
             if (MATRIX && P.vals == nullptr) {
                 // diagonal of the bilinear form: only the entry i == j of column j
@@ -707,7 +734,7 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
                             else P.vals[lo] += u[x][yy];
                         }
                 }
-            } else if (valid) {
+            } else if (valid && (!EXP_NOSCATTER || P.alpha == 12345.678)) {
                 const int *smc = row_of(cur);
 #pragma unroll
                 for (int x = 0; x < N; x++)
@@ -727,6 +754,8 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
     }
     cp_async_wait<0>();
 }
+
+#include "action_hex_ws.cuh"
 
 template <int N, bool MASS, bool ATOMIC, int MINB, bool MATRIX = false, bool SLIM = false, bool AFFINE = false>
 int launch_one(int grid_cap_per_sm, cudaStream_t st, HelmParams<N> &P, int sm_count)
@@ -850,6 +879,17 @@ int launch_n(fdb_kernel_s *k, fdb_int start, fdb_int end, int nlay, const fdb_in
         P.lay_first = 0;
         P.lay_step = 1;
         if (P.ncols <= 0 || nlay <= 0) return 0;
+        if constexpr (N == 4) {
+            // degree 3, scalar: warp-specialised kernel (action_hex_ws.cuh)
+            static const int ws = getenv("FDB_WS") ? atoi(getenv("FDB_WS")) : 0;
+            if (ws && P.cdim == 1 && nlay >= 8 && !k->desc.affine_cells) {
+                if (ws == 2)    // 8 compute warps x 232 registers, 3 stages
+                    return mass ? launch_ws<true, 8, 3>(c.stream, P, c.sm_count)
+                                : launch_ws<false, 8, 3>(c.stream, P, c.sm_count);
+                return mass ? launch_ws<true, 12, 2>(c.stream, P, c.sm_count)
+                            : launch_ws<false, 12, 2>(c.stream, P, c.sm_count);
+            }
+        }
         return launch_variant<N, true>(mass, minb, cap, c.stream, P, c.sm_count, k->desc.affine_cells != 0);
     }
     // deterministic: one launch per (colour, layer parity); within a launch no
