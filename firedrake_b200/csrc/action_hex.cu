@@ -67,6 +67,7 @@ struct HelmParams {
     const unsigned short *rank_tab;   // within-row positions per (column, layer class, j, i) or NULL
     int nvar, nlay_total;
     int chunk;               // items per work chunk
+    int ws_flags;            // warp-specialised kernel: timing probes (0 in production)
     int *counter;            // device work counter (zeroed before the launch)
     double alpha, beta;
     double B[N * N];         // B[q][a]
@@ -80,11 +81,11 @@ __device__ __forceinline__ double fast_rcp(double x)
 {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double e = fma(-x, r, 1.0);
-    r = fma(e, r, r);
-    e = fma(-x, r, 1.0);
-    r = fma(e, r, r);
-    return r;
+    // one third-order step r (1 + e + e^2), e = 1 - x r: |e| <= 2^-20 after MUFU.RCP64H -> 2^-60;
+    // three dependent FMAs (two Newton steps are four)
+    const double e = fma(-x, r, 1.0);
+    const double t = fma(e, e, e);
+    return fma(r, t, r);
 }
 
 // out[i][j] = sum_k M(i,k) in[k][j];  M(i,k) = T ? M[k*N+i] : M[i*N+k]
@@ -185,21 +186,13 @@ struct Tile {
 #ifndef FDB_WARPS
 #define FDB_WARPS 4
 #endif
-// timing-only experiment switches (tools/build_variant.sh; results are garbage, never shipped)
-#ifdef FDB_EXP_NOGATHER
-constexpr bool EXP_NOGATHER = true;
+// degree 3: the geometry coefficients that are needed once per zeta plane only (c2, c4, c5, c7 of the
+// cell, A1 of the lane) are parked in shared memory: 30 registers less in the quadrature loop
+// (9.75 -> 9.62 ms at 256^3, profiles/r02_action_variants.txt); -DFDB_NO_STASH builds without
+#ifdef FDB_NO_STASH
+constexpr bool OPT_STASH = false;
 #else
-constexpr bool EXP_NOGATHER = false;
-#endif
-#if defined(FDB_EXP_NOSCATTER) || defined(FDB_EXP_NOGATHER)
-constexpr bool EXP_NOSCATTER = true;
-#else
-constexpr bool EXP_NOSCATTER = false;
-#endif
-#ifdef FDB_EXP_NOCOMPUTE
-constexpr bool EXP_NOCOMPUTE = true;
-#else
-constexpr bool EXP_NOCOMPUTE = false;
+constexpr bool OPT_STASH = true;
 #endif
 // warps per CTA: 4 everywhere except degree 5 (N = 6), whose per-warp staging is 38 KB:
 // one CTA of 5 warps fills the 227 KB of shared memory better than one of 4
@@ -250,10 +243,12 @@ struct WarpSmem {
     static constexpr int TILE = CWS * Tile<N>::STRIDE;         // doubles
     static constexpr int UBUF = CWS * US;                      // doubles: gathered values (single buffer)
     static constexpr int COORD = CWS * CS;                     // doubles: vertex coordinates (single buffer)
+    static constexpr int GS = 28;                              // stash stride: c2 c4 c5 c7 (12) + A1 of 4 lanes (4 apart)
+    static constexpr int STASH = (OPT_STASH && N == 4 && !SLIM) ? CWS * GS : 0;   // doubles
     static constexpr int IDX = SLIM ? 0 : 2 * CWS * US;        // ints: global dof index per local dof
     static constexpr int MAPRAW = SLIM ? 3 * 2 * US : CWS * US;   // ints: bottom-cell map row(s)
     static constexpr int VIDX = SLIM ? 3 * 2 * 8 : 2 * CWS * 8;   // ints: bottom-cell vertex row(s)
-    static constexpr int BYTES = (((TILE + UBUF + COORD) * 8 + (IDX + MAPRAW + VIDX) * 4) + 15) / 16 * 16;
+    static constexpr int BYTES = (((TILE + UBUF + COORD + STASH) * 8 + (IDX + MAPRAW + VIDX) * 4) + 15) / 16 * 16;
     static constexpr int CTA_BYTES = WPC<N, SLIM>::value * BYTES + ND * 4 + 32;
 };
 
@@ -291,7 +286,9 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
     double *s_tile = wbase;
     double *s_u = s_tile + WS::TILE;                 // [CWS][US]   (single buffer)
     double *s_coord = s_u + WS::UBUF;                // [CWS][CS]   (single buffer)
-    int *s_idx = reinterpret_cast<int *>(s_coord + WS::COORD);   // [2][CWS][US]  (empty if SLIM)
+    double *s_stash = s_coord + WS::COORD;           // [CWS][GS]   (geometry coefficients, if STASH)
+    constexpr bool STASH = WS::STASH > 0 && !MATRIX && !AFFINE;
+    int *s_idx = reinterpret_cast<int *>(s_stash + WS::STASH);   // [2][CWS][US]  (empty if SLIM)
     int *s_mapraw = s_idx + WS::IDX;                 // [CWS][US], or [3][2][US] if SLIM
     int *s_vidx = s_mapraw + WS::MAPRAW;             // [2][CWS][8], or [3][2][8] if SLIM
     int *s_off0 = reinterpret_cast<int *>(smem_raw + (size_t)WPC<N, SLIM>::value * WS::BYTES);
@@ -385,7 +382,6 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
     // s_coord are shared by the N lanes of a cell and are read after the
     // wait + __syncwarp at the top of the loop.
     auto stageA = [&](const Unit &u) {
-        if (EXP_NOGATHER) return;
         if (u.valid && u.comp == 0 && u.lead) {
             const int *mrow = P.map0 + (long long)u.col * ND;
             int *sm = row_of(u);
@@ -401,7 +397,6 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
         }
     };
     auto stageB_coords = [&](const Unit &u) {
-        if (EXP_NOGATHER) return;
         if (u.valid && u.comp == 0) {
             const int *sv = vrow_of(u);
             double *scd = s_coord + cw * CS;
@@ -413,7 +408,6 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
         }
     };
     auto stageB_part = [&](const Unit &u, int ubuf, int part) {
-        if (EXP_NOGATHER) return;
         if (u.valid) {
             double *su = s_u + cw * US;
             int *si = s_idx + (u.ib * CWS + cw) * US;
@@ -515,6 +509,24 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
                 Gm[5] = rd * (r2[0] * r2[0] + r2[1] * r2[1] + r2[2] * r2[2]);
             }
         }
+        if (STASH && cur.comp == 0) {
+            // c2, c4, c5, c7 (cell) and A1 (lane) are needed once per zeta plane only: park them in
+            // shared memory and free 30 registers for the quadrature loop
+            double *sg = s_stash + cw * WS::GS;
+            if (t == 0) {
+                double2 *d = reinterpret_cast<double2 *>(sg);
+                d[0] = make_double2(c2[0], c2[1]);
+                d[1] = make_double2(c2[2], c4[0]);
+                d[2] = make_double2(c4[1], c4[2]);
+                d[3] = make_double2(c5[0], c5[1]);
+                d[4] = make_double2(c5[2], c7[0]);
+                d[5] = make_double2(c7[1], c7[2]);
+            }
+            double2 *d = reinterpret_cast<double2 *>(sg + 12 + 4 * t);
+            d[0] = make_double2(A1[0], A1[1]);
+            sg[12 + 4 * t + 2] = A1[2];
+            __syncwarp();
+        }
         const int comp = cur.comp;
         const int *si = s_idx + (cbuf * CWS + cw) * US;
         {
@@ -530,7 +542,6 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
                 }
             double tmp[N][N], U[N][N];
             double Vp[N][N];
-            if (!EXP_NOCOMPUTE) {
             // ---- forward: interpolate to the quadrature points
             apply_first<N, false>(P.B, u, tmp);          // a_x -> q_x
             apply_second<N, false>(P.B, tmp, u);         // a_y -> q_y     u = w[qx][qy] @ a_z
@@ -575,7 +586,22 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
 #pragma unroll
                 for (int j = 0; j < N; j++) dz[j] = P.DtR[qz * N + j];
                 double ca[3], pb[3], qb[3];
-                if (!AFFINE) {
+                if (STASH) {
+                    const double *sg = s_stash + cw * WS::GS;
+                    const double2 *d = reinterpret_cast<const double2 *>(sg);
+                    const double2 g0 = d[0], g1 = d[1], g2 = d[2], g3 = d[3], g4 = d[4], g5 = d[5];
+                    const double2 a01 = *reinterpret_cast<const double2 *>(sg + 12 + 4 * t);
+                    const double a2 = sg[12 + 4 * t + 2];
+                    pb[0] = fma(g3.x, zeta, g0.x);     // c5 zeta + c2
+                    pb[1] = fma(g3.y, zeta, g0.y);
+                    pb[2] = fma(g4.x, zeta, g1.x);
+                    qb[0] = fma(g4.y, zeta, g1.y);     // c7 zeta + c4
+                    qb[1] = fma(g5.x, zeta, g2.x);
+                    qb[2] = fma(g5.y, zeta, g2.y);
+                    ca[0] = fma(A6[0], zeta, a01.x);   // dx/dxi
+                    ca[1] = fma(A6[1], zeta, a01.y);
+                    ca[2] = fma(A6[2], zeta, a2);
+                } else if (!AFFINE) {
 #pragma unroll
                     for (int a = 0; a < 3; a++) {
                         ca[a] = fma(A6[a], zeta, A1[a]);       // dx/dxi
@@ -660,16 +686,10 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
                 }
             }
 
-            } else {
-                stageB_coords(nxt);
-#pragma unroll
-                for (int part = 0; part < N; part++) stageB_part(nxt, ubuf ^ 1, part);
-            }
             __syncwarp();            // all lanes are done reading the staged rows of `nxt`
             stageA(nn);
             cp_async_commit();
 
-            if (!EXP_NOCOMPUTE) {
             // ---- backward (the tile holds Fy[qx][qz] @ q_y)
             __syncwarp();
             tile.load_Z(tmp);                            // Fy[qx][qy] @ q_z
@@ -690,7 +710,6 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
             apply_first<N, true>(P.B, u, tmp);           // q_x -> a_x
             apply_second<N, true>(P.B, tmp, u);          // q_y -> a_y     R[ax][ay] @ a_z
 
-            }
             // ---- scatter-add, layout Z
             if (MATRIX && P.vals == nullptr) {
                 // diagonal of the bilinear form: only the entry i == j of column j
@@ -734,7 +753,7 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
                             else P.vals[lo] += u[x][yy];
                         }
                 }
-            } else if (valid && (!EXP_NOSCATTER || P.alpha == 12345.678)) {
+            } else if (valid) {
                 const int *smc = row_of(cur);
 #pragma unroll
                 for (int x = 0; x < N; x++)
@@ -883,11 +902,15 @@ int launch_n(fdb_kernel_s *k, fdb_int start, fdb_int end, int nlay, const fdb_in
             // degree 3, scalar: warp-specialised kernel (action_hex_ws.cuh)
             static const int ws = getenv("FDB_WS") ? atoi(getenv("FDB_WS")) : 0;
             if (ws && P.cdim == 1 && nlay >= 8 && !k->desc.affine_cells) {
-                if (ws == 2)    // 8 compute warps x 232 registers, 3 stages
-                    return mass ? launch_ws<true, 8, 3>(c.stream, P, c.sm_count)
-                                : launch_ws<false, 8, 3>(c.stream, P, c.sm_count);
-                return mass ? launch_ws<true, 12, 2>(c.stream, P, c.sm_count)
-                            : launch_ws<false, 12, 2>(c.stream, P, c.sm_count);
+#define FDB_WS_CASE(id, NC, NM, NS, ST)                                                            \
+    if (ws == id)                                                                              \
+        return mass ? launch_ws<true, NC, NM, NS, ST>(c.stream, P, c.sm_count)                 \
+                    : launch_ws<false, NC, NM, NS, ST>(c.stream, P, c.sm_count);
+                FDB_WS_CASE(1, 12, 4, 2, true)     // 12 compute warps x 160 registers, 4 movers x 32, 2 stages
+                FDB_WS_CASE(2, 8, 4, 3, true)      // 8 x 224, 4 movers x 56, 3 stages
+                FDB_WS_CASE(3, 8, 4, 3, false)     // ... geometry coefficients kept in registers
+                FDB_WS_CASE(4, 8, 8, 3, false)     // 8 x 208, one mover (48) per compute warp
+#undef FDB_WS_CASE
             }
         }
         return launch_variant<N, true>(mass, minb, cap, c.stream, P, c.sm_count, k->desc.affine_cells != 0);

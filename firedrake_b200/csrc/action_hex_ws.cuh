@@ -48,19 +48,19 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
     }
 }
 
-template <int NCOMP_, int NSTAGE_>
+template <int NCOMP_, int NMOVE_, int NSTAGE_>
 struct WsLayout {
     static constexpr int N = 4, ND = 64, CW = 8;
     static constexpr int US = 68;                      // cell stride of the value buffer (doubles)
     static constexpr int CS = 28;                      // cell stride of the coordinate buffer (24 + 4 used, see GEO)
-    static constexpr int NCOMP = NCOMP_, NMOVE = 4, NSTAGE = NSTAGE_;
+    static constexpr int NCOMP = NCOMP_, NMOVE = NMOVE_, NSTAGE = NSTAGE_;
     static constexpr int CPM = NCOMP / NMOVE;          // compute warps served by one mover
     static constexpr int THREADS = (NCOMP + NMOVE) * 32;
     // register split (setmaxnreg, per thread): NCOMP / 4 compute warpgroups + one mover warpgroup share 64 K
     // (the pool is what the CTA is LAUNCHED with: 512 x 128 or 384 x 168 registers -- launch_ws checks it)
-    static constexpr int REG_LAUNCH = NCOMP == 12 ? 128 : 168;
-    static constexpr int REG_COMPUTE = NCOMP == 12 ? 160 : 224;
-    static constexpr int REG_MOVER = NCOMP == 12 ? 32 : 56;
+    static constexpr int REG_LAUNCH = (65536 / THREADS) / 8 * 8;          // 512 threads: 128, 384 threads: 168
+    static constexpr int REG_COMPUTE = NCOMP == 12 ? 160 : (NMOVE == 8 ? 208 : 224);
+    static constexpr int REG_MOVER = NCOMP == 12 ? 32 : (NMOVE == 8 ? 48 : 56);
     // per stage (bytes)
     static constexpr int XBUF = CW * US * 8;           // 4352
     static constexpr int COORD = CW * CS * 8;          // 1664
@@ -76,13 +76,14 @@ struct WsLayout {
     static constexpr int BYTES = BARS + NCOMP * NSTAGE * 2 * 8;
 };
 
-template <bool MASS, int NCOMP, int NSTAGE>
-__global__ void __launch_bounds__((NCOMP + 4) * 32, 1)
+template <bool MASS, int NCOMP, int NMOVE, int NSTAGE, bool STASH>
+__global__ void __launch_bounds__((NCOMP + NMOVE) * 32, 1)
 helmholtz_action_ws_kernel(const __grid_constant__ HelmParams<4> P)
 {
     constexpr int N = 4;
-    using L = WsLayout<NCOMP, NSTAGE>;
-    static_assert(NCOMP % 4 == 0 && (NCOMP / 4) * L::REG_COMPUTE + L::REG_MOVER <= (NCOMP / 4 + 1) * L::REG_LAUNCH,
+    using L = WsLayout<NCOMP, NMOVE, NSTAGE>;
+    static_assert(NCOMP % 4 == 0 && NMOVE % 4 == 0 && NCOMP % NMOVE == 0, "whole warpgroups per role");
+    static_assert(NCOMP * L::REG_COMPUTE + NMOVE * L::REG_MOVER <= (NCOMP + NMOVE) * L::REG_LAUNCH,
                   "register split exceeds the pool the CTA is launched with");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -105,17 +106,18 @@ helmholtz_action_ws_kernel(const __grid_constant__ HelmParams<4> P)
         // =========================================================== mover
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(L::REG_MOVER));
         const int m = warp - L::NCOMP;
+        const bool probe_nomove = P.ws_flags & 2;      // timing probe: signal only, no gather / scatter traffic
         const int ncells = P.ncols * P.nlay_items;
         const int nitems = (ncells + L::CW - 1) / L::CW;
         int cur = 0, end = 0;
         bool drained = false;
         unsigned alive = 0;
 
-        // slot visited at step k: compute warp m + 4 (k % CPM), stage (k / CPM) % NSTAGE, fill number
+        // slot visited at step k: compute warp m + NMOVE (k % CPM), stage (k / CPM) % NSTAGE, fill number
         // k / (CPM NSTAGE)
         constexpr int CPM = L::CPM, NSLOT = L::CPM * NSTAGE;
         auto stage_of = [&](int k) -> unsigned char * {
-            return smem_raw + (m + 4 * (k % CPM)) * L::WARP + L::TILE + ((k / CPM) % NSTAGE) * L::STAGE;
+            return smem_raw + (m + NMOVE * (k % CPM)) * L::WARP + L::TILE + ((k / CPM) % NSTAGE) * L::STAGE;
         };
         // Claim the unit that step k will gather, decode it and start the copy of its map rows
         // (at most two distinct columns per unit) into the row set the stage is not scattering from.
@@ -179,7 +181,7 @@ helmholtz_action_ws_kernel(const __grid_constant__ HelmParams<4> P)
             const int cl = k % CPM, s = (k / CPM) % NSTAGE, f = k / NSLOT;
             const int slot = k % NSLOT;
             const bool active = f == 0 || ((alive >> slot) & 1u);
-            const int c = m + 4 * cl;
+            const int c = m + NMOVE * cl;
             unsigned char *stage = stage_of(k);
             double *xbuf = reinterpret_cast<double *>(stage);
             double *cbuf = reinterpret_cast<double *>(stage + L::XBUF);
@@ -198,11 +200,11 @@ helmholtz_action_ws_kernel(const __grid_constant__ HelmParams<4> P)
             if (active && f > 0) {
                 mbar_wait(empty, (unsigned)(f - 1) & 1u);
                 const unsigned oinfo = laneinfo[lane];
-                if (oinfo >> 31) {
+                if ((oinfo >> 31) && !probe_nomove) {
                     const int olayer = (int)(oinfo & 0x3fffffffu);
                     const int *sm = rows_old + ((oinfo >> 30) & 1u) * L::ND;
                     const double *xr = xbuf + cw * L::US;
-#pragma unroll 2
+#pragma unroll(L::REG_MOVER >= 48 ? 4 : 2)
                     for (int j = 0; j < 16; j++) {
                         const int loc = j * 4 + t;
                         const int g = sm[loc] + s_off0[loc] * olayer;
@@ -217,7 +219,7 @@ helmholtz_action_ws_kernel(const __grid_constant__ HelmParams<4> P)
             // ---- gather the new unit (or tell the compute warp that the queue is empty)
             if (active) {
                 if (item >= 0) {
-                    if (info >> 31) {
+                    if ((info >> 31) && !probe_nomove) {
                         const int layer = (int)(info & 0x3fffffffu);
                         const int src = (int)((info >> 30) & 1u);
                         const int *sv = rows_new + 2 * L::ND + src * 8;
@@ -230,7 +232,7 @@ helmholtz_action_ws_kernel(const __grid_constant__ HelmParams<4> P)
                         }
                         const int *sm = rows_new + src * L::ND;
                         double *xr = xbuf + cw * L::US;
-#pragma unroll 2
+#pragma unroll(L::REG_MOVER >= 48 ? 4 : 2)
                         for (int j = 0; j < 16; j++) {
                             const int loc = j * 4 + t;
                             const int g = sm[loc] + s_off0[loc] * layer;
@@ -270,6 +272,7 @@ helmholtz_action_ws_kernel(const __grid_constant__ HelmParams<4> P)
         const double wy_beta = P.wq[t] * P.beta;
         int s = 0;
         unsigned par = 0;
+#pragma unroll 1
         for (;; s = (s + 1 == NSTAGE) ? 0 : s + 1, par ^= (s == 0)) {
             unsigned char *stage = wbase + L::TILE + s * L::STAGE;
             double *xbuf = reinterpret_cast<double *>(stage);
@@ -280,32 +283,32 @@ helmholtz_action_ws_kernel(const __grid_constant__ HelmParams<4> P)
             if (meta[0] < 0) break;
             const bool valid = cw < meta[1];
 
-            // trilinear coefficients reduced at this lane's eta.  Only A3 / A6 (used at every point)
-            // stay in registers; c2, c4, c5, c7 (cell) and A1 (lane) are needed once per zeta plane and
-            // go back into the cell's slot of the coordinate buffer: [c2 c4 c5 c7 | A1 of lanes 0..3, 4 apart]
-            double A3[3], A6[3];
-            {
-                double A1[3], c2[3], c4[3], c5[3], c7[3];
+            // trilinear coefficients reduced at this lane's eta.  STASH (the 160-register split): only
+            // A3 / A6 (used at every point) stay in registers; c2, c4, c5, c7 (cell) and A1 (lane) are needed
+            // once per zeta plane and go back into the cell's slot of the coordinate buffer:
+            // [c2 c4 c5 c7 | A1 of lanes 0..3, 4 apart]
+            double A1[3], A3[3], A6[3], c2[3], c4[3], c5[3], c7[3];
 #pragma unroll
-                for (int a = 0; a < 3; a++) {
-                    double X000 = sc[0 * 3 + a], X001 = sc[1 * 3 + a], X010 = sc[2 * 3 + a],
-                           X011 = sc[3 * 3 + a], X100 = sc[4 * 3 + a], X101 = sc[5 * 3 + a],
-                           X110 = sc[6 * 3 + a], X111 = sc[7 * 3 + a];
-                    if (!valid) {   // keep idle lanes finite: unit cube
-                        X000 = 0; X001 = (a == 2); X010 = (a == 1); X011 = (a >= 1);
-                        X100 = (a == 0); X101 = (a != 1); X110 = (a != 2); X111 = 1;
-                    }
-                    const double c1 = X100 - X000;
-                    c2[a] = X010 - X000;
-                    const double c3 = X001 - X000;
-                    c4[a] = X110 - X100 - X010 + X000;
-                    c5[a] = X011 - X010 - X001 + X000;
-                    const double c6 = X101 - X100 - X001 + X000;
-                    c7[a] = X111 - X110 - X101 - X011 + X100 + X010 + X001 - X000;
-                    A1[a] = fma(c4[a], eta, c1);
-                    A3[a] = fma(c5[a], eta, c3);
-                    A6[a] = fma(c7[a], eta, c6);
+            for (int a = 0; a < 3; a++) {
+                double X000 = sc[0 * 3 + a], X001 = sc[1 * 3 + a], X010 = sc[2 * 3 + a],
+                       X011 = sc[3 * 3 + a], X100 = sc[4 * 3 + a], X101 = sc[5 * 3 + a],
+                       X110 = sc[6 * 3 + a], X111 = sc[7 * 3 + a];
+                if (!valid) {   // keep idle lanes finite: unit cube
+                    X000 = 0; X001 = (a == 2); X010 = (a == 1); X011 = (a >= 1);
+                    X100 = (a == 0); X101 = (a != 1); X110 = (a != 2); X111 = 1;
                 }
+                const double c1 = X100 - X000;
+                c2[a] = X010 - X000;
+                const double c3 = X001 - X000;
+                c4[a] = X110 - X100 - X010 + X000;
+                c5[a] = X011 - X010 - X001 + X000;
+                const double c6 = X101 - X100 - X001 + X000;
+                c7[a] = X111 - X110 - X101 - X011 + X100 + X010 + X001 - X000;
+                A1[a] = fma(c4[a], eta, c1);
+                A3[a] = fma(c5[a], eta, c3);
+                A6[a] = fma(c7[a], eta, c6);
+            }
+            if (STASH) {
                 __syncwarp();      // every lane of the cell has read the vertex coordinates
                 if (t == 0) {
                     double2 *d = reinterpret_cast<double2 *>(sc);
@@ -328,6 +331,7 @@ helmholtz_action_ws_kernel(const __grid_constant__ HelmParams<4> P)
 #pragma unroll
                 for (int yy = 0; yy < N; yy++) u[x][yy] = valid ? su[(x * N + yy) * N + t] : 0.0;
 
+            if (!(P.ws_flags & 1)) {       // (timing probe 1: skip the element arithmetic)
             double tmp[N][N], U[N][N], Vp[N][N];
             apply_first<N, false>(P.B, u, tmp);
             apply_second<N, false>(P.B, tmp, u);
@@ -355,7 +359,14 @@ helmholtz_action_ws_kernel(const __grid_constant__ HelmParams<4> P)
 #pragma unroll
                 for (int j = 0; j < N; j++) dz[j] = P.DtR[qz * N + j];
                 double ca[3], pb[3], qb[3];
-                {
+                if (!STASH) {
+#pragma unroll
+                    for (int a = 0; a < 3; a++) {
+                        ca[a] = fma(A6[a], zeta, A1[a]);
+                        pb[a] = fma(c5[a], zeta, c2[a]);
+                        qb[a] = fma(c7[a], zeta, c4[a]);
+                    }
+                } else {
                     const double2 *d = reinterpret_cast<const double2 *>(sc);
                     const double2 g0 = d[0], g1 = d[1], g2 = d[2], g3 = d[3], g4 = d[4], g5 = d[5];
                     const double2 a01 = *reinterpret_cast<const double2 *>(sc + 12 + 4 * t);
@@ -446,6 +457,7 @@ helmholtz_action_ws_kernel(const __grid_constant__ HelmParams<4> P)
             tile.load_Z(u);
             apply_first<N, true>(P.B, u, tmp);
             apply_second<N, true>(P.B, tmp, u);
+            }
             // element vector -> stage buffer (layout Z, the positions the values were read from)
 #pragma unroll
             for (int x = 0; x < N; x++)
@@ -457,11 +469,13 @@ helmholtz_action_ws_kernel(const __grid_constant__ HelmParams<4> P)
     }
 }
 
-template <bool MASS, int NCOMP, int NSTAGE>
+template <bool MASS, int NCOMP, int NMOVE, int NSTAGE, bool STASH>
 int launch_ws(cudaStream_t st, HelmParams<4> &P, int sm_count)
 {
-    using L = WsLayout<NCOMP, NSTAGE>;
-    auto kern = helmholtz_action_ws_kernel<MASS, NCOMP, NSTAGE>;
+    using L = WsLayout<NCOMP, NMOVE, NSTAGE>;
+    auto kern = helmholtz_action_ws_kernel<MASS, NCOMP, NMOVE, NSTAGE, STASH>;
+    static const int probe = getenv("FDB_WS_PROBE") ? atoi(getenv("FDB_WS_PROBE")) : 0;
+    P.ws_flags = probe;
     static bool configured = false;
     if (!configured) {
         // setmaxnreg.inc blocks until the CTA's pool has the registers: the pool is threads x the register
