@@ -475,7 +475,7 @@ def main():
     roofline = {"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
                 "traffic": traffic, "kernel": kname, "kernel_ms": kernel_ms,
                 "flop_per_cell": flop_cell,
-                "flop_source": "SASS count (profiles/kernel_counts.json, profiles/r02_action_cg3.sass)" if counts
+                "flop_source": "SASS count (profiles/kernel_counts.json, profiles/r02_action_cg3.sass, tools/sass_loops.py)" if counts
                                else "model 24 n^4 + 130 n^3 (kernel instance not counted)",
                 "peak_source": f"{sm_count} SMs x 64 fp64 FMA lanes/clk x 2 x {clk_hz / 1e9:.3f} GHz (clocks.sm_max_mhz); "
                                "microbenchmark: 37.1 TFLOP/s (profiles/r01_microbench_fp64.txt)",
@@ -488,6 +488,12 @@ def main():
     if counts:
         # share of the fp64 pipe's issue slots actually used (2 cycles per warp instruction per SMSP)
         roofline["fp64_pipe_frac"] = (counts["fp64_instr_per_cell"] * ncell_rank / (sm_count * 64 * clk_hz)) / (kernel_ms * 1e-3)
+        if "three_register_fp64_per_warp_unit" in counts:
+            # a DFMA with three distinct register sources needs a third register-read cycle (measured:
+            # profiles/r02_microbench_issue.txt, 3.05 cycles per DFMA against 2.0): pipe time the kernel cannot avoid
+            cyc_unit = 2.0 * counts["fp64_instr_per_warp_unit"] + counts["three_register_fp64_per_warp_unit"]
+            units = ncell_rank / counts["cells_per_warp_unit"]
+            roofline["fp64_pipe_frac_with_operand_reads"] = (cyc_unit * units / (sm_count * 4 * clk_hz)) / (kernel_ms * 1e-3)
 
     e2e = None
     if not args.no_e2e:

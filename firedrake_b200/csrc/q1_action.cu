@@ -40,11 +40,10 @@ __device__ __forceinline__ double rcp_nr(double x)
 {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double e = fma(-x, r, 1.0);
-    r = fma(e, r, r);
-    e = fma(-x, r, 1.0);
-    r = fma(e, r, r);
-    return r;
+    // one third-order step r (1 + e + e^2), e = 1 - x r (|e| <= 2^-20 -> 2^-60): 3 dependent FMAs, not 4
+    const double e = fma(-x, r, 1.0);
+    const double t = fma(e, e, e);
+    return fma(r, t, r);
 }
 
 // out[i][j][k] = sum_s M[i*2+s] in[s][j][k]   (AX = 0),  ... along y (AX = 1), z (AX = 2);

@@ -147,6 +147,34 @@ def test_vector_space_aos(engine, oracle):
     assert relerr(y.data_ro, yo) < TOL
 
 
+@pytest.mark.parametrize("cdim", [2, 3])
+def test_vector_space_degree3(engine, oracle, cdim):
+    """Degree 3 with several components per node: the geometry coefficients parked in shared memory
+    at component 0 serve the later components of the same cells (action_hex.cu, STASH)."""
+    p = 3
+    mesh = ExtrudedHexMesh(3, 4, 11, warp=0.05, permute_seed=2)
+    V, cells, m0, m1, x, y, X = build(mesh, p, cdim=cdim)
+    k = op2.Kernel("helmholtz", degree=p, alpha=1.0, beta=0.5, cdim=cdim)
+    op2.par_loop(k, cells, y(op2.INC, m0), X(op2.READ, m1), x(op2.READ, m0))
+    yo = oracle_action(oracle, mesh, V, p, x.data_ro, cdim=cdim, alpha=1.0, beta=0.5)
+    assert relerr(y.data_ro, yo) < TOL
+
+
+@pytest.mark.parametrize("ws", [1, 3])
+def test_warp_specialised_kernel(ws):
+    """The opt-in warp-specialised degree-3 kernel (action_hex_ws.cuh; FDB_WS is read once per process,
+    hence the worker): mass + stiffness, a ragged last unit, units straddling two columns, a subset."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, FDB_WS=str(ws))
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "_ws_worker.py")], env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "WS_OK" in r.stdout
+
+
 def test_subset_iteration(engine, oracle):
     p = 2
     mesh = ExtrudedHexMesh(5, 5, 4, warp=0.02)
