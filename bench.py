@@ -479,7 +479,7 @@ def main():
                                else "model 24 n^4 + 130 n^3 (kernel instance not counted)",
                 "peak_source": f"{sm_count} SMs x 64 fp64 FMA lanes/clk x 2 x {clk_hz / 1e9:.3f} GHz (clocks.sm_max_mhz); "
                                "microbenchmark: 37.1 TFLOP/s (profiles/r01_microbench_fp64.txt)",
-                "traffic_source": "ncu --set full capture, profiles/r02_action_cg3_n256_summary.txt (8.306 GB read + 3.893 GB written)" if traffic else None,
+                "traffic_source": "ncu --set full capture, profiles/r02s2_action_cg3_n256_summary.txt (8.783 GB read + 4.102 GB written)" if traffic else None,
                 "hbm": {"achieved": hbm_achieved, "peak": peak_gbs, "unit": "GB/s", "frac": hbm_achieved / peak_gbs,
                         "algorithmic_bytes_per_launch": abytes,
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",

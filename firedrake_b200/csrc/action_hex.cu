@@ -73,7 +73,7 @@ struct HelmParams {
     double B[N * N];         // B[q][a]
     double Dt[N * N];        // Dt[q][q']
     double DtR[N * N];       // DtR[q][j] = Dt[q][(j + q) % N]  (rolled zeta loop)
-    double DB[N * N];        // DB[q][a] = sum_j Dt[q][j] B[j][a] = d phi_a / dx at point q  (NOROT zeta loop)
+    double DB[N * N];        // DB[q][a] = sum_j Dt[q][j] B[j][a] = d phi_a / d x at point q (the collocated pair's product)
     double wq[N];
     double xq[N];
 };
@@ -190,15 +190,6 @@ struct Tile {
 // degree 3: the geometry coefficients that are needed once per zeta plane only (c2, c4, c5, c7 of the
 // cell, A1 of the lane) are parked in shared memory: 30 registers less in the quadrature loop
 // (9.75 -> 9.62 ms at 256^3, profiles/r02_action_variants.txt); -DFDB_NO_STASH builds without
-// degree 3, experiment (-DFDB_NOROT): no register rotation in the rolled zeta loop -- the loop works on the
-// tensor BEFORE the zeta interpolation (T) and accumulates AFTER its transpose (W), picking the zeta plane
-// through run-time rows of B and D = Dt B (uniform loads) instead of a run-time register column:
-// 128 more FMAs per lane and unit, 256 fewer register moves
-#ifdef FDB_NOROT
-constexpr bool OPT_NOROT = true;
-#else
-constexpr bool OPT_NOROT = false;
-#endif
 #ifdef FDB_NO_STASH
 constexpr bool OPT_STASH = false;
 #else
@@ -298,7 +289,6 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
     double *s_coord = s_u + WS::UBUF;                // [CWS][CS]   (single buffer)
     double *s_stash = s_coord + WS::COORD;           // [CWS][GS]   (geometry coefficients, if STASH)
     constexpr bool STASH = WS::STASH > 0 && !MATRIX && !AFFINE;
-    constexpr bool NOROT = OPT_NOROT && N == 4 && !MATRIX && !AFFINE && !SLIM;
     int *s_idx = reinterpret_cast<int *>(s_stash + WS::STASH);   // [2][CWS][US]  (empty if SLIM)
     int *s_mapraw = s_idx + WS::IDX;                 // [CWS][US], or [3][2][US] if SLIM
     int *s_vidx = s_mapraw + WS::MAPRAW;             // [2][CWS][8], or [3][2][8] if SLIM
@@ -561,11 +551,6 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
             __syncwarp();
             tile.load_Y(tmp);                            // tmp = w[qx][az] @ q_y
             apply_second<N, false>(P.B, tmp, U);         // a_z -> q_z     U[qx][qz] @ q_y
-            double T[N][N];                              // NOROT: w[qx][az] stays live, U dies after the store
-#pragma unroll
-            for (int i = 0; i < N; i++)
-#pragma unroll
-                for (int j = 0; j < N; j++) T[i][j] = NOROT ? tmp[i][j] : 0.0;
             __syncwarp();
             tile.store_Y(U);
             __syncwarp();
@@ -628,22 +613,6 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
                 const double wyz_a = wy_alpha * P.wq[qz];
                 const double wyz_b = wy_beta * P.wq[qz];
                 double *trow = tile.row_Y(qz);
-                double bz[N], dbz[N], Uc[N], vc[N];
-                if (NOROT) {
-#pragma unroll
-                    for (int k2 = 0; k2 < N; k2++) {
-                        bz[k2] = P.B[qz * N + k2];
-                        dbz[k2] = P.DB[qz * N + k2];
-                    }
-#pragma unroll
-                    for (int q = 0; q < N; q++) {
-                        double sU = 0.0;
-#pragma unroll
-                        for (int k2 = 0; k2 < N; k2++) sU = fma(bz[k2], T[q][k2], sU);
-                        Uc[q] = sU;                      // U[q][qz]
-                        vc[q] = 0.0;
-                    }
-                }
 #pragma unroll
                 for (int qx = 0; qx < N; qx++) {
                     const double xi = P.xq[qx];
@@ -658,13 +627,8 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
                     double gx = 0.0, gz = 0.0;
 #pragma unroll
                     for (int q = 0; q < N; q++) {
-                        if (NOROT) {
-                            gx = fma(P.Dt[qx * N + q], Uc[q], gx);
-                            gz = fma(dbz[q], T[qx][q], gz);
-                        } else {
-                            gx = fma(P.Dt[qx * N + q], U[q][0], gx);
-                            gz = fma(dz[q], U[qx][q], gz);
-                        }
+                        gx = fma(P.Dt[qx * N + q], U[q][0], gx);
+                        gz = fma(dz[q], U[qx][q], gz);
                     }
                     const double gy = trow[qx * N * N];
                     if (AFFINE) {
@@ -704,26 +668,10 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
                     trow[qx * N * N] = fy;
 #pragma unroll
                     for (int q = 0; q < N; q++) {
-                        if (NOROT) {
-                            vc[q] = fma(P.Dt[qx * N + q], fx, vc[q]);
-                            Vp[qx][q] = fma(dbz[q], fz, Vp[qx][q]);      // Vp holds W[qx][az] here
-                        } else {
-                            Vp[q][0] = fma(P.Dt[qx * N + q], fx, Vp[q][0]);
-                            Vp[qx][q] = fma(dz[q], fz, Vp[qx][q]);
-                        }
+                        Vp[q][0] = fma(P.Dt[qx * N + q], fx, Vp[q][0]);
+                        Vp[qx][q] = fma(dz[q], fz, Vp[qx][q]);
                     }
-                    if (MASS) {
-                        if (NOROT) vc[qx] = fma(wyz_b * P.wq[qx] * adet, Uc[qx], vc[qx]);
-                        else Vp[qx][0] = fma(wyz_b * P.wq[qx] * adet, U[qx][0], Vp[qx][0]);
-                    }
-                }
-                if (NOROT) {
-                    // this plane's xi-flux column, transposed zeta interpolation applied on the spot
-#pragma unroll
-                    for (int q = 0; q < N; q++)
-#pragma unroll
-                        for (int k2 = 0; k2 < N; k2++) Vp[q][k2] = fma(bz[k2], vc[q], Vp[q][k2]);
-                    continue;
+                    if (MASS) Vp[qx][0] = fma(wyz_b * P.wq[qx] * adet, U[qx][0], Vp[qx][0]);
                 }
                 // rotate: column j <- column j+1
 #pragma unroll
@@ -751,28 +699,11 @@ helmholtz_action_kernel(const __grid_constant__ HelmParams<N> P)
             tile.store_Z(u);
             __syncwarp();
             tile.load_Y(tmp);
-            if (NOROT) {
-                // only the eta part still needs q_z -> a_z; Vp already holds the rest of W[qx][az]
 #pragma unroll
-                for (int i = 0; i < N; i++)
+            for (int i = 0; i < N; i++)
 #pragma unroll
-                    for (int j = 0; j < N; j++) {
-                        double sW = Vp[i][j];
-#pragma unroll
-                        for (int k2 = 0; k2 < N; k2++) sW = fma(P.B[k2 * N + j], tmp[i][k2], sW);
-                        Vp[i][j] = sW;
-                    }
-#pragma unroll
-                for (int i = 0; i < N; i++)
-#pragma unroll
-                    for (int j = 0; j < N; j++) tmp[i][j] = Vp[i][j];
-            } else {
-#pragma unroll
-                for (int i = 0; i < N; i++)
-#pragma unroll
-                    for (int j = 0; j < N; j++) Vp[i][j] += tmp[i][j];
-                apply_second<N, true>(P.B, Vp, tmp);     // q_z -> a_z     W[qx][az] @ q_y
-            }
+                for (int j = 0; j < N; j++) Vp[i][j] += tmp[i][j];
+            apply_second<N, true>(P.B, Vp, tmp);         // q_z -> a_z     W[qx][az] @ q_y
             __syncwarp();
             tile.store_Y(tmp);
             __syncwarp();
