@@ -244,7 +244,10 @@ struct WarpSmem {
     static constexpr int TILE = CWS * Tile<N>::STRIDE;         // doubles
     static constexpr int UBUF = CWS * US;                      // doubles: gathered values (single buffer)
     static constexpr int COORD = CWS * CS;                     // doubles: vertex coordinates (single buffer)
-    static constexpr int GS = 28;                              // stash stride: c2 c4 c5 c7 (12) + A1 of 4 lanes (4 apart)
+#ifndef FDB_STASH_STRIDE
+#define FDB_STASH_STRIDE 28
+#endif
+    static constexpr int GS = FDB_STASH_STRIDE;                // stash stride: c2 c4 c5 c7 (12) + A1 of 4 lanes (4 apart)
     static constexpr int STASH = (OPT_STASH && N == 4 && !SLIM) ? CWS * GS : 0;   // doubles
     static constexpr int IDX = SLIM ? 0 : 2 * CWS * US;        // ints: global dof index per local dof
     static constexpr int MAPRAW = SLIM ? 3 * 2 * US : CWS * US;   // ints: bottom-cell map row(s)
