@@ -682,7 +682,14 @@ class Sparsity:
     (pyop2/types/mat.py:27-292).  Only square single-block sparsities whose row
     and column maps coincide are supported (every form of the supported set)."""
 
+    mixed = False
+
     def __init__(self, dsets, maps_and_regions, name=None):
+        if isinstance(dsets, MixedDataSet):
+            dsets = (dsets, dsets)
+        if isinstance(dsets, (tuple, list)) and any(isinstance(d, MixedDataSet) for d in dsets):
+            self._init_mixed(tuple(dsets), maps_and_regions, name)
+            return
         if isinstance(dsets, DataSet) or isinstance(dsets, Set):
             dsets = (dsets, dsets)
         self.dsets = tuple(_as_dataset(d) for d in dsets)
@@ -703,8 +710,76 @@ class Sparsity:
             raise NotImplementedError("exactly one (rmap, cmap) pair is supported")
         self.name = name or "sparsity"
 
+    def _init_mixed(self, dsets, maps_and_regions, name):
+        """Sparsity over MixedDataSets (pyop2/types/mat.py:75-160: one block per pair of data sets).
+        As the reference's default for mixed spaces (``mat_type='aij'``: ``Mat._init_monolithic``,
+        pyop2/types/mat.py:660-700) the blocks live in ONE scalar CSR matrix over the concatenated dof
+        numbering ``[block 0 dofs | block 1 dofs | ...]`` (dof = node * cdim + component); its pattern
+        comes from the concatenation of the dof-expanded block maps, so the engine's single-map
+        sparsity builder serves unchanged.  Square block structures with coinciding row / column maps
+        only (as for single blocks); one rank (no halo on the blocks)."""
+        rd, cd = dsets
+        if not (isinstance(rd, MixedDataSet) and isinstance(cd, MixedDataSet)) or len(rd) != len(cd) or \
+                any(r.set is not c.set or r.cdim != c.cdim for r, c in zip(rd, cd)):
+            raise NotImplementedError("mixed sparsities must be square: the same data sets for rows and columns")
+        if any(d.halo is not None for d in rd):
+            raise NotImplementedError("mixed sparsities are not partitioned (no halo on the blocks)")
+        if len(maps_and_regions) != 1:
+            raise NotImplementedError("exactly one (rmaps, cmaps) pair is supported")
+        rmaps, cmaps = maps_and_regions[0][0], maps_and_regions[0][1]
+        if not (isinstance(rmaps, MixedMap) and isinstance(cmaps, MixedMap)) or len(rmaps) != len(rd) or \
+                any(r is not c for r, c in zip(rmaps, cmaps)):
+            raise NotImplementedError("row and column maps must be the same MixedMap blocks")
+        for m, d in zip(rmaps, rd):
+            if m.toset is not d.set:
+                raise MapValueError("sparsity map does not target the data set of its block")
+        self.mixed = True
+        self.dsets = (rd, cd)
+        self.maps = [rmaps]
+        self.bs = 1
+        self.name = name or "mixed_sparsity"
+        sizes = [d.set.total_size * d.cdim for d in rd]
+        self.block_offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        self.mono_set = Set(int(self.block_offsets[-1]), name=self.name + "_dofs")
+        self._expanded = {}
+        parts = [self.expand_map(m, i) for i, m in enumerate(rmaps)]
+        it = rmaps.iterset
+        off = None
+        if it._extruded:
+            off = np.concatenate([e.offset for e in parts])
+        self.mono_map = Map(it, self.mono_set, sum(e.arity for e in parts),
+                            np.concatenate([e.values_with_halo for e in parts], axis=1),
+                            name=self.name + "_map", offset=off)
+        self.mono = Sparsity((self.mono_set, self.mono_set), [(self.mono_map, self.mono_map, None)],
+                             name=self.name + "_monolithic")
+
+    def expand_map(self, m, block):
+        """The dof map of ``m`` (a Map into the node set of ``block``) in the monolithic numbering:
+        arity * cdim entries ``offset_block + node * cdim + component``, node-major like the element
+        tensors of vector-valued spaces (pyop2/codegen/builder.py:575-625)."""
+        key = (id(m), block)
+        hit = self._expanded.get(key)
+        if hit is not None and hit[0] is m:
+            return hit[1]
+        d = self.dsets[0][block]
+        if m.toset is not d.set:
+            raise MapValueError(f"map {m.name} does not target the node set of block {block}")
+        cd = d.cdim
+        comp = np.arange(cd, dtype=np.int64)
+        vals = (m.values_with_halo.astype(np.int64)[:, :, None] * cd + comp[None, None, :]
+                + int(self.block_offsets[block])).reshape(m.values_with_halo.shape[0], -1)
+        off = None if m.offset is None else np.repeat(m.offset.astype(np.int64) * cd, cd)
+        if getattr(m, "offset_quotient", None) is not None:
+            raise NotImplementedError("periodic extrusion in a mixed matrix")
+        e = Map(m.iterset, self.mono_set, m.arity * cd, vals, name=f"{m.name}_dofs{block}", offset=off)
+        self._expanded[key] = (m, e)
+        return e
+
     @property
     def shape(self):
+        if self.mixed:
+            n = self.mono_set.total_size
+            return (n, n)
         n = self.dsets[0].set.total_size
         return (n, n)
 
@@ -717,6 +792,13 @@ class Mat:
     _ids = itertools.count()
 
     def __init__(self, sparsity: Sparsity, dtype=ScalarType, name=None):
+        if sparsity.mixed:
+            # monolithic matrix of a mixed space: the scalar CSR of the concatenated dof numbering;
+            # ``mat[i, j]`` are MatBlock views (pyop2/types/mat.py:660-700, 990-1060)
+            Mat.__init__(self, sparsity.mono, dtype, name)
+            self.sparsity = sparsity
+            self._blocks = {}
+            return
         self.sparsity = sparsity
         self.name = name or f"mat_{next(Mat._ids)}"
         m = sparsity.maps[0]
@@ -745,10 +827,49 @@ class Mat:
 
     def __call__(self, access, path, lgmaps=None):
         rmap, cmap = path
+        if self._mixed:
+            # the whole mixed element tensor at once: rows / columns ordered block by block
+            if not (isinstance(rmap, MixedMap) and isinstance(cmap, MixedMap)):
+                raise MapValueError("a mixed Mat argument needs MixedMaps (or pass mat[i, j] block by block)")
+            sp = self.sparsity
+            rmap = sp.mono_map if rmap is sp.maps[0] else self._mono_map_of(rmap)
+            cmap = sp.mono_map if cmap is sp.maps[0] else self._mono_map_of(cmap)
         a = LegacyArg(self, access, rmap)
         a.cmap = cmap
         a.lgmaps = lgmaps
         return a
+
+    @property
+    def _mixed(self):
+        return getattr(getattr(self, "sparsity", None), "mixed", False)
+
+    def _mono_map_of(self, mm):
+        sp = self.sparsity
+        parts = [sp.expand_map(m, i) for i, m in enumerate(mm)]
+        key = ("mono",) + tuple(id(m) for m in mm)
+        hit = sp._expanded.get(key)
+        if hit is not None and all(a is b for a, b in zip(hit[0], mm)):
+            return hit[1]
+        off = np.concatenate([e.offset for e in parts]) if mm.iterset._extruded else None
+        e = Map(mm.iterset, sp.mono_set, sum(p.arity for p in parts),
+                np.concatenate([p.values_with_halo for p in parts], axis=1), offset=off)
+        sp._expanded[key] = (tuple(mm), e)
+        return e
+
+    def __getitem__(self, ij):
+        """``mat[i, j]``: the block coupling row space i and column space j (pyop2 ``MatBlock``)."""
+        if not self._mixed:
+            if tuple(ij) != (0, 0):
+                raise IndexError("a single-block Mat has the block (0, 0) only")
+            return self
+        i, j = ij
+        nb = len(self.sparsity.dsets[0])
+        if not (0 <= i < nb and 0 <= j < nb):
+            raise IndexError(f"block ({i}, {j}) of a {nb} x {nb} mixed matrix")
+        blk = self._blocks.get((i, j))
+        if blk is None:
+            blk = self._blocks[(i, j)] = MatBlock(self, i, j)
+        return blk
 
     def zero(self):
         _lib.check(_lib.lib().fdb_mat_zero(self.handle), "fdb_mat_zero")
@@ -798,7 +919,25 @@ class Mat:
                 A[r * bs:(r + 1) * bs, c * bs:(c + 1) * bs] = blocks[k]
         return A
 
-    def mult(self, x: "Dat", y: "Dat"):
+    def mult(self, x, y):
+        if self._mixed and isinstance(x, MixedDat):
+            # block vectors <-> the contiguous dof vector of the monolithic matrix (device copies)
+            L = _lib.lib()
+            if getattr(self, "_xy", None) is None:
+                self._xy = (Dat(self.sparsity.mono_set), Dat(self.sparsity.mono_set))
+            xm, ym = self._xy
+            offs = self.sparsity.block_offsets
+            xm.zero()
+            for xb, o in zip(x, offs):
+                _lib.check(L.fdb_vec_axpy(xb._data.size, 1.0, xb.device_ptr, xm.device_ptr + int(o) * 8), "pack")
+            xm._device_written()
+            _lib.check(L.fdb_mat_mult(self.handle, xm.device_ptr, ym.device_ptr), "fdb_mat_mult")
+            ym._device_written()
+            for yb, o in zip(y, offs):
+                yb.zero()
+                _lib.check(L.fdb_vec_axpy(yb._data.size, 1.0, ym.device_ptr + int(o) * 8, yb.device_ptr), "unpack")
+                yb._device_written()
+            return
         _lib.check(_lib.lib().fdb_mat_mult(self.handle, x.device_ptr, y.device_ptr), "fdb_mat_mult")
         y._device_written()
 
@@ -808,6 +947,85 @@ class Mat:
                 _lib._lib.fdb_mat_destroy(self.handle)
         except Exception:
             pass
+
+
+class MatBlock(Mat):
+    """``mixed_mat[i, j]`` (pyop2/types/mat.py MatBlock, ``MatGetLocalSubMatrix``): a VIEW of the
+    monolithic matrix.  ``block(op2.INC, (rmap_i, cmap_j), lgmaps=...)`` is a parloop argument whose
+    maps are the dof-expanded, offset maps of the two spaces (block size 1), so the element tensor
+    of the block, rows (node, component) x columns (node, component), lands in the right rows and
+    columns of the parent; ``lgmaps`` are dof-level arrays over the block's own rows / columns."""
+
+    def __init__(self, parent, i, j):
+        self.parent, self.i, self.j = parent, i, j
+        self.sparsity = parent.sparsity
+        self.handle = parent.handle
+        self.bs = 1
+        self.name = f"{parent.name}_{i}{j}"
+
+    @property
+    def dat_version(self):
+        return self.parent.dat_version
+
+    @dat_version.setter
+    def dat_version(self, v):
+        self.parent.dat_version = v
+
+    @property
+    def _range(self):
+        o = self.sparsity.block_offsets
+        return (int(o[self.i]), int(o[self.i + 1])), (int(o[self.j]), int(o[self.j + 1]))
+
+    def __call__(self, access, path, lgmaps=None):
+        rmap, cmap = path
+        sp = self.sparsity
+        a = LegacyArg(self, access, sp.expand_map(rmap, self.i))
+        a.cmap = sp.expand_map(cmap, self.j)
+        a.lgmaps = None
+        if lgmaps is not None:
+            n = sp.mono_set.total_size
+            (r0, r1), (c0, c1) = self._range
+            out = []
+            for lg, lo, hi in ((lgmaps[0], r0, r1), (lgmaps[1], c0, c1)):
+                lg = np.asarray(lg, dtype=np.int64).ravel()
+                if lg.size != hi - lo:
+                    raise ValueError(f"block lgmap has {lg.size} entries, the block has {hi - lo} dofs")
+                full = np.arange(n, dtype=np.int64)
+                full[lo:hi] = np.where(lg >= 0, lg + lo, -1)
+                out.append(full.astype(IntType))
+            a.lgmaps = tuple(out)
+        return a
+
+    def __getitem__(self, ij):
+        raise IndexError("a MatBlock has no sub-blocks")
+
+    def zero(self):
+        raise NotImplementedError("zero the mixed Mat, not one of its blocks")
+
+    def assemble(self):
+        self.parent.assemble()
+
+    def set_local_diagonal_entries(self, rows, diag_val=1.0, idx=None):
+        """Diagonal of a diagonal block: ``rows`` are NODE rows of the block's space, ``idx`` one
+        component (default all), as for blocked matrices (pyop2/types/mat.py:897-937)."""
+        if self.i != self.j:
+            raise ValueError("only diagonal blocks have a diagonal")
+        cd = self.sparsity.dsets[0][self.i].cdim
+        rows = np.asarray(rows, dtype=np.int64).ravel()
+        comps = np.arange(cd) if idx is None else np.array([int(idx)])
+        dofs = (rows[:, None] * cd + comps[None, :]).ravel() + self._range[0][0]
+        Mat.set_local_diagonal_entries(self.parent, dofs.astype(IntType), diag_val)
+
+    @property
+    def values(self):
+        (r0, r1), (c0, c1) = self._range
+        return self.parent.values[r0:r1, c0:c1]
+
+    def mult(self, x, y):
+        raise NotImplementedError("multiply with the mixed Mat")
+
+    def __del__(self):
+        pass                                    # the parent owns the engine handle
 
 
 class Global:

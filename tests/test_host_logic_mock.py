@@ -56,6 +56,12 @@ def test_mixed_dat_host_logic(mock):
     tj.test_mixed_dat_parloop_and_vector_operations(mock)
 
 
+@pytest.mark.parametrize("extruded", [False, True])
+def test_mixed_mat_host_logic(mock, extruded):
+    """Monolithic mixed matrices: dof-expanded block maps, MatBlock arguments, block lgmaps, mult on MixedDats."""
+    tj.test_mixed_mat_monolithic(mock, extruded)
+
+
 @pytest.mark.parametrize("region", ["ALL", "ON_TOP", "ON_INTERIOR_FACETS"])
 def test_variable_layers_host_logic(mock, region):
     tj.test_variable_layers_on_device(mock, region)
