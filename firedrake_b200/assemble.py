@@ -158,7 +158,7 @@ def functional_kernel(degree, measure, facet=None, name=None, integrand="avg"):
     extruded ds_b / ds_t kernels -- else read from a 4th argument: ds_v), or "dS" (interior
     facet; ``integrand`` "avg" = avg(f), "jump2" = (f('+') - f('-'))**2; ``facet`` = the pair of
     local facet numbers or None to read uint[2])."""
-    from .fiat_lite import interval_element, _lagrange_tab
+    from .fiat_lite import interval_element
     from .codegen import CStringKernel
     el = interval_element(degree)
     n = degree + 1
