@@ -66,7 +66,7 @@ def matrix_case(name, n, p, steps=3):
 
 
 def blocked_matrix_case(name, n, p, cdim, steps=2):
-    """config 4, explicit: vector-valued space -> blocked CSR (not yet validated on a GPU)."""
+    """config 4, explicit: vector-valued space -> blocked CSR."""
     mesh = ExtrudedHexMesh(n, n, n, warp=0.05)
     V = FunctionSpace(mesh, p, cdim=cdim)
     t0 = time.perf_counter()
@@ -82,7 +82,7 @@ def blocked_matrix_case(name, n, p, cdim, steps=2):
 
 def generic_vs_fast_case(name, n, steps=5):
     """The generic NVRTC wrapper around a plain-C Q1 Poisson kernel against the hand-written
-    kernel on the same problem (not yet validated on a GPU)."""
+    kernel on the same problem."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import test_codegen as tc
     mesh = ExtrudedHexMesh(n, n, n, warp=0.05)
@@ -146,8 +146,6 @@ def dg_case(name, n, steps=10, fused=False):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
-    ap.add_argument("--unvalidated", action="store_true",
-                    help="also run the cases whose code paths have not passed on a GPU yet (DESIGN.md 7b)")
     ap.add_argument("--only", default=None, help="run only the cases whose name contains this substring")
     args = ap.parse_args()
     _lib.init(0)
@@ -167,12 +165,11 @@ def main():
         lambda: matrix_case("Poisson CG2 matrix", 16 if q else 48, 2),
         lambda: matrix_case("Poisson CG3 matrix", 8 if q else 32, 3),
     ]
-    if True:
-        jobs += [
-            lambda: matrix_case("Poisson CG4 matrix (new instantiation)", 8 if q else 24, 4),
-            lambda: blocked_matrix_case("config4 vector Helmholtz CG4 explicit (blocked CSR)", 8 if q else 32, 4, 3),
-            lambda: generic_vs_fast_case("generic NVRTC wrapper vs hand-written kernel, Poisson CG1", 32 if q else 128),
-        ]
+    jobs += [
+        lambda: matrix_case("Poisson CG4 matrix (new instantiation)", 8 if q else 24, 4),
+        lambda: blocked_matrix_case("config4 vector Helmholtz CG4 explicit (blocked CSR)", 8 if q else 32, 4, 3),
+        lambda: generic_vs_fast_case("generic NVRTC wrapper vs hand-written kernel, Poisson CG1", 32 if q else 128),
+    ]
     if args.only:
         import inspect
         jobs = [j for j in jobs if args.only in inspect.getsource(j)]
