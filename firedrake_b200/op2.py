@@ -928,14 +928,14 @@ class Mat:
             xm, ym = self._xy
             offs = self.sparsity.block_offsets
             xm.zero()
-            for xb, o in zip(x, offs):
-                _lib.check(L.fdb_vec_axpy(xb._data.size, 1.0, xb.device_ptr, xm.device_ptr + int(o) * 8), "pack")
+            xd, yd = xm.device_ptr, ym.device_ptr
+            for xb, o in zip(x, offs):           # plain device copies: no alignment demands on odd offsets
+                _lib.check(L.fdb_memcpy_d2d(xd + int(o) * 8, xb.device_ptr, xb.nbytes), "pack")
             xm._device_written()
-            _lib.check(L.fdb_mat_mult(self.handle, xm.device_ptr, ym.device_ptr), "fdb_mat_mult")
+            _lib.check(L.fdb_mat_mult(self.handle, xd, yd), "fdb_mat_mult")
             ym._device_written()
             for yb, o in zip(y, offs):
-                yb.zero()
-                _lib.check(L.fdb_vec_axpy(yb._data.size, 1.0, ym.device_ptr + int(o) * 8, yb.device_ptr), "unpack")
+                _lib.check(L.fdb_memcpy_d2d(yb.device_ptr, yd + int(o) * 8, yb.nbytes), "unpack")
                 yb._device_written()
             return
         _lib.check(_lib.lib().fdb_mat_mult(self.handle, x.device_ptr, y.device_ptr), "fdb_mat_mult")
