@@ -36,3 +36,31 @@ def test_reference_arm_json_line():
 
 def test_reference_arm_other_ranks_are_silent():
     assert run({"RANK": "1", "WORLD_SIZE": "2"}, "--gpus", "2") == ""
+
+
+def test_counted_work_follows_from_the_committed_sass_listing():
+    """bench.py's roofline uses profiles/kernel_counts.json; the numbers there must be what
+    tools/sass_loops.py counts in the committed listing of the headline kernel (one pipeline unit of
+    8 cells = the main loop once + the rolled zeta loop four times)."""
+    import re
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import sass_loops
+    ins = sass_loops.parse(os.path.join(ROOT, "profiles", "r02_action_cg3.sass"))
+    loops = []
+    for a, t, _ in ins:
+        m = re.match(r"BRA(?!\.DIV)\S*\s+(?:\S+,\s*)?(0x[0-9a-f]+)", t)
+        if m and int(m.group(1), 16) < a:
+            loops.append((int(m.group(1), 16), a))
+    outer = max(loops, key=lambda l: l[1] - l[0])
+    inner = max((l for l in loops if outer[0] <= l[0] and l[1] < outer[1]), key=lambda l: l[1] - l[0])
+    count = {}
+    for a, t, _ in ins:
+        if outer[0] <= a <= outer[1]:
+            op = t.split()[0].split(".")[0]
+            count[op] = count.get(op, 0) + (4 if inner[0] <= a <= inner[1] else 1)
+    k = json.load(open(os.path.join(ROOT, "profiles", "kernel_counts.json")))["helmholtz_action_kernel<4,false,true,3>"]
+    assert (count["DFMA"], count["DMUL"], count["DADD"], count["MUFU"]) == (k["dfma"], k["dmul"], k["dadd"], k["mufu_rcp64h"])
+    fp64 = count["DFMA"] + count["DMUL"] + count["DADD"] + count["MUFU"]
+    assert fp64 == k["fp64_instr_per_warp_unit"] and sum(count.values()) == k["instr_per_warp_unit"]
+    assert k["fp64_instr_per_cell"] == fp64 * 32 // k["cells_per_warp_unit"]
+    assert k["flop_per_cell"] == (2 * count["DFMA"] + count["DMUL"] + count["DADD"]) * 32 // k["cells_per_warp_unit"]
