@@ -627,10 +627,17 @@ class Dat:
     # in-place algebra on the device (pyop2/types/dat.py:312-352 copy, :354-540 _iop / maxpy)
     def copy(self, other, subset=None):
         """``other <- self`` (note the direction: pyop2/types/dat.py:312-330)."""
-        if subset is not None:
-            raise NotImplementedError("copy on a subset")
         if other.nbytes != self.nbytes:
             raise ValueError("copy between Dats of different sizes")
+        if subset is not None:
+            # only the rows of the subset (pyop2/types/dat.py:312-330, _copy_parloop on a Subset)
+            if not hasattr(subset, "_dev_idx"):
+                subset._dev_idx = DeviceArray.from_host(subset.indices)      # uploaded once
+            dst, src = other.device_ptr, self.device_ptr
+            _lib.check(_lib.lib().fdb_dat_set_nodes(dst, src, self.cdim, subset._dev_idx.ptr,
+                                                    len(subset.indices)), "fdb_dat_set_nodes")
+            other._device_written()
+            return
         _lib.check(_lib.lib().fdb_memcpy_d2d(other.device_ptr, self.device_ptr, self.nbytes), "d2d")
         other._device_written(halo_valid=self.halo_valid)
 

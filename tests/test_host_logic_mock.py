@@ -126,6 +126,14 @@ def test_dat_algebra_host_logic(mock):
     c.data[:] = 1.0                                   # host write, then device op must see it
     c += b
     assert np.allclose(c.data_ro, 1 + b0)
+    # copy restricted to a subset: the other rows of the target keep their values
+    sub = op2.Subset(s, np.array([3, 7, 8, 41], dtype=np.int32))
+    d = op2.Dat(op2.DataSet(s, 2), rng.standard_normal((50, 2)))
+    e = op2.Dat(op2.DataSet(s, 2), np.full((50, 2), -5.0))
+    d.copy(e, subset=sub)
+    want = np.full((50, 2), -5.0)
+    want[sub.indices] = d.data_ro[sub.indices]
+    assert np.array_equal(e.data_ro, want)
 
 
 @pytest.mark.parametrize("pc", ["none", "jacobi", "mg"])
