@@ -242,6 +242,31 @@ class Map:
         return self._dev.ptr
 
 
+class ComposedMap(Map):
+    """``op2.ComposedMap(m0, m1, ..., mk)``: ``local[i] = global[m0[m1[...mk[e]...]][i]]``
+    (pyop2/types/map.py:219-279): ``m0`` has the arity of the result, every inner map has arity 1 and
+    lands on the iteration set of the map before it.  The reference keeps the factors and emits the
+    chained indirection in the wrapper; here the composition is materialised ONCE on the host (one
+    int32 gather per factor) and the device sees a plain map -- one dependent load per access instead
+    of k + 1.  ``offset`` / ``offset_quotient`` are those of ``m0`` (map.py:257)."""
+
+    def __init__(self, *maps_, name=None):
+        if len(maps_) < 1 or not all(isinstance(m, Map) for m in maps_):
+            raise TypeError("all factors of a ComposedMap must be Maps")
+        for tomap, frommap in zip(maps_[:-1], maps_[1:]):
+            if tomap.iterset is not frommap.toset:
+                raise MapValueError("tomap.iterset must match frommap.toset")
+            if frommap.arity != 1:
+                raise MapValueError("inner maps of a ComposedMap have arity 1")
+        vals = maps_[0].values_with_halo
+        for m in maps_[1:]:
+            vals = vals[m.values_with_halo[:, 0]]
+        self.maps_ = tuple(maps_)
+        super().__init__(maps_[-1].iterset, maps_[0].toset, maps_[0].arity, vals,
+                         name=name or "cmap_" + "_".join(m.name for m in maps_),
+                         offset=maps_[0].offset, offset_quotient=maps_[0].offset_quotient)
+
+
 # -------------------------------------------------------------- device memory
 class DeviceArray:
     """RAII wrapper around fdb_malloc/fdb_free."""

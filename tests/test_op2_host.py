@@ -129,3 +129,29 @@ def test_firedrake_hook_needs_firedrake():
     with pytest.raises(ImportError):
         hook.install()
     hook.uninstall()        # no-op when nothing was installed
+
+
+def test_composed_map_is_materialised():
+    """op2.ComposedMap (pyop2/types/map.py:219-279): facets -> cells -> nodes; the inner maps have arity 1."""
+    rng = np.random.default_rng(3)
+    facets, cells, nodes = op2.Set(11), op2.Set(7), op2.Set(20)
+    c2n = op2.Map(cells, nodes, 4, rng.integers(0, 20, (7, 4)), offset=None)
+    f2c = op2.Map(facets, cells, 1, rng.integers(0, 7, (11, 1)))
+    cm = op2.ComposedMap(c2n, f2c)
+    assert cm.iterset is facets and cm.toset is nodes and cm.arity == 4 and cm.maps_ == (c2n, f2c)
+    assert np.array_equal(cm.values, c2n.values[f2c.values[:, 0]])
+    sub = op2.Set(5)
+    s2f = op2.Map(sub, facets, 1, rng.integers(0, 11, (5, 1)))
+    cm3 = op2.ComposedMap(c2n, f2c, s2f)
+    assert np.array_equal(cm3.values, c2n.values[f2c.values[s2f.values[:, 0], 0]])
+    with pytest.raises(op2.MapValueError):
+        op2.ComposedMap(f2c, c2n)                      # c2n lands on nodes, f2c iterates facets
+    with pytest.raises(op2.MapValueError):
+        op2.ComposedMap(c2n, op2.Map(facets, cells, 2, rng.integers(0, 7, (11, 2))))   # inner arity 2
+    # extruded: the offset of the outer map is inherited
+    ecells = op2.ExtrudedSet(op2.Set(7), 4)
+    ec2n = op2.Map(ecells, nodes, 2, rng.integers(0, 10, (7, 2)), offset=[1, 1])
+    efac = op2.ExtrudedSet(op2.Set(11), 4)
+    ef2c = op2.Map(efac, ecells, 1, rng.integers(0, 7, (11, 1)), offset=[0])
+    ecm = op2.ComposedMap(ec2n, ef2c)
+    assert np.array_equal(ecm.offset, [1, 1]) and ecm.iterset is efac
