@@ -172,6 +172,12 @@ class Subset(Set):
 
     def __init__(self, superset: Set, indices):
         idx = np.unique(np.asarray(indices, dtype=IntType))
+        if isinstance(superset, Subset):
+            # a subset of a subset addresses the parent's entries (pyop2/types/set.py:413-416)
+            if len(idx) and (idx[0] < 0 or idx[-1] >= superset.total_size):
+                raise ValueError("subset indices out of range")
+            idx = np.unique(superset.indices[idx])
+            superset = superset.superset
         if len(idx) and (idx[0] < 0 or idx[-1] >= superset.total_size):
             raise ValueError("subset indices out of range")
         self.superset = superset
@@ -185,6 +191,37 @@ class Subset(Set):
         if self._extruded:
             self.constant_layers = superset.constant_layers
             self.layers_array = superset.layers_array
+
+
+    # set algebra on the index lists (pyop2/types/set.py:486-547); a plain Set stands for "everything"
+    @property
+    def owned_indices(self):
+        return self.indices[self.indices < self.superset.size]
+
+    def _other_indices(self, other):
+        if other is self.superset:
+            return None
+        if not isinstance(other, Subset) or other.superset is not self.superset:
+            raise TypeError("set operations need a subset of the same superset (or the superset itself)")
+        return other.indices
+
+    def intersection(self, other):
+        o = self._other_indices(other)
+        return self if o is None else Subset(self.superset, np.intersect1d(self.indices, o))
+
+    def union(self, other):
+        o = self._other_indices(other)
+        return other if o is None else Subset(self.superset, np.union1d(self.indices, o))
+
+    def difference(self, other):
+        o = self._other_indices(other)
+        return Subset(self.superset, [] if o is None else np.setdiff1d(self.indices, o))
+
+    def symmetric_difference(self, other):
+        o = self._other_indices(other)
+        if o is None:
+            return Subset(self.superset, np.setdiff1d(np.arange(self.superset.total_size, dtype=IntType), self.indices))
+        return Subset(self.superset, np.setxor1d(self.indices, o))
 
 
 class DataSet:

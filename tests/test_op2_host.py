@@ -155,3 +155,23 @@ def test_composed_map_is_materialised():
     ef2c = op2.Map(efac, ecells, 1, rng.integers(0, 7, (11, 1)), offset=[0])
     ecm = op2.ComposedMap(ec2n, ef2c)
     assert np.array_equal(ecm.offset, [1, 1]) and ecm.iterset is efac
+
+
+def test_subset_nesting_and_set_algebra():
+    """Subsets of subsets address the parent (pyop2/types/set.py:413-416); intersection / union /
+    difference / symmetric_difference work on the index lists (set.py:486-547)."""
+    s = op2.Set((6, 10, 14))
+    a = op2.Subset(s, [1, 3, 5, 7, 9, 11, 13])
+    b = a([0, 2, 2, 6])                                   # positions in a -> entries 1, 5, 13 of s
+    assert b.superset is s and list(b.indices) == [1, 5, 13] and b.sizes == (2, 2, 3)
+    assert list(a.owned_indices) == [1, 3, 5, 7, 9]
+    c = op2.Subset(s, [0, 1, 2, 3, 13])
+    assert list(a.intersection(c).indices) == [1, 3, 13] and a.intersection(s) is a
+    assert list(a.union(c).indices) == [0, 1, 2, 3, 5, 7, 9, 11, 13] and a.union(s) is s
+    assert list(a.difference(c).indices) == [5, 7, 9, 11] and len(a.difference(s).indices) == 0
+    assert list(a.symmetric_difference(c).indices) == [0, 2, 5, 7, 9, 11]
+    assert list(a.symmetric_difference(s).indices) == [0, 2, 4, 6, 8, 10, 12]
+    with pytest.raises(TypeError):
+        a.union(op2.Subset(op2.Set(14), [1]))
+    with pytest.raises(ValueError):
+        a([7])
