@@ -593,8 +593,56 @@ class Dat:
         self._is_zero = False
         return self._data
 
+    @property
+    def data_wo(self):
+        """Write-only host access (pyop2/types/dat.py data_wo): the caller overwrites every owned row, so
+        nothing is downloaded first."""
+        self._host_valid = True
+        self.increment_dat_version()
+        self._dev_valid = False
+        self._is_zero = False
+        self.halo_valid = False
+        return self._data[:self.dataset.set.size]
+
+    @property
+    def data_wo_with_halos(self):
+        self._host_valid = True
+        self.increment_dat_version()
+        self._dev_valid = False
+        self._is_zero = False
+        return self._data
+
     def increment_dat_version(self):
         self.dat_version += 1
+
+    # -- a Dat is also the 1-tuple of itself (pyop2/types/dat.py:118-138: split / iteration / indexing)
+    def split(self):
+        return (self,)
+
+    def __iter__(self):
+        yield self
+
+    def __len__(self):
+        return 1
+
+    def __getitem__(self, i):
+        if i != 0:
+            raise IndexError("a Dat has the block 0 only")
+        return self
+
+    def save(self, filename):
+        """Owned rows to a NumPy file (pyop2/types/dat.py:286-294)."""
+        np.save(filename, self.data_ro)
+
+    def load(self, filename):
+        """Owned rows from a NumPy file written by ``save`` (".npy" appended as NumPy does)."""
+        import os
+        if not os.path.exists(filename) and os.path.exists(str(filename) + ".npy"):
+            filename = str(filename) + ".npy"
+        v = np.load(filename)
+        if v.shape != self._data[:self.dataset.set.size].shape:
+            raise ValueError("file holds an array of a different shape")
+        self.data_wo[...] = v
 
     # -- device residency
     @property
@@ -726,6 +774,65 @@ class Dat:
             hv = self.halo_valid          # a uniform scaling keeps current ghost rows current
         self._device_written(halo_valid=hv)
         return self
+
+    def __itruediv__(self, other):
+        if isinstance(other, Dat):
+            raise NotImplementedError("pointwise division of Dats: scale by the reciprocal field")
+        return self.__imul__(1.0 / float(other))
+
+    # binary operators build a new Dat on the device (pyop2/types/dat.py:422-505)
+    def _copy_of(self):
+        r = Dat(self.dataset, dtype=self.dtype)
+        self.copy(r)
+        return r
+
+    def _shift(self, value):
+        """self += value (a scalar), through a filled temporary."""
+        t = Dat(self.dataset, dtype=self.dtype)
+        _lib.check(_lib.lib().fdb_vec_fill(t._data.size, float(value), t.device_ptr), "fdb_vec_fill")
+        t._device_written(halo_valid=True)
+        self.axpy(1.0, t)
+
+    def __pos__(self):
+        return self._copy_of()
+
+    def __neg__(self):
+        r = self._copy_of()
+        r *= -1.0
+        return r
+
+    def __add__(self, other):
+        r = self._copy_of()
+        if isinstance(other, Dat):
+            r += other
+        else:
+            r._shift(other)
+        return r
+
+    __radd__ = __add__
+
+    def __sub__(self, other):
+        r = self._copy_of()
+        if isinstance(other, Dat):
+            r -= other
+        else:
+            r._shift(-float(other))
+        return r
+
+    def __rsub__(self, other):
+        return (-self).__add__(other)
+
+    def __mul__(self, other):
+        r = self._copy_of()
+        r *= other
+        return r
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, other):
+        r = self._copy_of()
+        r /= other
+        return r
 
     def maxpy(self, scalars, dats):
         """``self += sum_i scalars[i] * dats[i]`` (pyop2/types/dat.py:509-540)."""

@@ -126,6 +126,27 @@ def test_dat_algebra_host_logic(mock):
     c.data[:] = 1.0                                   # host write, then device op must see it
     c += b
     assert np.allclose(c.data_ro, 1 + b0)
+    # binary operators return new Dats; scalars shift / scale
+    f = a + b
+    g = 2.0 * a - b + 1.5
+    h = -(a / 4.0) + (1.0 - b)
+    assert f is not a and np.allclose(f.data_ro, a.data_ro + b.data_ro)
+    assert np.allclose(g.data_ro, 2 * a.data_ro - b.data_ro + 1.5)
+    assert np.allclose(h.data_ro, -a.data_ro / 4 + 1 - b.data_ro)
+    g /= 2.0
+    assert np.allclose(g.data_ro, (2 * a.data_ro - b.data_ro + 1.5) / 2)
+    assert a.split() == (a,) and len(a) == 1 and a[0] is a and list(a) == [a]
+    # write-only host access does not download; save / load round trip
+    v0 = h.dat_version
+    h.data_wo[...] = 7.0
+    assert h.dat_version > v0 and np.all(h.data_ro == 7.0)
+    import os
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        fn = os.path.join(tmp, "dat")
+        f.save(fn)
+        h.load(fn)
+    assert np.array_equal(h.data_ro, f.data_ro)
     # copy restricted to a subset: the other rows of the target keep their values
     sub = op2.Subset(s, np.array([3, 7, 8, 41], dtype=np.int32))
     d = op2.Dat(op2.DataSet(s, 2), rng.standard_normal((50, 2)))
