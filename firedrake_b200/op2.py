@@ -1051,6 +1051,52 @@ class Mat:
         _lib.check(_lib.lib().fdb_mat_zero(self.handle), "fdb_mat_zero")
         self.dat_version += 1
 
+    zeroEntries = zero
+
+    # shape bookkeeping of pyop2/types/mat.py:820-890
+    @property
+    def is_mixed(self):
+        return self._mixed
+
+    @property
+    def dims(self):
+        d = self.sparsity.dsets
+        if self._mixed:
+            return tuple(tuple((r.dim, c.dim) for c in d[1]) for r in d[0])
+        return (((d[0].dim, d[1].dim),),)
+
+    @property
+    def nblock_rows(self):
+        return len(self.sparsity.dsets[0]) if self._mixed else 1
+
+    @property
+    def nblock_cols(self):
+        return len(self.sparsity.dsets[1]) if self._mixed else 1
+
+    @property
+    def nblocks(self):
+        return self.nblock_rows * self.nblock_cols
+
+    @property
+    def blocks(self):
+        return [[self[i, j] for j in range(self.nblock_cols)] for i in range(self.nblock_rows)]
+
+    def __iter__(self):
+        """The blocks in row-major order (pyop2/types/mat.py:835-838)."""
+        for row in self.blocks:
+            yield from row
+
+    @property
+    def ncols(self):
+        return self.nrows
+
+    @property
+    def shape(self):
+        return (self.nrows * self.bs, self.nrows * self.bs)
+
+    def increment_dat_version(self):
+        self.dat_version += 1
+
     def assemble(self):
         """MatAssemblyBegin/End: nothing is stashed here (single address space
         per GPU, owner-computes across GPUs); just drain the stream."""
@@ -1172,8 +1218,30 @@ class MatBlock(Mat):
             a.lgmaps = tuple(out)
         return a
 
+    _mixed = False                              # a block is a single-block matrix to its users
+
     def __getitem__(self, ij):
-        raise IndexError("a MatBlock has no sub-blocks")
+        if tuple(ij) != (0, 0):
+            raise IndexError("a MatBlock has the block (0, 0) only")
+        return self
+
+    @property
+    def dims(self):
+        d = self.sparsity.dsets
+        return (((d[0][self.i].dim, d[1][self.j].dim),),)
+
+    @property
+    def shape(self):
+        (r0, r1), (c0, c1) = self._range
+        return (r1 - r0, c1 - c0)
+
+    @property
+    def nrows(self):
+        return self.shape[0]
+
+    @property
+    def ncols(self):
+        return self.shape[1]
 
     def zero(self):
         raise NotImplementedError("zero the mixed Mat, not one of its blocks")
@@ -1220,6 +1288,51 @@ class Global:
     @property
     def data_ro(self):
         return self._data
+
+    # host data: the vector operations of pyop2/types/glob.py:33-180 are NumPy one-liners
+    @property
+    def data_wo(self):
+        return self.data
+
+    @property
+    def shape(self):
+        return self._data.shape
+
+    @property
+    def dtype(self):
+        return self._data.dtype
+
+    @property
+    def nbytes(self):
+        return self._data.nbytes
+
+    def increment_dat_version(self):
+        self.dat_version += 1
+
+    def split(self):
+        return (self,)
+
+    def zero(self, subset=None):
+        if subset is not None:
+            raise NotImplementedError("a Global has no subsets")
+        self.data[...] = 0
+
+    def copy(self, other, subset=None):
+        """``other <- self`` (the direction of Dat.copy)."""
+        other.data[...] = self._data
+
+    def duplicate(self):
+        return Global(self.dim, self._data, dtype=self._data.dtype, name=self.name + "_dup")
+
+    def inner(self, other):
+        return float(np.dot(self._data.ravel(), np.conj(other.data_ro.ravel())))
+
+    def axpy(self, alpha, other):
+        self.data[...] += alpha * other.data_ro
+
+    def maxpy(self, scalars, globs):
+        for a, g in zip(scalars, globs):
+            self.axpy(a, g)
 
     def __call__(self, access, path=None):
         return LegacyArg(self, access, None)

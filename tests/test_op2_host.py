@@ -175,3 +175,19 @@ def test_subset_nesting_and_set_algebra():
         a.union(op2.Subset(op2.Set(14), [1]))
     with pytest.raises(ValueError):
         a([7])
+
+
+def test_global_vector_operations():
+    """The host-side vector interface of op2.Global (pyop2/types/glob.py:33-180)."""
+    g = op2.Global(3, [1.0, 2.0, 3.0])
+    h = g.duplicate()
+    assert h is not g and np.array_equal(h.data_ro, g.data_ro) and g.shape == (3,) and g.nbytes == 24
+    v = g.dat_version
+    g.axpy(2.0, h)
+    assert g.dat_version > v and np.array_equal(g.data_ro, [3.0, 6.0, 9.0])
+    g.maxpy([1.0, -1.0], [h, h])
+    assert np.array_equal(g.data_ro, [3.0, 6.0, 9.0]) and g.inner(h) == 3 + 12 + 27
+    g.copy(h)
+    assert np.array_equal(h.data_ro, g.data_ro)
+    g.zero()
+    assert not g.data_ro.any() and g.split() == (g,)
