@@ -17,6 +17,7 @@ import _mock_engine as me
 import test_assemble_gpu as ta
 import test_jit_gpu as tj
 import test_matrix_gpu as tm
+import test_zz_mixed_mat_gpu as tz
 
 
 @pytest.fixture()
@@ -59,7 +60,7 @@ def test_mixed_dat_host_logic(mock):
 @pytest.mark.parametrize("extruded", [False, True])
 def test_mixed_mat_host_logic(mock, extruded):
     """Monolithic mixed matrices: dof-expanded block maps, MatBlock arguments, block lgmaps, mult on MixedDats."""
-    tj.test_mixed_mat_monolithic(mock, extruded)
+    tz.test_mixed_mat_monolithic(mock, extruded)
 
 
 @pytest.mark.parametrize("region", ["ALL", "ON_TOP", "ON_INTERIOR_FACETS"])
